@@ -1,0 +1,377 @@
+// core.cu — error plumbing + the small bandwidth/latency-bound kernels of the path:
+//   a10 EMA multi-tensor lerp, fused AdamW+EMA, a9 SoftTargetCrossEntropy fwd/bwd, a11 mixup_target,
+//   partial-sum reduction, fp32->bf16 cast.
+#include "common.cuh"
+#include <string.h>
+#include <mutex>
+
+namespace cnx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 148; }
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// ================================================================================================
+// a10: EMA.  One CTA per CNX_EMA_CHUNK elements; the CTA finds its tensor by binary search over
+// chunk_start.  ema <- fmaf(w, p - ema, ema): the |w|<0.5 branch of ATen's lerp (bit-exact).
+// 12 B/element of HBM traffic; 128-bit loads, 8 independent loads in flight per thread.
+// ================================================================================================
+template <typename Entry>
+__device__ __forceinline__ int find_tensor(const Entry* __restrict__ table, int n, int64_t chunk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (table[mid].chunk_start <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) ema_lerp_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
+                                                              float w) {
+  __shared__ cnx_ema_entry ent;
+  int64_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
+  __syncthreads();
+  float* __restrict__ e = (float*)ent.ema;
+  const float* __restrict__ p = (const float*)ent.param;
+  int64_t base = (chunk - ent.chunk_start) * (int64_t)CNX_EMA_CHUNK;
+  int64_t rem = ent.numel - base;
+  int n = rem < CNX_EMA_CHUNK ? (int)rem : CNX_EMA_CHUNK;
+  e += base;
+  p += base;
+  bool aligned = ((((uintptr_t)e) | ((uintptr_t)p)) & 15) == 0;
+  if (aligned && n == CNX_EMA_CHUNK) {
+    // 8192 elements / 256 threads = 8 float4 per thread, all loads issued before any use
+    float4 ev[8], pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = (i * 256 + threadIdx.x);
+      ev[i] = reinterpret_cast<const float4*>(e)[idx];
+      pv[i] = __ldg(reinterpret_cast<const float4*>(p) + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = (i * 256 + threadIdx.x);
+      float4 r;
+      r.x = fmaf(w, pv[i].x - ev[i].x, ev[i].x);
+      r.y = fmaf(w, pv[i].y - ev[i].y, ev[i].y);
+      r.z = fmaf(w, pv[i].z - ev[i].z, ev[i].z);
+      r.w = fmaf(w, pv[i].w - ev[i].w, ev[i].w);
+      reinterpret_cast<float4*>(e)[idx] = r;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      float ev = e[i];
+      e[i] = fmaf(w, p[i] - ev, ev);
+    }
+  }
+}
+
+// Fused AdamW (+EMA).  torch.optim.AdamW (single-tensor formulation, torch/optim/adam.py):
+//   p *= 1 - lr*wd ; m = lerp(m, g, 1-b1) ; v = b2*v + (1-b2)*g*g ;
+//   denom = sqrt(v)/bc2_sqrt + eps ; p += -(lr/bc1) * m/denom ; then ema = lerp(ema, p, w).
+__global__ void __launch_bounds__(256) adamw_ema_multi_kernel(const cnx_adamw_entry* __restrict__ table, int n_tensors,
+                                                               float lr, float beta1, float beta2, float eps, float wd,
+                                                               float bc1, float bc2_sqrt, float ema_w) {
+  __shared__ cnx_adamw_entry ent;
+  int64_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
+  __syncthreads();
+  int64_t base = (chunk - ent.chunk_start) * (int64_t)CNX_EMA_CHUNK;
+  int64_t rem = ent.numel - base;
+  int n = rem < CNX_EMA_CHUNK ? (int)rem : CNX_EMA_CHUNK;
+  float* __restrict__ p = (float*)ent.param + base;
+  const float* __restrict__ g = (const float*)ent.grad + base;
+  float* __restrict__ m = (float*)ent.exp_avg + base;
+  float* __restrict__ v = (float*)ent.exp_avg_sq + base;
+  float* __restrict__ e = ent.ema ? (float*)ent.ema + base : nullptr;
+  const float step_size = lr / bc1;
+  const float decay = 1.0f - lr * wd;
+  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    float pi = p[i], gi = g[i], mi = m[i], vi = v[i];
+    pi = pi * decay;
+    mi = fmaf(omb1, gi - mi, mi);
+    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(omb2, gi), gi));
+    float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (e) { float ei = e[i]; e[i] = fmaf(ema_w, pi - ei, ei); }
+  }
+}
+
+// ================================================================================================
+// a9: SoftTargetCrossEntropy.  One CTA per row (K up to a few thousand): two passes over the row held
+// in registers/L1 (max, then sum-exp and sum t*x), deterministic final mean by the last CTA to finish.
+// ================================================================================================
+template <typename TX, int THREADS>
+__global__ void __launch_bounds__(THREADS) soft_ce_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ t,
+                                                              int64_t B, int64_t K, float* __restrict__ loss,
+                                                              float* __restrict__ lse_out, float* __restrict__ row_loss,
+                                                              unsigned int* __restrict__ counter) {
+  __shared__ float red[THREADS / 32];
+  __shared__ float bcast;
+  __shared__ bool is_last;
+  const int64_t row = blockIdx.x;
+  const TX* xr = x + row * K;
+  const float* tr = t + row * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  float m = -INFINITY;
+  for (int64_t k = threadIdx.x; k < K; k += THREADS) m = fmaxf(m, to_f32(xr[k]));
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = red[0];
+    for (int i = 1; i < THREADS / 32; ++i) mm = fmaxf(mm, red[i]);
+    bcast = mm;
+  }
+  __syncthreads();
+  m = bcast;
+  __syncthreads();
+
+  float se = 0.f;
+  for (int64_t k = threadIdx.x; k < K; k += THREADS) se += expf(to_f32(xr[k]) - m);
+  se = warp_sum(se);
+  if (lane == 0) red[warp] = se;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < THREADS / 32; ++i) s += red[i];
+    bcast = m + logf(s);
+  }
+  __syncthreads();
+  const float lse = bcast;
+  __syncthreads();
+
+  // sum_k -t * (x - lse): same per-element form as -target * log_softmax(x)
+  float acc = 0.f;
+  for (int64_t k = threadIdx.x; k < K; k += THREADS) acc += -tr[k] * (to_f32(xr[k]) - lse);
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < THREADS / 32; ++i) s += red[i];
+    row_loss[row] = s;
+    lse_out[row] = lse;
+    __threadfence();
+    unsigned int done = atomicAdd(counter, 1u);
+    is_last = (done == (unsigned int)(B - 1));
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    // fixed-order tree: each thread strides, then warp/CTA reduce (deterministic for a given B)
+    float s = 0.f;
+    for (int64_t r = threadIdx.x; r < B; r += THREADS) s += __ldcg(row_loss + r);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < THREADS / 32; ++i) tot += red[i];
+      loss[0] = tot / (float)B;
+      *counter = 0u;   // leave the scratch counter ready for the next call
+    }
+  }
+}
+
+template <typename TX, typename TD>
+__global__ void __launch_bounds__(256) soft_ce_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ t,
+                                                          const float* __restrict__ lse, const float* __restrict__ dloss,
+                                                          int64_t B, int64_t K, TD* __restrict__ dx) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int64_t row = blockIdx.x;
+  const TX* xr = x + row * K;
+  const float* tr = t + row * K;
+  TD* dr = dx + row * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float st = 0.f;
+  for (int64_t k = threadIdx.x; k < K; k += 256) st += tr[k];
+  st = warp_sum(st);
+  if (lane == 0) red[warp] = st;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    bcast = s;
+  }
+  __syncthreads();
+  st = bcast;
+  const float l = lse[row];
+  const float scale = dloss[0] / (float)B;
+  for (int64_t k = threadIdx.x; k < K; k += 256) {
+    float p = expf(to_f32(xr[k]) - l);
+    dr[k] = from_f32<TD>((p * st - tr[k]) * scale);
+  }
+}
+
+// ================================================================================================
+// a11: mixup_target.  y(t)[k] = (k == t) ? on : off, out = fl(fl(y1*lam) + fl(y2*oml)).
+// __fmul_rn/__fadd_rn keep the three roundings separate (no FMA contraction), as three ATen kernels do.
+// ================================================================================================
+__global__ void __launch_bounds__(256) mixup_target_kernel(const int64_t* __restrict__ target, int64_t B, int64_t K,
+                                                           float on, float off, float lam, float oml,
+                                                           float* __restrict__ out) {
+  int64_t total = B * K;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    int64_t b = i / K, k = i - b * K;
+    float y1 = (target[b] == k) ? on : off;
+    float y2 = (target[B - 1 - b] == k) ? on : off;
+    out[i] = __fadd_rn(__fmul_rn(y1, lam), __fmul_rn(y2, oml));
+  }
+}
+
+// ================================================================================================
+// deterministic reduction of per-CTA partial sums: out[j] = scale * sum_p partial[p, j]
+// ================================================================================================
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int P, int64_t L,
+                                                              float scale, int accumulate, float* __restrict__ out) {
+  int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= L) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 4 <= P; p += 4) {
+    s0 += partial[(int64_t)(p + 0) * L + j];
+    s1 += partial[(int64_t)(p + 1) * L + j];
+    s2 += partial[(int64_t)(p + 2) * L + j];
+    s3 += partial[(int64_t)(p + 3) * L + j];
+  }
+  for (; p < P; ++p) s0 += partial[(int64_t)p * L + j];
+  float s = ((s0 + s1) + (s2 + s3)) * scale;
+  out[j] = accumulate ? out[j] + s : s;
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, int64_t n, bf16* __restrict__ out) {
+  int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  int64_t stride = (int64_t)gridDim.x * 256 * 4;
+  bool aligned = ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 7) == 0);
+  for (; i4 < n; i4 += stride) {
+    if (aligned && i4 + 4 <= n) {
+      float v[4];
+      load4(in + i4, v);
+      store4(out + i4, v);
+    } else {
+      for (int64_t i = i4; i < n && i < i4 + 4; ++i) out[i] = __float2bfloat16_rn(in[i]);
+    }
+  }
+}
+
+}  // namespace cnx
+
+using namespace cnx;
+
+extern "C" {
+
+int cnx_version(void) { return CNX_VERSION; }
+const char* cnx_last_error_string(void) { return cnx::g_err; }
+int cnx_sm_count(void) { return cnx::sm_count(); }
+
+int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float w, void* stream) {
+  CNX_REQUIRE(table_dev && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "ema_lerp_multi: empty table");
+  CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "ema_lerp_multi: too many chunks");
+  ema_lerp_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_ema_entry*)table_dev,
+                                                                                 n_tensors, w);
+  return check_launch("ema_lerp_multi");
+}
+
+int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float bias_correction1,
+                        float bias_correction2_sqrt, float ema_w, void* stream) {
+  CNX_REQUIRE(table_dev && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "adamw_ema_multi: empty table");
+  CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "adamw_ema_multi: too many chunks");
+  adamw_ema_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>(
+      (const cnx_adamw_entry*)table_dev, n_tensors, lr, beta1, beta2, eps, weight_decay, bias_correction1,
+      bias_correction2_sqrt, ema_w);
+  return check_launch("adamw_ema_multi");
+}
+
+int cnx_soft_target_ce_fwd(const void* x, int x_dtype, const float* t, int64_t B, int64_t K, float* loss,
+                           float* lse, float* row_loss, unsigned int* counter, void* stream) {
+  CNX_REQUIRE(x && t && loss && lse && row_loss && counter, CNX_E_BADARG, "soft_target_ce_fwd: null pointer");
+  CNX_REQUIRE(B > 0 && K > 0 && dtype_ok(x_dtype), CNX_E_BADARG, "soft_target_ce_fwd: bad shape/dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K <= 64) {
+    if (x_dtype == CNX_F32) soft_ce_fwd_kernel<float, 32><<<(unsigned)B, 32, 0, s>>>((const float*)x, t, B, K, loss, lse, row_loss, counter);
+    else soft_ce_fwd_kernel<bf16, 32><<<(unsigned)B, 32, 0, s>>>((const bf16*)x, t, B, K, loss, lse, row_loss, counter);
+  } else {
+    if (x_dtype == CNX_F32) soft_ce_fwd_kernel<float, 256><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, B, K, loss, lse, row_loss, counter);
+    else soft_ce_fwd_kernel<bf16, 256><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, B, K, loss, lse, row_loss, counter);
+  }
+  return check_launch("soft_target_ce_fwd");
+}
+
+int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, const float* lse, const float* dloss,
+                           int64_t B, int64_t K, void* dx, int dx_dtype, void* stream) {
+  CNX_REQUIRE(x && t && lse && dloss && dx, CNX_E_BADARG, "soft_target_ce_bwd: null pointer");
+  CNX_REQUIRE(B > 0 && K > 0 && dtype_ok(x_dtype) && dtype_ok(dx_dtype), CNX_E_BADARG, "soft_target_ce_bwd: bad shape/dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == CNX_F32 && dx_dtype == CNX_F32) soft_ce_bwd_kernel<float, float><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, lse, dloss, B, K, (float*)dx);
+  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_BF16) soft_ce_bwd_kernel<bf16, bf16><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, lse, dloss, B, K, (bf16*)dx);
+  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_F32) soft_ce_bwd_kernel<bf16, float><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, lse, dloss, B, K, (float*)dx);
+  else soft_ce_bwd_kernel<float, bf16><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, lse, dloss, B, K, (bf16*)dx);
+  return check_launch("soft_target_ce_bwd");
+}
+
+int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, double smoothing, float* out,
+                     void* stream) {
+  CNX_REQUIRE(target && out && B > 0 && K > 0, CNX_E_BADARG, "mixup_target: bad argument");
+  // timm mixup_target: python-double arithmetic on the host, rounded to fp32 when it meets the tensor
+  double off = smoothing / (double)K;
+  double on = 1.0 - smoothing + off;
+  double oml = 1.0 - lam;
+  int64_t total = B * K;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (grid > 148u * 16u) grid = 148u * 16u;
+  mixup_target_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(target, B, K, (float)on, (float)off, (float)lam,
+                                                               (float)oml, out);
+  return check_launch("mixup_target");
+}
+
+int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
+                        void* stream) {
+  CNX_REQUIRE(partial && out && P > 0 && L > 0, CNX_E_BADARG, "reduce_partials: bad argument");
+  reduce_partials_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, P, L, scale,
+                                                                                         accumulate, out);
+  return check_launch("reduce_partials");
+}
+
+int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
+  CNX_REQUIRE(in && out && n > 0, CNX_E_BADARG, "cast_f32_to_bf16: bad argument");
+  int64_t blocks = (n / 4 + 255) / 256 + 1;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, (bf16*)out);
+  return check_launch("cast_f32_to_bf16");
+}
+
+}  // extern "C"

@@ -1,0 +1,82 @@
+// epilogue.cuh — the fused GEMM epilogues of the Block MLP, shared by the tcgen05 kernel (gemm_tc.cu)
+// and the fp32 CUDA-core kernel (gemm_simt.cu).  An epilogue consumes 8 consecutive accumulator columns
+// of one output row and performs all the elementwise work the reference does in separate ATen kernels
+// (convnext.py:48-55): bias, exact GELU, layer-scale, drop-path scale, residual add, GELU'.
+#pragma once
+#include "common.cuh"
+
+namespace cnx {
+
+enum {
+  EPI_PLAIN = 0,        // out0 = acc (+bias)                                  [out dtype = TOUT]
+  EPI_BIAS_GELU = 1,    // h = acc + b1 -> out0 (optional), g = GELU(h) -> out1 [act dtype]
+  EPI_SCALE_RES = 2,    // out0 = shortcut + dp[row/rps] * gamma[n] * (acc + b2[n])  [stream dtype]
+  EPI_DGELU = 3         // out0 = acc * GELU'(h[m,n])                           [act dtype], aux = h
+};
+
+struct EpiParams {
+  const float* bias;        // [N] or null
+  const float* gamma;       // [N] or null
+  const float* dp;          // [num_samples] or null
+  int64_t rows_per_sample;  // H*W
+  const void* aux;          // shortcut (TOUT) for SCALE_RES, h (TOUT) for DGELU
+  void* out0;
+  void* out1;
+  int64_t ld;               // row stride of out0/out1/aux (= N)
+};
+
+// acc[8] -> global, columns n..n+7 of row m (n % 8 == 0, N % 8 == 0 so vectors never straddle a row end)
+template <int KIND, typename TOUT>
+__device__ __forceinline__ void epilogue_store8(const EpiParams& p, int64_t m, int64_t n, float (&acc)[8]) {
+  const int64_t off = m * p.ld + n;
+  if (KIND == EPI_PLAIN) {
+    if (p.bias) {
+      float b[8];
+      load8(p.bias + n, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += b[i];
+    }
+    store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
+  } else if (KIND == EPI_BIAS_GELU) {
+    float b[8], g[8];
+    load8(p.bias + n, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // h is rounded to the activation dtype before GELU, as autocast's Linear output is
+      acc[i] = round_to<TOUT>(acc[i] + b[i]);
+      g[i] = gelu_erf(acc[i]);
+    }
+    if (p.out0) store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
+    store8(reinterpret_cast<TOUT*>(p.out1) + off, g);
+  } else if (KIND == EPI_SCALE_RES) {
+    float s = 1.0f;
+    if (p.dp) s = p.dp[m / p.rows_per_sample];
+    float b[8], gm[8], sc[8];
+    if (p.bias) load8(p.bias + n, b);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i] = 0.f;
+    }
+    if (p.gamma) load8(p.gamma + n, gm);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gm[i] = 1.f;
+    }
+    if (p.aux) load8(reinterpret_cast<const TOUT*>(p.aux) + off, sc);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = sc[i] + s * (gm[i] * (acc[i] + b[i]));
+    store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
+  } else {  // EPI_DGELU
+    float h[8];
+    load8(reinterpret_cast<const TOUT*>(p.aux) + off, h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= gelu_erf_grad(h[i]);
+    store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
+  }
+}
+
+}  // namespace cnx

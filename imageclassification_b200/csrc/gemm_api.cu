@@ -1,0 +1,108 @@
+// gemm_api.cu — extern "C" entry points of the MLP GEMMs: bf16 -> tcgen05 kernels (gemm_tc.cu),
+// fp32 (or CNX_GEMM_FORCE_SIMT) -> CUDA-core kernels (gemm_simt.cu).  There is no CPU path.
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace cnx {
+template <typename TIN, typename TOUT, int KIND>
+int gemm_tn_simt(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s);
+template <int KIND, typename TOUT>
+int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s);
+template <typename TIN>
+int gemm_wgrad_simt(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                    float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int64_t wgrad_workspace_bytes_simt(int64_t M, int64_t N1, int64_t N2);
+int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2);
+}  // namespace cnx
+
+using namespace cnx;
+
+#define CNX_GEMM_ARGS_OK(name)                                                                        \
+  CNX_REQUIRE(M > 0 && N > 0 && K > 0, CNX_E_BADARG, name ": bad shape");                             \
+  CNX_REQUIRE(dtype_ok(dtype), CNX_E_BADARG, name ": bad dtype");                                     \
+  CNX_REQUIRE(N % 8 == 0, CNX_E_SHAPE, name ": N=%lld must be a multiple of 8", (long long)N)
+
+extern "C" {
+
+int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64_t M, int64_t N, int64_t K,
+                           void* h_out, void* g_out, int dtype, int flags, void* stream) {
+  CNX_REQUIRE(A && W1 && b1 && g_out, CNX_E_BADARG, "gemm_bias_gelu_fwd: null pointer");
+  CNX_GEMM_ARGS_OK("gemm_bias_gelu_fwd");
+  EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, h_out, g_out, N};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNX_F32) return gemm_tn_simt<float, float, EPI_BIAS_GELU>(A, W1, M, N, K, ep, s);
+  if (flags & CNX_GEMM_FORCE_SIMT) return gemm_tn_simt<bf16, bf16, EPI_BIAS_GELU>(A, W1, M, N, K, ep, s);
+  return gemm_tn_tc<EPI_BIAS_GELU, bf16>(A, W1, M, N, K, ep, s);
+}
+
+int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float* b2, const float* gamma,
+                                     const float* dp, int64_t rows_per_sample, const void* shortcut, void* out,
+                                     int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,
+                                     void* stream) {
+  CNX_REQUIRE(A && W2 && out, CNX_E_BADARG, "gemm_bias_scale_residual_fwd: null pointer");
+  CNX_GEMM_ARGS_OK("gemm_bias_scale_residual_fwd");
+  CNX_REQUIRE(dtype_ok(stream_dtype) && rows_per_sample > 0, CNX_E_BADARG, "gemm_bias_scale_residual_fwd: bad argument");
+  EpiParams ep = {b2, gamma, dp, rows_per_sample, shortcut, out, nullptr, N};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNX_F32) {
+    CNX_REQUIRE(stream_dtype == CNX_F32, CNX_E_BADARG, "fp32 GEMM needs an fp32 residual stream");
+    return gemm_tn_simt<float, float, EPI_SCALE_RES>(A, W2, M, N, K, ep, s);
+  }
+  if (flags & CNX_GEMM_FORCE_SIMT) {
+    if (stream_dtype == CNX_F32) return gemm_tn_simt<bf16, float, EPI_SCALE_RES>(A, W2, M, N, K, ep, s);
+    return gemm_tn_simt<bf16, bf16, EPI_SCALE_RES>(A, W2, M, N, K, ep, s);
+  }
+  if (stream_dtype == CNX_F32) return gemm_tn_tc<EPI_SCALE_RES, float>(A, W2, M, N, K, ep, s);
+  return gemm_tn_tc<EPI_SCALE_RES, bf16>(A, W2, M, N, K, ep, s);
+}
+
+int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* h, void* dh, int64_t M, int64_t N,
+                            int64_t K, int dtype, int flags, void* stream) {
+  CNX_REQUIRE(dz && Bt && h && dh, CNX_E_BADARG, "gemm_dgrad_gelu_bwd: null pointer");
+  CNX_GEMM_ARGS_OK("gemm_dgrad_gelu_bwd");
+  EpiParams ep = {nullptr, nullptr, nullptr, 1, h, dh, nullptr, N};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNX_F32) return gemm_tn_simt<float, float, EPI_DGELU>(dz, Bt, M, N, K, ep, s);
+  if (flags & CNX_GEMM_FORCE_SIMT) return gemm_tn_simt<bf16, bf16, EPI_DGELU>(dz, Bt, M, N, K, ep, s);
+  return gemm_tn_tc<EPI_DGELU, bf16>(dz, Bt, M, N, K, ep, s);
+}
+
+int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,
+                   int64_t N, int64_t K, int dtype, int flags, void* stream) {
+  CNX_REQUIRE(A && B && out, CNX_E_BADARG, "gemm_plain: null pointer");
+  CNX_GEMM_ARGS_OK("gemm_plain");
+  CNX_REQUIRE(dtype_ok(out_dtype), CNX_E_BADARG, "gemm_plain: bad out dtype");
+  EpiParams ep = {bias, nullptr, nullptr, 1, nullptr, out, nullptr, N};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNX_F32) {
+    CNX_REQUIRE(out_dtype == CNX_F32, CNX_E_BADARG, "gemm_plain: fp32 operands need an fp32 output");
+    return gemm_tn_simt<float, float, EPI_PLAIN>(A, B, M, N, K, ep, s);
+  }
+  if (flags & CNX_GEMM_FORCE_SIMT) {
+    if (out_dtype == CNX_F32) return gemm_tn_simt<bf16, float, EPI_PLAIN>(A, B, M, N, K, ep, s);
+    return gemm_tn_simt<bf16, bf16, EPI_PLAIN>(A, B, M, N, K, ep, s);
+  }
+  if (out_dtype == CNX_F32) return gemm_tn_tc<EPI_PLAIN, float>(A, B, M, N, K, ep, s);
+  return gemm_tn_tc<EPI_PLAIN, bf16>(A, B, M, N, K, ep, s);
+}
+
+int64_t cnx_gemm_wgrad_workspace_bytes(int64_t M, int64_t N1, int64_t N2, int dtype, int flags) {
+  if (M <= 0 || N1 <= 0 || N2 <= 0) return 0;
+  if (dtype == CNX_F32 || (flags & CNX_GEMM_FORCE_SIMT)) return wgrad_workspace_bytes_simt(M, N1, N2);
+  return wgrad_workspace_bytes_tc(M, N1, N2);
+}
+
+int cnx_gemm_wgrad(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                   float* colsum_x, void* workspace, int64_t workspace_bytes, int dtype, int flags, void* stream) {
+  CNX_REQUIRE(X && Y && out && workspace, CNX_E_BADARG, "gemm_wgrad: null pointer");
+  CNX_REQUIRE(M > 0 && N1 > 0 && N2 > 0 && dtype_ok(dtype), CNX_E_BADARG, "gemm_wgrad: bad shape/dtype");
+  CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad: N1, N2 must be multiples of 8");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNX_F32) return gemm_wgrad_simt<float>(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
+  if (flags & CNX_GEMM_FORCE_SIMT) return gemm_wgrad_simt<bf16>(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
+  return gemm_wgrad_tc(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
+}
+
+}  // extern "C"

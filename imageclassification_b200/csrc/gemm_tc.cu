@@ -1,0 +1,560 @@
+// gemm_tc.cu — a3/a5 and their four backward GEMMs on the 5th-gen tensor cores (sm_100a):
+// TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (one elected thread,
+// kind::f16, bf16 operands, fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue (epilogue.cuh).
+//
+//   gemm_tn_tc_kernel    acc[M,N] = A[M,K].B[N,K]^T, both operands K-major (nn.Linear layout).
+//                        Persistent (one CTA per SM, static round-robin tiles, N fastest so the A tile
+//                        is shared through L2), STAGES-deep smem ring, TWO TMEM accumulator buffers so
+//                        the epilogue of tile i overlaps the MMAs of tile i+1.  Warp roles: 0 = TMA
+//                        producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (8 warps: the
+//                        exact-erf GELU epilogue at K=C=96 costs more issue slots than the MMAs).
+//   gemm_wgrad_tc_kernel out[N1,N2] = X[M,N1]^T.Y[M,N2]: both operands MN-major straight from the
+//                        row-major activations (no transposes), split-K over M with fp32 partials
+//                        (deterministic), bias gradient = column sums of X computed BY THE TENSOR CORE
+//                        with a constant all-ones B tile (one extra N=16 MMA per k-step).
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor"
+// tables (bit positions cross-checked against cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS tree).
+#include "common.cuh"
+#include "epilogue.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace cnx {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // 64 bf16 = 128 B = one swizzle row
+constexpr int kEpiWarps = 8;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors -------------------------------------------------------------------------------
+// shared-memory matrix descriptor: [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
+// [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), majors (15, 16),
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct TnCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int EPI_COLS = BN / 2;                              // columns per epilogue warp
+  static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ================================================================================================
+template <int BN, int KIND, typename TOUT>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int64_t N,
+                  int64_t K, EpiParams ep) {
+  typedef TnCfg<BN> Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * Cfg::A_BYTES;
+  const uint32_t bars = sB + STAGES * Cfg::B_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int nkb = (int)((K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int s = 0; uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), kb * BK, (int32_t)(mt * BM));
+          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, (int32_t)(nt * BN));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sA + s * Cfg::A_BYTES, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sB + s * Cfg::B_BYTES, 16, 1024);
+          int64_t krem = K - (int64_t)kb * BK;
+          const int kmma = krem >= BK ? BK / 16 : (int)((krem + 15) / 16);
+          for (int k = 0; k < kmma; ++k)
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(empty_bar(s));                 // smem slot free once these MMAs retire
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(as));                  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    // ===== epilogue: TMEM -> registers -> fused math -> global =====
+    const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) are this warp's
+    const int half = (warp - kFirstEpiWarp) >> 2;    // which half of the tile's columns
+    int as = 0; uint32_t aph = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int64_t m = mt * BM + quarter * 32 + lane;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < Cfg::EPI_COLS; c += Cfg::CHUNK) {
+        const int col = half * Cfg::EPI_COLS + c;
+        float v[Cfg::CHUNK];
+        if constexpr (Cfg::CHUNK == 32) tmem_ld32(t_row + col, *reinterpret_cast<float(*)[32]>(v));
+        else tmem_ld16(t_row + col, *reinterpret_cast<float(*)[16]>(v));
+        tmem_ld_wait();
+        const int64_t n = nt * BN + col;
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < Cfg::CHUNK; j += 8)
+            if (n + j < N) epilogue_store8<KIND, TOUT>(ep, m, n + j, *reinterpret_cast<float(*)[8]>(&v[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// wgrad: part[split][i][j] = sum_{m in split} X[m,i] * Y[m,j] ; cs_part[split][i] = sum_m X[m,i]
+// grid = (i_tiles * j_tiles, splits).  A = X^T and B = Y^T are both MN-major operands: the TMA box is
+// [64 m-rows][64 contiguous channels] (128 B rows, 128B swizzle), two boxes per operand per stage.
+// ================================================================================================
+template <int BN> struct WgCfg {
+  static constexpr int A_BYTES = 2 * 64 * BK * 2;      // two 64-wide boxes
+  static constexpr int B_BYTES = 2 * 64 * BK * 2;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 256;                // BN (<=128) accumulator + 16 colsum columns at 128
+  static constexpr int CS_COL = 128;
+  static constexpr int EPI_COLS = BN / 2;
+  static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
+  static constexpr int ONES_BYTES = 2048;
+  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + ONES_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, int64_t Mtot,
+                     int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part) {
+  typedef WgCfg<BN> Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * Cfg::A_BYTES;
+  const uint32_t sOnes = sB + STAGES * Cfg::B_BYTES;
+  const uint32_t bars = sOnes + Cfg::ONES_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t j_tiles = (N2 + BN - 1) / BN;
+  const int64_t it = blockIdx.x / j_tiles, jt = blockIdx.x - it * j_tiles;
+  const int split = blockIdx.y;
+  const int kb_total = (int)((Mtot + BK - 1) / BK);
+  const int kb0 = split * kb_per_split;
+  int kb1 = kb0 + kb_per_split;
+  if (kb1 > kb_total) kb1 = kb_total;
+  const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+  const bool do_colsum = (cs_part != nullptr) && (jt == 0);
+
+  // constant all-ones B tile for the bias-gradient MMA (any layout of ones is ones)
+  {
+    uint8_t* gen = smem_raw + (sOnes - smem_u32(smem_raw));
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(gen)[i] = 0x3F803F80u;
+    fence_proxy_async();     // generic-proxy writes must be visible to the tensor core's async proxy
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int32_t mrow = (kb0 + kb) * BK;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
+        tma_load_2d(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), (int32_t)(it * BM), mrow);
+        tma_load_2d(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), (int32_t)(it * BM + 64), mrow);
+        tma_load_2d(sB + s * Cfg::B_BYTES, &tmY, full_bar(s), (int32_t)(jt * BN), mrow);
+        tma_load_2d(sB + s * Cfg::B_BYTES + 8192, &tmY, full_bar(s), (int32_t)(jt * BN + 64), mrow);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+      constexpr uint32_t idesc_ones = make_idesc(BM, 16, 1, 1);
+      const uint64_t odesc = make_smem_desc(sOnes, 8192, 1024);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        // MN-major SW128: 64-channel atoms are LBO = 8192 B apart (one TMA box), 8-row k-groups SBO = 1024 B
+        const uint64_t adesc = make_smem_desc(sA + s * Cfg::A_BYTES, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(sB + s * Cfg::B_BYTES, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // one UMMA_K = 16 rows = two 8-row groups = 2048 B further into the tile
+          umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+          if (do_colsum) umma_f16(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
+        }
+        umma_commit(empty_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    const int quarter = warp & 3;
+    const int half = (warp - kFirstEpiWarp) >> 2;
+    const int64_t i = it * BM + quarter * 32 + lane;
+    float* po = part + (int64_t)split * N1 * N2;
+    if (nkb > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < Cfg::EPI_COLS; c += Cfg::CHUNK) {
+      const int col = half * Cfg::EPI_COLS + c;
+      float v[Cfg::CHUNK];
+      if (nkb > 0) {
+        if constexpr (Cfg::CHUNK == 32) tmem_ld32(t_row + col, *reinterpret_cast<float(*)[32]>(v));
+        else tmem_ld16(t_row + col, *reinterpret_cast<float(*)[16]>(v));
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < Cfg::CHUNK; ++j) v[j] = 0.f;
+      }
+      const int64_t jj = jt * BN + col;
+      if (i < N1) {
+#pragma unroll
+        for (int j = 0; j < Cfg::CHUNK; j += 8)
+          if (jj + j < N2) store8(po + i * N2 + jj + j, *reinterpret_cast<float(*)[8]>(&v[j]));
+      }
+    }
+    if (do_colsum && half == 0) {
+      float v[16];
+      if (nkb > 0) {
+        tmem_ld16(t_row + Cfg::CS_COL, v);
+        tmem_ld_wait();
+      } else {
+        v[0] = 0.f;
+      }
+      if (i < N1) cs_part[(int64_t)split * N1 + i] = v[0];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols]; box = [box_rows][64 cols], 128-byte swizzle, OOB -> zeros
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  CNX_REQUIRE(enc != nullptr, CNX_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  CNX_REQUIRE((((uintptr_t)ptr) & 15) == 0, CNX_E_SHAPE, "GEMM operand must be 16-byte aligned");
+  CNX_REQUIRE(cols % 8 == 0, CNX_E_SHAPE, "GEMM operand inner dimension %lld must be a multiple of 8", (long long)cols);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CNX_REQUIRE(r == CUDA_SUCCESS, CNX_E_DRIVER, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d",
+              (int)r, (long long)rows, (long long)cols, box_rows);
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%d): %s", bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+template <int BN, int KIND, typename TOUT>
+static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
+  if (int rc = make_map(&tmB, B, N, K, BN)) return rc;
+  auto k = gemm_tn_tc_kernel<BN, KIND, TOUT>;
+  if (int rc = set_smem(k, TnCfg<BN>::SMEM)) return rc;
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int64_t grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  k<<<(unsigned)grid, kThreads, TnCfg<BN>::SMEM, s>>>(tmA, tmB, M, N, K, ep);
+  return check_launch("gemm_tn_tc");
+}
+
+}  // namespace tc
+
+template <int KIND, typename TOUT>
+int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  CNX_REQUIRE(N % 8 == 0 && K % 8 == 0, CNX_E_SHAPE, "gemm_tc: N=%lld and K=%lld must be multiples of 8", (long long)N,
+              (long long)K);
+  if (N % 128 == 0) return tc::launch_tn<128, KIND, TOUT>(A, B, M, N, K, ep, s);
+  if (N % 96 == 0) return tc::launch_tn<96, KIND, TOUT>(A, B, M, N, K, ep, s);
+  if (N % 64 == 0) return tc::launch_tn<64, KIND, TOUT>(A, B, M, N, K, ep, s);
+  return tc::launch_tn<128, KIND, TOUT>(A, B, M, N, K, ep, s);   // ragged N: TMA zero-fills, epilogue guards
+}
+
+#define CNX_INST(KIND, TOUT) \
+  template int gemm_tn_tc<KIND, TOUT>(const void*, const void*, int64_t, int64_t, int64_t, const EpiParams&, cudaStream_t);
+CNX_INST(EPI_PLAIN, bf16)
+CNX_INST(EPI_PLAIN, float)
+CNX_INST(EPI_BIAS_GELU, bf16)
+CNX_INST(EPI_SCALE_RES, float)
+CNX_INST(EPI_SCALE_RES, bf16)
+CNX_INST(EPI_DGELU, bf16)
+#undef CNX_INST
+
+static int wgrad_splits_tc(int64_t M, int64_t N1, int64_t N2, int bn) {
+  int64_t tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + bn - 1) / bn);
+  int64_t want = ((int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t kb_total = (M + tc::BK - 1) / tc::BK;
+  int64_t maxs = (kb_total + 7) / 8;            // at least 8 k-blocks (512 rows) per split
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+static int wgrad_bn(int64_t N2) { return (N2 % 128 == 0) ? 128 : ((N2 % 96 == 0) ? 96 : 128); }
+
+int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2) {
+  return (int64_t)wgrad_splits_tc(M, N1, N2, wgrad_bn(N2)) * (N1 * N2 + N1) * 4;
+}
+
+int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+  CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_tc: N1, N2 must be multiples of 8");
+  const int bn = wgrad_bn(N2);
+  const int splits = wgrad_splits_tc(M, N1, N2, bn);
+  CNX_REQUIRE(workspace_bytes >= (int64_t)splits * (N1 * N2 + N1) * 4, CNX_E_WORKSPACE, "gemm_wgrad: workspace too small");
+  CUtensorMap tmX, tmY;
+  if (int rc = tc::make_map(&tmX, X, M, N1, tc::BK)) return rc;
+  if (int rc = tc::make_map(&tmY, Y, M, N2, tc::BK)) return rc;
+  const int64_t kb_total = (M + tc::BK - 1) / tc::BK;
+  const int kb_per_split = (int)((kb_total + splits - 1) / splits);
+  float* part = (float*)workspace;
+  float* cs_part = part + (int64_t)splits * N1 * N2;
+  const int64_t tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + bn - 1) / bn);
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  if (bn == 128) {
+    auto k = tc::gemm_wgrad_tc_kernel<128>;
+    if (int rc = tc::set_smem(k, tc::WgCfg<128>::SMEM)) return rc;
+    k<<<grid, tc::kThreads, tc::WgCfg<128>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+  } else {
+    auto k = tc::gemm_wgrad_tc_kernel<96>;
+    if (int rc = tc::set_smem(k, tc::WgCfg<96>::SMEM)) return rc;
+    k<<<grid, tc::kThreads, tc::WgCfg<96>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+  }
+  if (int rc = check_launch("gemm_wgrad_tc")) return rc;
+  if (int rc = cnx_reduce_partials(part, splits, N1 * N2, 1.0f, accumulate, out, s)) return rc;
+  if (colsum_x) return cnx_reduce_partials(cs_part, splits, N1, 1.0f, accumulate, colsum_x, s);
+  return 0;
+}
+
+}  // namespace cnx

@@ -1,0 +1,221 @@
+// ln.cu — a2: channels-last LayerNorm forward (stand-alone) and backward.
+// One warp per row; a row's C values sit in registers as NJ groups of 4 (lane + 32*j -th 4-vector), so
+// loads/stores are 8-byte (bf16) or 16-byte (fp32) and fully coalesced.  Statistics are two-pass fp32
+// (mean, then biased variance), reductions are warp shuffles.  Backward keeps the per-channel sums
+// (d ln_w, d ln_b) in warp-private shared-memory columns across all the rows a persistent CTA visits and
+// writes one partial row per CTA (deterministic; reduced by cnx_reduce_partials).
+#include "common.cuh"
+
+namespace cnx {
+
+constexpr int LN_WARPS = 8;
+
+template <typename TX, typename TO, int NJ>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ ln_w,
+                                                               const float* __restrict__ ln_b, float eps, int64_t M,
+                                                               int C, TO* __restrict__ out, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 2;
+  float lw[NJ][4], lb[NJ][4];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int v = lane + 32 * j;
+    if (v < nvec) { load4(ln_w + v * 4, lw[j]); load4(ln_b + v * 4, lb[j]); }
+  }
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += (int64_t)gridDim.x * LN_WARPS) {
+    const TX* xr = x + row * C;
+    float v[NJ][4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int vi = lane + 32 * j;
+      if (vi < nvec) {
+        load4(xr + vi * 4, v[j]);
+        s += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+      }
+    }
+    s = warp_sum(s);
+    const float mu = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int vi = lane + 32 * j;
+      if (vi < nvec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float d = v[j][k] - mu; q = fmaf(d, d, q); }
+      }
+    }
+    q = warp_sum(q);
+    const float rs = rsqrtf(q / (float)C + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = rs;
+    }
+    TO* orow = out + row * C;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int vi = lane + 32 * j;
+      if (vi < nvec) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = fmaf((v[j][k] - mu) * rs, lw[j][k], lb[j][k]);
+        store4(orow + vi * 4, o);
+      }
+    }
+  }
+}
+
+// dy = rstd * (g - mean_C(g) - xhat * mean_C(g * xhat)),  g = dxn * ln_w
+template <typename TG, typename TY, typename TD, int NJ>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restrict__ dxn, const TY* __restrict__ y,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ ln_w, int64_t M, int C,
+                                                               TD* __restrict__ dy, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = C >> 2;
+  float* my_dw = colacc + (size_t)warp * 2 * C;
+  float* my_db = my_dw + C;
+  for (int i = lane; i < 2 * C; i += 32) my_dw[i] = 0.f;
+  float lw[NJ][4];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    int v = lane + 32 * j;
+    if (v < nvec) load4(ln_w + v * 4, lw[j]);
+  }
+  __syncwarp();
+  const float invC = 1.0f / (float)C;
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += (int64_t)gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[NJ][4], xh[NJ][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int vi = lane + 32 * j;
+      if (vi < nvec) {
+        float d[4], yv[4];
+        load4(dxn + row * C + vi * 4, d);
+        load4(y + row * C + vi * 4, yv);
+        float4 aw = *reinterpret_cast<float4*>(my_dw + vi * 4);
+        float4 ab = *reinterpret_cast<float4*>(my_db + vi * 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xh[j][k] = (yv[k] - mu) * rs;
+          g[j][k] = d[k] * lw[j][k];
+          s1 += g[j][k];
+          s2 = fmaf(g[j][k], xh[j][k], s2);
+        }
+        aw.x = fmaf(d[0], xh[j][0], aw.x); aw.y = fmaf(d[1], xh[j][1], aw.y);
+        aw.z = fmaf(d[2], xh[j][2], aw.z); aw.w = fmaf(d[3], xh[j][3], aw.w);
+        ab.x += d[0]; ab.y += d[1]; ab.z += d[2]; ab.w += d[3];
+        *reinterpret_cast<float4*>(my_dw + vi * 4) = aw;
+        *reinterpret_cast<float4*>(my_db + vi * 4) = ab;
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      int vi = lane + 32 * j;
+      if (vi < nvec) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rs * (g[j][k] - s1 - xh[j][k] * s2);
+        store4(dy + row * C + vi * 4, o);
+      }
+    }
+  }
+  __syncthreads();
+  // sum the 8 warp-private columns in a fixed order -> partial[blockIdx.x][2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += LN_WARPS * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < LN_WARPS; ++wv) s += colacc[(size_t)wv * 2 * C + i];
+    partial[(int64_t)blockIdx.x * 2 * C + i] = s;
+  }
+}
+
+static inline int nj_for(int64_t C) { return (int)((C / 4 + 31) / 32); }
+
+#define CNX_NJ_SWITCH(nj, ...)                                   \
+  switch (nj) {                                                  \
+    case 1: { constexpr int NJ = 1; __VA_ARGS__; } break;        \
+    case 2: { constexpr int NJ = 2; __VA_ARGS__; } break;        \
+    case 3: { constexpr int NJ = 3; __VA_ARGS__; } break;        \
+    case 4: { constexpr int NJ = 4; __VA_ARGS__; } break;        \
+    case 5: case 6: { constexpr int NJ = 6; __VA_ARGS__; } break;   \
+    case 7: case 8: { constexpr int NJ = 8; __VA_ARGS__; } break;   \
+    case 9: case 10: case 11: case 12: { constexpr int NJ = 12; __VA_ARGS__; } break; \
+    case 13: case 14: case 15: case 16: { constexpr int NJ = 16; __VA_ARGS__; } break; \
+    default: set_error("layer_norm: C too large (max 2048)"); return CNX_E_SHAPE; \
+  }
+
+template <typename TX, typename TO>
+static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C, void* out,
+                         float* mean, float* rstd, cudaStream_t s) {
+  int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  CNX_NJ_SWITCH(nj_for(C), (ln_fwd_kernel<TX, TO, NJ><<<(unsigned)blocks, LN_WARPS * 32, 0, s>>>(
+                               (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, mean, rstd)));
+  return check_launch("ln_fwd");
+}
+
+template <typename TG, typename TY, typename TD>
+static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, const float* rstd, const float* ln_w,
+                         int64_t M, int64_t C, void* dy, float* partial, int P, cudaStream_t s) {
+  size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
+  CNX_NJ_SWITCH(nj_for(C), {
+    auto k = ln_bwd_kernel<TG, TY, TD, NJ>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,
+                                               partial);
+  });
+  return check_launch("ln_bwd");
+}
+
+}  // namespace cnx
+
+using namespace cnx;
+
+extern "C" {
+
+int cnx_ln_fwd(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
+               void* out, int out_dtype, float* mean, float* rstd, void* stream) {
+  CNX_REQUIRE(x && ln_w && ln_b && out, CNX_E_BADARG, "ln_fwd: null pointer");
+  CNX_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype) && M > 0 && C > 0, CNX_E_BADARG, "ln_fwd: bad shape/dtype");
+  CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "ln_fwd: C=%lld must be a multiple of 4", (long long)C);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == CNX_F32 && out_dtype == CNX_F32) return launch_ln_fwd<float, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
+  if (x_dtype == CNX_F32 && out_dtype == CNX_BF16) return launch_ln_fwd<float, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
+  if (x_dtype == CNX_BF16 && out_dtype == CNX_F32) return launch_ln_fwd<bf16, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
+  return launch_ln_fwd<bf16, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
+}
+
+int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+               const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
+               void* stream) {
+  CNX_REQUIRE(dxn && y && mean && rstd && ln_w && dy && partial && P > 0, CNX_E_BADARG, "ln_bwd: bad argument");
+  CNX_REQUIRE(dtype_ok(dxn_dtype) && dtype_ok(y_dtype) && dtype_ok(dy_dtype) && M > 0 && C > 0, CNX_E_BADARG,
+              "ln_bwd: bad shape/dtype");
+  CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "ln_bwd: C=%lld must be a multiple of 4", (long long)C);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int key = (dxn_dtype << 2) | (y_dtype << 1) | dy_dtype;
+  switch (key) {
+    case 0: return launch_ln_bwd<float, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 7: return launch_ln_bwd<bf16, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 1: return launch_ln_bwd<float, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 2: return launch_ln_bwd<float, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 3: return launch_ln_bwd<float, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 4: return launch_ln_bwd<bf16, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 5: return launch_ln_bwd<bf16, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    default: return launch_ln_bwd<bf16, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+  }
+}
+
+}  // extern "C"
