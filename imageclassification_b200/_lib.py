@@ -1,0 +1,111 @@
+"""ctypes binding of libcnx.so (include/cnx.h).
+
+This is the only place Python touches the C-ABI.  There is no CPU fallback: if the library is missing
+or a call fails, a RuntimeError is raised (the reference's engine.train_one_epoch would otherwise keep
+training on silently wrong numbers).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcnx.so")
+
+CNX_F32, CNX_BF16 = 0, 1
+CNX_GEMM_FORCE_SIMT = 1
+CNX_EMA_CHUNK = 8192
+
+_lib = None
+
+
+class EmaEntry(ctypes.Structure):
+    _fields_ = [("ema", c_void_p), ("param", c_void_p), ("numel", c_int64), ("chunk_start", c_int64)]
+
+
+class AdamWEntry(ctypes.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("ema", c_void_p), ("numel", c_int64), ("chunk_start", c_int64)]
+
+
+# name -> (restype, argtypes); must list every symbol include/cnx.h declares (tests/test_cabi.py checks)
+_P, _I, _L, _F, _D = c_void_p, c_int, c_int64, c_float, c_double
+SIGNATURES = {
+    "cnx_version": (c_int, []),
+    "cnx_last_error_string": (c_char_p, []),
+    "cnx_sm_count": (c_int, []),
+    "cnx_ema_lerp_multi": (c_int, [_P, _I, _L, _F, _P]),
+    "cnx_adamw_ema_multi": (c_int, [_P, _I, _L, _F, _F, _F, _F, _F, _F, _F, _F, _P]),
+    "cnx_soft_target_ce_fwd": (c_int, [_P, _I, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "cnx_soft_target_ce_bwd": (c_int, [_P, _I, _P, _P, _P, _L, _L, _P, _I, _P]),
+    "cnx_mixup_target": (c_int, [_P, _L, _L, _D, _D, _P, _P]),
+    "cnx_dwconv7_ln_fwd": (c_int, [_P, _I, _P, _P, _P, _P, _F, _L, _L, _L, _L, _P, _P, _I, _P, _P, _P]),
+    "cnx_ln_fwd": (c_int, [_P, _I, _P, _P, _F, _L, _L, _P, _I, _P, _P, _P]),
+    "cnx_ln_bwd": (c_int, [_P, _I, _P, _I, _P, _P, _P, _L, _L, _P, _I, _P, _I, _P]),
+    "cnx_reduce_partials": (c_int, [_P, _I, _L, _F, _I, _P, _P]),
+    "cnx_dwconv7_dgrad": (c_int, [_P, _I, _P, _P, _P, _I, _L, _L, _L, _L, _P]),
+    "cnx_dwconv7_wgrad": (c_int, [_P, _I, _P, _I, _L, _L, _L, _L, _P, _I, _P]),
+    "cnx_dwconv7_wgrad_finalize": (c_int, [_P, _I, _L, _I, _P, _P, _P]),
+    "cnx_gemm_bias_gelu_fwd": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _I, _I, _P]),
+    "cnx_gemm_bias_scale_residual_fwd": (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _L, _L, _L, _I, _I, _P]),
+    "cnx_gemm_dgrad_gelu_bwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _P]),
+    "cnx_gemm_plain": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _I, _I, _P]),
+    "cnx_gemm_wgrad_workspace_bytes": (c_int64, [_L, _L, _L, _I, _I]),
+    "cnx_gemm_wgrad": (c_int, [_P, _P, _L, _L, _L, _I, _P, _P, _P, _L, _I, _I, _P]),
+    "cnx_grad_prep": (c_int, [_P, _I, _P, _L, _L, _L, _P, _I, _P]),
+    "cnx_weight_prep": (c_int, [_P, _L, _L, _P, _I, _P, _I, _P]),
+    "cnx_layerscale_finalize": (c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
+    "cnx_cast_f32_to_bf16": (c_int, [_P, _L, _P, _P]),
+}
+
+
+def load():
+    """Load libcnx.so once; raise (never fall back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libcnx.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C imageclassification_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().cnx_last_error_string()
+        raise RuntimeError(f"libcnx {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d == torch.float32:
+        return CNX_F32
+    if d == torch.bfloat16:
+        return CNX_BF16
+    raise TypeError(f"libcnx supports float32 and bfloat16 tensors, got {d}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "imageclassification_b200 kernels run on CUDA (sm_100a) tensors only; got a tensor on "
+                f"{t.device}. There is no CPU fallback — use oracle/ for CPU reference numbers.")

@@ -1,0 +1,268 @@
+"""torch.autograd bindings of the libcnx kernels (one Function per reference op on the hot path).
+
+Every Function launches hand-written sm_100a kernels through the C-ABI on the caller's current CUDA
+stream; tensors (outputs, saved activations, scratch) are owned by PyTorch's caching allocator.
+Reference ops replaced:
+  block_forward        convnext.py:43-56 (Block.forward) == timm ConvNeXtBlock.forward
+  layer_norm_cl        convnext.py:175-176 (LayerNorm, channels_last)
+  soft_target_ce       timm SoftTargetCrossEntropy.forward (train.py:257)
+  mixup_target         timm mixup_target (engine.py:44)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+# Test-only switch: route the bf16 GEMMs through the CUDA-core kernel to cross-check the tcgen05 path.
+GEMM_FLAGS = 0
+
+
+def _act_dtype() -> torch.dtype:
+    """bf16 activations under torch.autocast('cuda', dtype=torch.bfloat16), fp32 otherwise."""
+    if torch.is_autocast_enabled("cuda"):
+        d = torch.get_autocast_dtype("cuda")
+        if d == torch.bfloat16:
+            return torch.bfloat16
+        raise NotImplementedError(
+            f"imageclassification_b200 implements the bf16 autocast path (BASELINE north_star); autocast dtype {d} "
+            "is not supported — use torch.autocast('cuda', dtype=torch.bfloat16)")
+    return torch.float32
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """logical NCHW tensor -> contiguous [N,H,W,C] tensor (a view when x is channels-last strided)."""
+    xl = x.permute(0, 2, 3, 1)
+    return xl if xl.is_contiguous() else xl.contiguous()
+
+
+def _num_partials() -> int:
+    return L.load().cnx_sm_count() * 2
+
+
+def _weight_prep(w: torch.Tensor, mode: int, row_scale, out_dtype) -> torch.Tensor:
+    lib = L.load()
+    R, Cc = w.shape
+    out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
+    L.check(lib.cnx_weight_prep(L.ptr(w), R, Cc, L.ptr(row_scale), mode, L.ptr(out), L.dt(out_dtype), L.stream()),
+            "weight_prep")
+    return out
+
+
+def _wgrad(X, Y, M, N1, N2, want_colsum: bool):
+    lib = L.load()
+    d = L.dt(X)
+    ws_bytes = lib.cnx_gemm_wgrad_workspace_bytes(M, N1, N2, d, GEMM_FLAGS)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=X.device)
+    out = torch.empty((N1, N2), dtype=torch.float32, device=X.device)
+    cs = torch.empty((N1,), dtype=torch.float32, device=X.device) if want_colsum else None
+    L.check(lib.cnx_gemm_wgrad(L.ptr(X), L.ptr(Y), M, N1, N2, 0, L.ptr(out), L.ptr(cs), L.ptr(ws), ws_bytes, d,
+                               GEMM_FLAGS, L.stream()), "gemm_wgrad")
+    return out, cs
+
+
+class _BlockFn(torch.autograd.Function):
+    """dwconv7 -> LN -> fc1 -> GELU -> fc2 -> gamma -> drop_path -> + shortcut, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps, act_dtype):
+        lib = L.load()
+        L.require_cuda(x, conv_w, w1, w2)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"ConvNeXtBlock: unsupported residual-stream dtype {x.dtype}")
+        N, C, H, W = x.shape
+        xl = _nhwc(x.detach())
+        M = N * H * W
+        dev = x.device
+        sd, ad = L.dt(xl), L.dt(act_dtype)
+        st = L.stream()
+        y = torch.empty((M, C), dtype=act_dtype, device=dev)
+        xn = torch.empty((M, C), dtype=act_dtype, device=dev)
+        mean = torch.empty((M,), dtype=torch.float32, device=dev)
+        rstd = torch.empty((M,), dtype=torch.float32, device=dev)
+        L.check(lib.cnx_dwconv7_ln_fwd(L.ptr(xl), sd, L.ptr(conv_w), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps,
+                                       N, H, W, C, L.ptr(y), L.ptr(xn), ad, L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd")
+        if act_dtype == torch.float32:
+            w1a, w2a = w1, w2
+        else:
+            w1a = _weight_prep(w1, 0, None, act_dtype)
+            w2a = _weight_prep(w2, 0, None, act_dtype)
+        C4 = w1.shape[0]
+        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:10])
+        h = torch.empty((M, C4), dtype=act_dtype, device=dev) if need_grad else None
+        g = torch.empty((M, C4), dtype=act_dtype, device=dev)
+        L.check(lib.cnx_gemm_bias_gelu_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), M, C4, C, L.ptr(h), L.ptr(g), ad,
+                                           GEMM_FLAGS, st), "gemm_bias_gelu_fwd")
+        out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+        L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g), L.ptr(w2a), L.ptr(b2), L.ptr(gamma), L.ptr(dp), H * W,
+                                                     L.ptr(xl), L.ptr(out), sd, M, C, C4, ad, GEMM_FLAGS, st),
+                "gemm_bias_scale_residual_fwd")
+        if need_grad:
+            ctx.save_for_backward(xl, y, xn, mean, rstd, h, g, conv_w, ln_w, w1, w2, b2, gamma, dp)
+            ctx.shape = (N, C, H, W)
+            ctx.act_dtype = act_dtype
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        xl, y, xn, mean, rstd, h, g, conv_w, ln_w, w1, w2, b2, gamma, dp = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        act_dtype = ctx.act_dtype
+        M, C4 = N * H * W, w1.shape[0]
+        dev = xl.device
+        sd, ad = L.dt(xl), L.dt(act_dtype)
+        st = L.stream()
+        doutl = _nhwc(dout)
+        if doutl.dtype != xl.dtype:
+            doutl = doutl.to(xl.dtype)
+        # 1. dz = act(dp * dout): the operand copy of the incoming gradient (drop-path folded in once)
+        if dp is None and act_dtype == xl.dtype:
+            dz = doutl.reshape(M, C)
+        else:
+            dz = torch.empty((M, C), dtype=act_dtype, device=dev)
+            L.check(lib.cnx_grad_prep(L.ptr(doutl), sd, L.ptr(dp), H * W, M, C, L.ptr(dz), ad, st), "grad_prep")
+        # 2. dh = (dz . (gamma*W2)) * GELU'(h)
+        w2gt = _weight_prep(w2, 2, gamma, act_dtype)            # [4C, C]
+        dh = torch.empty((M, C4), dtype=act_dtype, device=dev)
+        L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
+                "gemm_dgrad_gelu_bwd")
+        # 3. fc2 wgrad on the UNSCALED gradient; layer-scale identities give dW2, db2, dgamma without saving z
+        G2, s = _wgrad(dz, g, M, C, C4, True)
+        dW2 = torch.empty_like(w2)
+        db2 = torch.empty_like(b2)
+        dgamma = torch.empty_like(gamma) if gamma is not None else None
+        L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, 0,
+                                            L.ptr(dW2), L.ptr(db2), L.ptr(dgamma), st), "layerscale_finalize")
+        # 4. dxn = dh . W1
+        w1t = _weight_prep(w1, 1, None, act_dtype)              # [C, 4C]
+        dxn = torch.empty((M, C), dtype=act_dtype, device=dev)
+        L.check(lib.cnx_gemm_plain(L.ptr(dh), L.ptr(w1t), None, L.ptr(dxn), ad, M, C, C4, ad, GEMM_FLAGS, st), "gemm_plain")
+        # 5. fc1 wgrad + bias grad
+        dW1, db1 = _wgrad(dh, xn, M, C4, C, True)
+        # 6. LayerNorm backward
+        P = _num_partials()
+        dy = torch.empty((M, C), dtype=act_dtype, device=dev)
+        part = torch.empty((P, 2 * C), dtype=torch.float32, device=dev)
+        L.check(lib.cnx_ln_bwd(L.ptr(dxn), ad, L.ptr(y), ad, L.ptr(mean), L.ptr(rstd), L.ptr(ln_w), M, C, L.ptr(dy), ad,
+                               L.ptr(part), P, st), "ln_bwd")
+        dln = torch.empty((2 * C,), dtype=torch.float32, device=dev)
+        L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dln), st), "reduce_partials")
+        # 7. dwconv wgrad (+bias)
+        Pw = max(1, min(P, (N * ((H + 7) // 8) * ((W + 7) // 8))))
+        wpart = torch.empty((Pw, 50, C), dtype=torch.float32, device=dev)
+        L.check(lib.cnx_dwconv7_wgrad(L.ptr(dy), ad, L.ptr(xl), sd, N, H, W, C, L.ptr(wpart), Pw, st), "dwconv7_wgrad")
+        dconv_w = torch.empty_like(conv_w)
+        dconv_b = torch.empty((C,), dtype=torch.float32, device=dev)
+        L.check(lib.cnx_dwconv7_wgrad_finalize(L.ptr(wpart), Pw, C, 0, L.ptr(dconv_w), L.ptr(dconv_b), st),
+                "dwconv7_wgrad_finalize")
+        # 8. dx = dout + dwconv_dgrad(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxl = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+            L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(conv_w), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
+                    "dwconv7_dgrad")
+            dx = dxl.permute(0, 3, 1, 2)
+        return (dx, dconv_w, dconv_b, dln[:C], dln[C:], dW1, db1, dW2, db2, dgamma, None, None, None)
+
+
+def block_forward(x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps: float):
+    """ConvNeXt Block forward (autograd-enabled).  x: logical [N,C,H,W]; dp: per-sample drop-path scale [N] or None."""
+    act_dtype = _act_dtype()
+    if act_dtype == torch.float32 and x.dtype != torch.float32:
+        raise TypeError("fp32 mode (no autocast) needs an fp32 residual stream")
+    return _BlockFn.apply(x, conv_w.contiguous(), conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, float(eps), act_dtype)
+
+
+class _LayerNormCLFn(torch.autograd.Function):
+    """LayerNorm over the last dim of a contiguous [..., C] tensor; fp32 output under autocast (as ATen's policy)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps, out_dtype):
+        lib = L.load()
+        L.require_cuda(x, w, b)
+        C = x.shape[-1]
+        x2 = x.detach().reshape(-1, C)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        out = torch.empty((M, C), dtype=out_dtype, device=x.device)
+        mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+        L.check(lib.cnx_ln_fwd(L.ptr(x2), L.dt(x2), L.ptr(w), L.ptr(b), eps, M, C, L.ptr(out), L.dt(out_dtype),
+                               L.ptr(mean), L.ptr(rstd), L.stream()), "ln_fwd")
+        ctx.save_for_backward(x2, mean, rstd, w)
+        ctx.xshape = x.shape
+        return out.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        x2, mean, rstd, w = ctx.saved_tensors
+        M, C = x2.shape
+        d2 = dout.reshape(M, C)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        P = max(1, min(_num_partials(), (M + 7) // 8))
+        dx = torch.empty((M, C), dtype=x2.dtype, device=x2.device)
+        part = torch.empty((P, 2 * C), dtype=torch.float32, device=x2.device)
+        L.check(lib.cnx_ln_bwd(L.ptr(d2), L.dt(d2), L.ptr(x2), L.dt(x2), L.ptr(mean), L.ptr(rstd), L.ptr(w), M, C,
+                               L.ptr(dx), L.dt(dx), L.ptr(part), P, L.stream()), "ln_bwd")
+        dwb = torch.empty((2 * C,), dtype=torch.float32, device=x2.device)
+        L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
+        return dx.reshape(ctx.xshape), dwb[:C], dwb[C:], None, None
+
+
+def layer_norm_cl(x, w, b, eps: float):
+    """F.layer_norm(x, (C,), w, b, eps) for channels-last x; output fp32 under autocast (ATen autocast policy)."""
+    out_dtype = torch.float32 if (torch.is_autocast_enabled("cuda") or x.dtype == torch.float32) else x.dtype
+    return _LayerNormCLFn.apply(x, w, b, float(eps), out_dtype)
+
+
+class _SoftTargetCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target):
+        lib = L.load()
+        L.require_cuda(x, target)
+        if x.dim() != 2 or target.shape != x.shape:
+            raise ValueError(f"SoftTargetCrossEntropy expects x and target of the same [B,K] shape, got {tuple(x.shape)} "
+                             f"and {tuple(target.shape)}")
+        B, K = x.shape
+        xc = x.detach().contiguous()
+        tc = target.detach().to(torch.float32).contiguous()
+        dev = x.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        lse = torch.empty((B,), dtype=torch.float32, device=dev)
+        row = torch.empty((B,), dtype=torch.float32, device=dev)
+        counter = torch.zeros((1,), dtype=torch.int32, device=dev)
+        L.check(lib.cnx_soft_target_ce_fwd(L.ptr(xc), L.dt(xc), L.ptr(tc), B, K, L.ptr(loss), L.ptr(lse), L.ptr(row),
+                                           L.ptr(counter), L.stream()), "soft_target_ce_fwd")
+        ctx.save_for_backward(xc, tc, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = L.load()
+        xc, tc, lse = ctx.saved_tensors
+        B, K = xc.shape
+        dl = dloss.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(xc)
+        L.check(lib.cnx_soft_target_ce_bwd(L.ptr(xc), L.dt(xc), L.ptr(tc), L.ptr(lse), L.ptr(dl), B, K, L.ptr(dx),
+                                           L.dt(dx), L.stream()), "soft_target_ce_bwd")
+        return dx, None
+
+
+def soft_target_cross_entropy(x, target):
+    return _SoftTargetCEFn.apply(x, target)
+
+
+def mixup_target(target: torch.Tensor, num_classes: int, lam: float = 1.0, smoothing: float = 0.0) -> torch.Tensor:
+    """timm.data.mixup.mixup_target on the GPU, bit-exact in fp32 (one kernel instead of six)."""
+    lib = L.load()
+    L.require_cuda(target)
+    t = target.detach().long().contiguous().view(-1)
+    B = t.numel()
+    out = torch.empty((B, num_classes), dtype=torch.float32, device=t.device)
+    L.check(lib.cnx_mixup_target(L.ptr(t), B, num_classes, float(lam), float(smoothing), L.ptr(out), L.stream()),
+            "mixup_target")
+    return out

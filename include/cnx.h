@@ -27,6 +27,8 @@ extern "C" {
 #endif
 
 #define CNX_VERSION 100
+/* exported symbols (the library is built with -fvisibility=hidden) */
+#define CNX_API __attribute__((visibility("default")))
 
 enum { CNX_F32 = 0, CNX_BF16 = 1 };
 
@@ -38,10 +40,10 @@ enum {
   CNX_E_WORKSPACE = -4 /* caller workspace too small */
 };
 
-int cnx_version(void);
-const char* cnx_last_error_string(void);
+CNX_API int cnx_version(void);
+CNX_API const char* cnx_last_error_string(void);
 /* Number of SMs of the current device (grid sizing for callers that allocate per-CTA partials). */
-int cnx_sm_count(void);
+CNX_API int cnx_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * a10  ModelEmaV3.update  (engine.py:68,77 -> timm ModelEmaV3.apply_update_ -> torch._foreach_lerp_)
@@ -56,7 +58,7 @@ typedef struct {
   int64_t numel;
   int64_t chunk_start;  /* index of this tensor's first chunk */
 } cnx_ema_entry;
-int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float w, void* stream);
+CNX_API int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float w, void* stream);
 
 /* Fused AdamW + EMA over the same kind of pointer table (optim_factory.py:74-75 +
  * engine.py:73-77).  torch.optim.AdamW single-tensor semantics, decoupled weight decay, no amsgrad. */
@@ -69,7 +71,7 @@ typedef struct {
   int64_t numel;
   int64_t chunk_start;
 } cnx_adamw_entry;
-int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float lr, float beta1,
+CNX_API int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float lr, float beta1,
                         float beta2, float eps, float weight_decay, float bias_correction1,
                         float bias_correction2_sqrt, float ema_w, void* stream);
 
@@ -81,9 +83,9 @@ int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chun
  *        final mean is summed in a fixed order (deterministic).
  *   bwd: dx[n,k] = (softmax(x)[n,k] * sum_k t[n,:] - t[n,k]) * dloss / B
  * ---------------------------------------------------------------------------------------------- */
-int cnx_soft_target_ce_fwd(const void* x, int x_dtype, const float* t, int64_t B, int64_t K, float* loss,
+CNX_API int cnx_soft_target_ce_fwd(const void* x, int x_dtype, const float* t, int64_t B, int64_t K, float* loss,
                            float* lse, float* row_loss, unsigned int* counter, void* stream);
-int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, const float* lse, const float* dloss,
+CNX_API int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, const float* lse, const float* dloss,
                            int64_t B, int64_t K, void* dx, int dx_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -91,7 +93,7 @@ int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, const flo
  *     off = s/K; on = 1 - s + off (double, then rounded to fp32)
  *     out[b,k] = fl(fl(y(t[b])[k] * lam) + fl(y(t[B-1-b])[k] * (1-lam)))   — three separate roundings.
  * ---------------------------------------------------------------------------------------------- */
-int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, double smoothing, float* out,
+CNX_API int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, double smoothing, float* out,
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -101,36 +103,36 @@ int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, do
  *   x [N,H,W,C] stream dtype; w [C,49] fp32 (the canonical [C,1,7,7] parameter, contiguous);
  *   outputs y, xn [M,C] act dtype; mean, rstd [M] fp32.
  * ---------------------------------------------------------------------------------------------- */
-int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w,
+CNX_API int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w,
                        const float* ln_b, float eps, int64_t N, int64_t H, int64_t W, int64_t C, void* y,
                        void* xn, int act_dtype, float* mean, float* rstd, void* stream);
 
 /* Stand-alone channels-last LayerNorm forward (used by LayerNorm2d in stem/downsample/head; convnext.py:175-176).
  * x [M,C] (x_dtype) -> out [M,C] (out_dtype), mean/rstd [M] fp32. */
-int cnx_ln_fwd(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
+CNX_API int cnx_ln_fwd(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
                void* out, int out_dtype, float* mean, float* rstd, void* stream);
 
 /* LayerNorm backward.  dy = rstd * (g - mean_C(g) - xhat * mean_C(g*xhat)), g = dxn*ln_w, xhat=(y-mean)*rstd.
  * partial [P, 2, C] fp32 receives per-CTA column sums of (dxn*xhat, dxn); P = number of CTAs the caller
  * wants launched (>=1); reduce with cnx_reduce_partials. */
-int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+CNX_API int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
                const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
                void* stream);
 
 /* out[j] = (accumulate ? out[j] : 0) + scale * sum_p partial[p, j], fixed order (deterministic). */
-int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
+CNX_API int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream);
 
 /* dwconv backward-data (+ residual-gradient add): dx = dres + dwconv7x7_flipped(dy).  dres may be NULL.
  * dy [M,C] act dtype; dres, dx [M,C] stream dtype. */
-int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* w, const void* dres, void* dx, int stream_dtype,
+CNX_API int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* w, const void* dres, void* dx, int stream_dtype,
                       int64_t N, int64_t H, int64_t W, int64_t C, void* stream);
 
 /* dwconv backward-weights + bias grad: partial [P, 50, C] fp32 (taps 0..48 then bias), P CTAs (persistent). */
-int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W,
+CNX_API int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W,
                       int64_t C, float* partial, int P, void* stream);
 /* dw[c, t] (+)= sum_p partial[p, t, c]; db[c] (+)= sum_p partial[p, 49, c]  (transposes to the canonical layout) */
-int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, int accumulate, float* dw, float* db,
+CNX_API int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, int accumulate, float* dw, float* db,
                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -143,53 +145,53 @@ int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, int accum
 #define CNX_GEMM_FORCE_SIMT 1
 
 /* fc1: h = A.W1^T + b1 ; g = GELU_erf(h).  h_out may be NULL (inference). */
-int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64_t M, int64_t N, int64_t K,
+CNX_API int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64_t M, int64_t N, int64_t K,
                            void* h_out, void* g_out, int dtype, int flags, void* stream);
 
 /* fc2: out[m,n] = shortcut[m,n] + dp[m / rows_per_sample] * gamma[n] * (acc[m,n] + b2[n]).
  * dp NULL -> 1 (eval / no drop-path); gamma NULL -> 1; shortcut NULL -> 0.  out/shortcut stream dtype. */
-int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float* b2, const float* gamma,
+CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float* b2, const float* gamma,
                                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out,
                                      int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,
                                      void* stream);
 
 /* dgrad of fc2 with GELU': dh[m,n] = acc[m,n] * GELU'(h[m,n]),  acc = dz.W2s (B given as [N=4C, K=C]). */
-int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* h, void* dh, int64_t M, int64_t N,
+CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* h, void* dh, int64_t M, int64_t N,
                             int64_t K, int dtype, int flags, void* stream);
 
 /* plain GEMM with cast epilogue: out = A.B^T (dgrad of fc1; also patchify convs).  bias may be NULL. */
-int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,
+CNX_API int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,
                    int64_t N, int64_t K, int dtype, int flags, void* stream);
 
 /* wgrad: out[N1,N2] (+)= sum_m X[m,i] * Y[m,j]   (X [M,N1], Y [M,N2], act dtype; fp32 out).
  * colsum_x (optional, [N1] fp32) (+)= sum_m X[m,i]  (the bias gradient; on the bf16 path the tensor core
  * computes it with an all-ones B tile).  workspace: scratch of >= cnx_gemm_wgrad_workspace_bytes(...)
  * bytes.  Deterministic split-K over M (fp32 partials reduced in a fixed order). */
-int64_t cnx_gemm_wgrad_workspace_bytes(int64_t M, int64_t N1, int64_t N2, int dtype, int flags);
-int cnx_gemm_wgrad(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+CNX_API int64_t cnx_gemm_wgrad_workspace_bytes(int64_t M, int64_t N1, int64_t N2, int dtype, int flags);
+CNX_API int cnx_gemm_wgrad(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                    float* colsum_x, void* workspace, int64_t workspace_bytes, int dtype, int flags, void* stream);
 
 /* Gradient prep at block-backward entry: dz[m,c] = act(dp[n] * dout[m,c]) (dp NULL -> 1).
  * dout stream dtype -> dz act dtype. */
-int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, int64_t rows_per_sample, int64_t M,
+CNX_API int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, int64_t rows_per_sample, int64_t M,
                   int64_t C, void* dz, int act_dtype, void* stream);
 
 /* Weight prep (tiny, [R,Ccols] fp32 -> act dtype):
  *   mode 0: out[r,c]   = W[r,c]                       (cast)
  *   mode 1: out[c,r]   = W[r,c]                       (transpose + cast)      -> W1^T for dgrad fc1
  *   mode 2: out[c,r]   = row_scale[r] * W[r,c]        (scale rows, transpose) -> (gamma.W2)^T for dgrad fc2 */
-int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_scale, int mode, void* out,
+CNX_API int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_scale, int mode, void* out,
                     int out_dtype, void* stream);
 
 /* Layer-scale gradient from the UNSCALED fc2 wgrad G2[c,k] = sum_m dz[m,c] g[m,k], s[c] = sum_m dz[m,c]:
  *   dgamma[c] (+)= sum_k W2[c,k]*G2[c,k] + b2[c]*s[c];  dW2[c,k] (+)= gamma[c]*G2[c,k];  db2[c] (+)= gamma[c]*s[c]
  * (identity used instead of saving z = fc2 output).  gamma NULL -> 1 and dgamma skipped. */
-int cnx_layerscale_finalize(const float* G2, const float* s, const float* W2, const float* b2, const float* gamma,
+CNX_API int cnx_layerscale_finalize(const float* G2, const float* s, const float* W2, const float* b2, const float* gamma,
                             int64_t C, int64_t K4, int accumulate, float* dW2, float* db2, float* dgamma,
                             void* stream);
 
 /* Elementwise fp32 -> bf16 cast of a flat buffer (parameter shadow copies). */
-int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
+CNX_API int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
 
 #ifdef __cplusplus
 }

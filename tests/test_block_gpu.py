@@ -1,0 +1,129 @@
+"""ConvNeXt Block fwd+bwd (BASELINE config 5 sweep C x H) and the full ConvNeXt-T:
+libcnx modules vs the oracle modules with identical weights and inputs.
+Bars: fp32 <= 1e-4 relative on outputs and gradients; bf16 autocast <= 2e-2 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+import imageclassification_b200 as P
+from cabi import max_rel
+from oracle import convnext as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _pair_block(C, drop_path, gamma_init, seed):
+    torch.manual_seed(seed)
+    o = O.ConvNeXtBlock(C, drop_path=drop_path, ls_init_value=gamma_init).to(DEV)
+    with torch.no_grad():                                   # non-trivial biases / affine params / gamma
+        for n, p in o.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.05)
+            elif n == "norm.weight":
+                p.add_(0.1 * torch.randn_like(p))
+            elif n == "gamma":
+                p.mul_(1 + 0.2 * torch.randn_like(p))
+    p_ = P.ConvNeXtBlock(C, drop_path=drop_path, ls_init_value=gamma_init).to(DEV)
+    p_.load_state_dict(o.state_dict())
+    return o, p_
+
+
+def _run(mod, x, dout, autocast, seed):
+    x = x.clone().requires_grad_(True)
+    torch.manual_seed(seed)                                 # same drop-path mask draw in both
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = mod(x)
+    else:
+        y = mod(x)
+    y.backward(dout.to(y.dtype))
+    return y, x.grad, {n: p.grad for n, p in mod.named_parameters()}
+
+
+SWEEP = [(96, 56), (192, 28), (384, 14), (768, 7), (96, 7), (768, 14), (128, 9), (1536, 12)]
+
+
+@pytest.mark.parametrize("C,H", SWEEP)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("drop_path", [0.0, 0.4])
+def test_block_fwd_bwd(C, H, mode, drop_path):
+    N = 4 if C * H * H > 200000 else 6
+    o, p = _pair_block(C, drop_path, 1.0, C + H)
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(N, C, H, H, generator=g).to(DEV)
+    dout = torch.randn(N, C, H, H, generator=g).to(DEV)
+    ac = mode == "bf16"
+    yo, dxo, go = _run(o, x, dout, ac, 123)
+    yp, dxp, gp = _run(p, x, dout, ac, 123)
+    assert yp.shape == yo.shape and yp.dtype == yo.dtype == torch.float32    # residual stream stays fp32 under autocast
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert max_rel(yp, yo) <= tol
+    assert max_rel(dxp, dxo) <= tol
+    for n in go:
+        assert gp[n] is not None, n
+        assert gp[n].shape == go[n].shape
+        assert max_rel(gp[n], go[n]) <= tol, n
+
+
+def test_block_tiny_gamma_and_eval():
+    """gamma = 1e-6 (the timm default): the branch nearly vanishes from y, but dgamma must still be right."""
+    o, p = _pair_block(96, 0.0, 1e-6, 9)
+    x = torch.randn(2, 96, 14, 14, device=DEV)
+    dout = torch.randn_like(x)
+    yo, dxo, go = _run(o, x, dout, False, 1)
+    yp, dxp, gp = _run(p, x, dout, False, 1)
+    assert max_rel(yp, yo) <= 1e-6
+    assert max_rel(gp["gamma"], go["gamma"]) <= 1e-4
+    assert max_rel(dxp, dxo) <= 1e-6
+    o.eval(); p.eval()
+    with torch.no_grad():
+        assert max_rel(p(x), o(x)) <= 1e-6
+    o2, p2 = _pair_block(96, 0.5, 1.0, 9)
+    o2.eval(); p2.eval()                                     # drop-path is the identity in eval mode
+    with torch.no_grad():
+        assert max_rel(p2(x), o2(x)) <= 1e-4
+
+
+def test_block_channels_last_input_and_errors():
+    o, p = _pair_block(64, 0.0, 1.0, 4)
+    x = torch.randn(2, 64, 9, 11, device=DEV).contiguous(memory_format=torch.channels_last)
+    assert max_rel(p(x), o(x)) <= 1e-4
+    with pytest.raises(RuntimeError):
+        P.ConvNeXtBlock(64)(torch.randn(1, 64, 8, 8))        # CPU tensors: no fallback, loud failure
+    with pytest.raises(NotImplementedError):
+        P.ConvNeXtBlock(64, kernel_size=3)
+
+
+def _pair_model(name, num_classes, dpr, gamma_init, seed):
+    torch.manual_seed(seed)
+    o = O.create_model(name, num_classes=num_classes, drop_path_rate=dpr, ls_init_value=gamma_init).to(DEV)
+    p = P.create_model(name, num_classes=num_classes, drop_path_rate=dpr, ls_init_value=gamma_init).to(DEV)
+    p.load_state_dict(o.state_dict())
+    return o, p
+
+
+@pytest.mark.parametrize("mode,gamma_init,dpr", [("fp32", 1.0, 0.0), ("fp32", 1e-6, 0.05), ("bf16", 1.0, 0.0), ("bf16", 1e-6, 0.05)])
+def test_convnext_tiny_fwd_bwd(mode, gamma_init, dpr):
+    """BASELINE config 1 shape (batch 8, 2 classes, 224^2): logits and ALL 182 gradients vs the oracle."""
+    o, p = _pair_model("convnext_tiny", 2, dpr, gamma_init, 88)
+    g = torch.Generator().manual_seed(88)
+    x = torch.randn(8, 3, 224, 224, generator=g).to(DEV)
+    t = torch.softmax(torch.randn(8, 2, generator=g), -1).to(DEV)
+    outs = []
+    for m in (o, p):
+        torch.manual_seed(7)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            logits = m(x)
+            loss = torch.sum(-t * torch.log_softmax(logits.float(), -1), -1).mean()
+        loss.backward()
+        outs.append((logits.float(), {n: q.grad for n, q in m.named_parameters()}))
+    (lo, go), (lp, gp) = outs
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert max_rel(lp, lo) <= tol
+    worst = max((max_rel(gp[n], go[n]), n) for n in go)
+    # gradients: per-tensor max-relative error; bf16 errors accumulate over 18 blocks, bar is per north_star 2e-2
+    assert worst[0] <= (1e-3 if mode == "fp32" else 5e-2), worst
+    import math
+    tot_p = math.sqrt(sum((gp[n].double() ** 2).sum().item() for n in go))
+    tot_d = math.sqrt(sum(((gp[n].double() - go[n].double()) ** 2).sum().item() for n in go))
+    assert tot_d / tot_p <= tol, (tot_d / tot_p)

@@ -1,0 +1,109 @@
+"""a3..a8: the MLP GEMMs with fused epilogues.  fp32 CUDA-core path vs torch fp32 (<= 1e-4 relative);
+bf16 tcgen05 path vs (i) the CUDA-core kernel on the same bf16 operands (tight: same operands, fp32 accumulate)
+and (ii) torch fp32 on the bf16-rounded operands (<= 2e-2, the bf16 bar of BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cabi import gemm_bias_gelu, gemm_dgelu, gemm_plain, gemm_scale_res, gemm_wgrad, max_rel
+from imageclassification_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SIMT = L.CNX_GEMM_FORCE_SIMT
+
+# (M, C): fc1 is [M,C]x[4C,C]^T, fc2 is [M,4C]x[C,4C]^T
+MC = [(3136, 96), (784 * 2, 192), (196 * 3, 384), (49 * 4, 768), (100, 96), (1, 96), (129, 128), (300, 1536), (257, 32)]
+
+
+def _mk(M, C, dt, seed):
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, C, generator=g).to(dt).to(DEV)
+    W1 = (torch.randn(4 * C, C, generator=g) / math.sqrt(C)).to(dt).to(DEV)
+    b1 = (0.1 * torch.randn(4 * C, generator=g)).to(DEV)
+    W2 = (torch.randn(C, 4 * C, generator=g) / math.sqrt(4 * C)).to(dt).to(DEV)
+    b2 = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    gamma = torch.rand(C, generator=g).to(DEV) + 0.5
+    return A, W1, b1, W2, b2, gamma
+
+
+@pytest.mark.parametrize("M,C", MC)
+@pytest.mark.parametrize("mode", ["f32", "bf16_simt", "bf16_tc"])
+def test_mlp_forward_gemms(M, C, mode):
+    dt = torch.float32 if mode == "f32" else torch.bfloat16
+    flags = SIMT if mode == "bf16_simt" else 0
+    A, W1, b1, W2, b2, gamma = _mk(M, C, dt, M + C)
+    h, gl = gemm_bias_gelu(A, W1, b1, flags)
+    href = (A.float() @ W1.float().t() + b1)
+    tol = 1e-4 if dt == torch.float32 else 1e-2
+    assert max_rel(h.float(), href) <= tol
+    assert max_rel(gl.float(), F.gelu(h.float())) <= tol      # GELU of the rounded h, as autocast computes it
+    rps = 7
+    n_s = (M + rps - 1) // rps
+    dp = (torch.rand(n_s, device=DEV) > 0.3).float() / 0.7
+    for sdt in ([torch.float32] if dt == torch.float32 else [torch.float32, torch.bfloat16]):
+        sc = torch.randn(M, C, device=DEV).to(sdt)
+        out = gemm_scale_res(gl, W2, b2, gamma, dp, rps, sc, sdt, flags)
+        z = gl.float() @ W2.float().t() + b2
+        ref = sc.float() + dp.repeat_interleave(rps)[:M, None] * (gamma * z)
+        assert max_rel(out.float(), ref) <= (1e-4 if dt == torch.float32 else 2e-2)
+        out2 = gemm_scale_res(gl, W2, None, None, None, 1, None, sdt, flags)
+        assert max_rel(out2.float(), gl.float() @ W2.float().t()) <= (1e-4 if dt == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("M,C", MC)
+@pytest.mark.parametrize("mode", ["f32", "bf16_simt", "bf16_tc"])
+def test_mlp_backward_gemms(M, C, mode):
+    dt = torch.float32 if mode == "f32" else torch.bfloat16
+    flags = SIMT if mode == "bf16_simt" else 0
+    A, W1, b1, W2, b2, gamma = _mk(M, C, dt, 2 * M + C)
+    g = torch.Generator().manual_seed(5)
+    dz = torch.randn(M, C, generator=g).to(dt).to(DEV)
+    h = torch.randn(M, 4 * C, generator=g).to(dt).to(DEV)
+    tol = 1e-4 if dt == torch.float32 else 2e-2
+    # dgrad fc2 with GELU':  Bt = W2^T [4C, C]
+    Bt = W2.t().contiguous()
+    dh = gemm_dgelu(dz, Bt, h, flags)
+    hf = h.float().requires_grad_(True)
+    F.gelu(hf).backward(dz.float() @ W2.float())
+    assert max_rel(dh.float(), hf.grad) <= tol
+    # dgrad fc1: dxn = dh . W1  (B = W1^T [C, 4C])
+    dxn = gemm_plain(dh, W1.t().contiguous(), None, dt, flags)
+    assert max_rel(dxn.float(), dh.float() @ W1.float()) <= tol
+    if dt == torch.bfloat16:
+        out32 = gemm_plain(dh, W1.t().contiguous(), b2, torch.float32, flags)
+        assert max_rel(out32, dh.float() @ W1.float() + b2) <= 1e-3
+    # wgrads + bias grads
+    G, s = gemm_wgrad(dz, h, flags)                       # [C, 4C]
+    assert max_rel(G, dz.float().t() @ h.float()) <= (1e-4 if dt == torch.float32 else 1e-3)
+    assert max_rel(s, dz.float().sum(0)) <= 1e-4
+    G1, s1 = gemm_wgrad(h, A, flags)                      # [4C, C]
+    assert max_rel(G1, h.float().t() @ A.float()) <= (1e-4 if dt == torch.float32 else 1e-3)
+    assert max_rel(s1, h.float().sum(0)) <= 1e-4
+
+
+@pytest.mark.parametrize("M,C", [(3136, 96), (1000, 192), (260, 768)])
+def test_tc_matches_simt_on_same_operands(M, C):
+    """Same bf16 operands, both accumulate in fp32: differences are summation-order only."""
+    A, W1, b1, W2, b2, gamma = _mk(M, C, torch.bfloat16, 3 * M + C)
+    h0, g0 = gemm_bias_gelu(A, W1, b1, SIMT)
+    h1, g1 = gemm_bias_gelu(A, W1, b1, 0)
+    assert max_rel(h1.float(), h0.float()) <= 4e-3        # <= 1 bf16 ulp on the rare rounding flip
+    assert (h1 != h0).float().mean().item() < 0.02
+    o0 = gemm_scale_res(g0, W2, b2, gamma, None, 1, None, torch.float32, SIMT)
+    o1 = gemm_scale_res(g0, W2, b2, gamma, None, 1, None, torch.float32, 0)
+    assert max_rel(o1, o0) <= 1e-5
+    G0, s0 = gemm_wgrad(g0, A, SIMT)
+    G1, s1 = gemm_wgrad(g0, A, 0)
+    assert max_rel(G1, G0) <= 1e-4 and max_rel(s1, s0) <= 1e-4
+
+
+def test_gemm_argument_errors():
+    lib = L.load()
+    a = torch.zeros(8, 12, device=DEV)
+    rc = lib.cnx_gemm_plain(L.ptr(a), L.ptr(a), None, L.ptr(a), 0, 8, 12, 12, 0, 0, L.stream())   # N % 8 != 0
+    assert rc == -2 and b"multiple of 8" in lib.cnx_last_error_string()
+    rc = lib.cnx_gemm_plain(None, L.ptr(a), None, L.ptr(a), 0, 8, 8, 12, 0, 0, L.stream())
+    assert rc == -1
