@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: ConvNeXt-T 224^2 bf16 training images/s (1/2/4/8 B200) + per-kernel roofline.
+
+  python bench.py [--gpus N --steps K --warmup W]        this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference [...]                  the reference's CPU path (oracle port of engine.py's step) on
+                                                           the host cores, bounded sample of the same workload
+
+One "step" = one pass of the reference's training step (engine.py:27-97) over one batch of 256 synthetic images per
+GPU: mixup(0.8)+label smoothing 0.1 -> ConvNeXt-T forward (bf16 autocast) -> SoftTargetCrossEntropy -> backward ->
+AdamW -> ModelEmaV3 update -> the no-grad accuracy forward on the un-mixed batch (engine.py:89-97).  Prints ONE JSON
+line (rank 0).  Keys: see the task contract; `value` = device-resident inputs, `e2e` = through engine.train_one_epoch
+with pinned HOST buffers (H2D of the batch and D2H of the loss inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ConvNeXt-T 224^2 bf16 train images/sec"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="convnext_tiny")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--classes", type=int, default=1000)
+    ap.add_argument("--img", type=int, default=224)
+    ap.add_argument("--cpu-sample-batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW instead of the fused AdamW+EMA")
+    ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.model} {a.img}x{a.img} bf16 autocast, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
+            f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward (engine.py:27-97)")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------ roofline
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+def kernel_work(name, a):
+    """(algorithmic bytes, flops, label) of one C-ABI call from its arguments (include/cnx.h order); DESIGN.md §roofline."""
+    es = lambda d: 2 if d == 1 else 4
+    if name == "cnx_dwconv7_ln_fwd":
+        N, H, W, C = a[7:11]
+        MC = N * H * W * C
+        return MC * (es(a[1]) + 2 * es(a[13])) + 8 * N * H * W + 52 * C * 4, 106 * MC, f"dwconv7_ln_fwd C{C} H{H}"
+    if name == "cnx_dwconv7_dgrad":
+        N, H, W, C = a[6:10]
+        MC = N * H * W * C
+        return MC * (es(a[1]) + (2 if a[3] else 1) * es(a[5])), 98 * MC, f"dwconv7_dgrad C{C} H{H}"
+    if name == "cnx_dwconv7_wgrad":
+        N, H, W, C = a[4:8]
+        MC = N * H * W * C
+        return MC * (es(a[1]) + es(a[3])) + 50 * C * 4, 98 * MC, f"dwconv7_wgrad C{C} H{H}"
+    if name == "cnx_ln_bwd":
+        M, C = a[7:9]
+        return M * C * (es(a[1]) + es(a[3]) + es(a[10])) + 8 * M + 16 * C, 0, f"ln_bwd C{C}"
+    if name == "cnx_ln_fwd":
+        M, C = a[5:7]
+        return M * C * (es(a[1]) + es(a[8])) + 8 * M + 8 * C, 0, f"ln_fwd C{C}"
+    if name == "cnx_gemm_bias_gelu_fwd":
+        M, N, K = a[3:6]
+        e = es(a[8])
+        return (M * K + N * K + M * N * (2 if a[6] else 1)) * e, 2 * M * N * K, f"fc1_gelu K{K}"
+    if name == "cnx_gemm_bias_scale_residual_fwd":
+        M, N, K = a[9:12]
+        e, s = es(a[12]), es(a[8])
+        return (M * K + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
+    if name == "cnx_gemm_dgrad_gelu_bwd":
+        M, N, K = a[4:7]
+        e = es(a[7])
+        return (M * K + N * K + 2 * M * N) * e, 2 * M * N * K, f"dgrad_fc2_gelu K{K}"
+    if name == "cnx_gemm_plain":
+        M, N, K = a[5:8]
+        e = es(a[8])
+        return (M * K + N * K) * e + M * N * es(a[4]), 2 * M * N * K, f"gemm_plain N{N} K{K}"
+    if name == "cnx_gemm_wgrad":
+        M, N1, N2 = a[2:5]
+        e = es(a[10])
+        return M * (N1 + N2) * e + N1 * N2 * 4, 2 * M * N1 * N2, f"wgrad {N1}x{N2}"
+    if name == "cnx_grad_prep":
+        M, C = a[4:6]
+        return M * C * (es(a[1]) + es(a[7])), 0, f"grad_prep C{C}"
+    if name in ("cnx_ema_lerp_multi",):
+        return None, 0, "ema"
+    return None, 0, name.replace("cnx_", "")
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import imageclassification_b200 as P
+    from imageclassification_b200 import _lib as L, ddp as pddp, engine as pengine, optim as poptim
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(88 + rank)
+    np.random.seed(88 + rank)                                     # train.py:116-118
+
+    model = P.create_model(a.model, pretrained=False, num_classes=a.classes, drop_path_rate=0.05).to(dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    ema = P.ModelEmaV3(model, decay=0.9995, device=dev)           # train.py:201
+    net = pddp.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    groups = [{"params": [p for p in model.parameters() if p.requires_grad], "weight_decay": 5e-4}]   # optim_factory.py:23-47
+    if a.torch_adamw:
+        opt = torch.optim.AdamW(groups, lr=1e-3, weight_decay=0.0)
+    else:
+        opt = poptim.AdamW(groups, lr=1e-3, weight_decay=0.0)
+        opt.fuse_ema(ema, model)
+    mix = P.Mixup(mixup_alpha=0.8, cutmix_alpha=0.0, label_smoothing=0.1, num_classes=a.classes)     # train.py:176-185
+    crit = P.SoftTargetCrossEntropy()
+
+    B = a.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host = 4                                                    # distinct synthetic batches, cycled
+    host = [(torch.randn(B, 3, a.img, a.img, generator=g).pin_memory(),
+             torch.randint(0, a.classes, (B,), generator=g).pin_memory()) for _ in range(n_host)]
+    devb = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def epoch(batches):
+        if a.no_acc_forward:
+            return _fast_epoch(batches)
+        return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=True,
+                                       num_classes=a.classes, verbose=False)
+
+    def _fast_epoch(batches):
+        net.train(True)
+        for x, t in batches:
+            x, t = x.to(dev, non_blocking=True), t.to(dev, non_blocking=True)
+            xs, ts = mix(x.clone(), t)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = crit(net(xs), ts)
+            lv = loss.item()
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            ema.update(net)
+        return {"loss": lv}
+
+    def timed(batches_src, steps):
+        batches = [batches_src[i % len(batches_src)] for i in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stats = epoch(batches)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, stats
+
+    # warm-up (both input sources), then the two timed regions
+    timed(devb, max(a.warmup, 3))
+    timed(host, 2)
+    names_top = None
+    with ClockSampler(local) as clk:
+        c0 = L.gpu_launches()
+        ms_dev, stats = timed(devb, a.steps)
+        launches = L.gpu_launches() - c0
+        ms_e2e, _ = timed(host, a.steps)
+    clocks = clk.summary()
+
+    # per-kernel breakdown pass (untimed for the headline): every C-ABI call bracketed by CUDA events
+    roof, table = None, []
+    peaks = _peaks()
+    if not a.no_breakdown and rank == 0 or (not a.no_breakdown and world > 1):
+        L.TIMER = L.KernelTimer()
+        bsteps = 3
+        ms_b, _ = timed(devb, bsteps)
+        recs = L.TIMER.summary()
+        L.TIMER = None
+        agg = {}
+        for name, lst in recs.items():
+            for ms, args in lst:
+                by, fl, label = kernel_work(name, args)
+                d = agg.setdefault(label, {"ms": 0.0, "n": 0, "bytes": 0, "flops": 0, "name": name})
+                d["ms"] += ms
+                d["n"] += 1
+                d["bytes"] += by or 0
+                d["flops"] += fl
+        tot = sum(d["ms"] for d in agg.values())
+        for label, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else None
+            tfs = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["flops"] else None
+            table.append({"kernel": label, "calls_per_step": d["n"] / bsteps, "ms_per_step": round(d["ms"] / bsteps, 4),
+                          "share_of_cnx": round(d["ms"] / tot, 4), "GBps": gbs and round(gbs, 1),
+                          "hbm_frac": gbs and round(gbs / peaks["hbm"], 4), "TFLOPs": tfs and round(tfs, 2),
+                          "tensor_frac": tfs and round(tfs / peaks["tensor"], 4)})
+        if table:
+            top = table[0]
+            d = agg[top["kernel"]]
+            hb = (top["hbm_frac"] or 0)
+            tf = (top["tensor_frac"] or 0) if d["name"].startswith("cnx_gemm") else 0
+            if tf > hb:
+                roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": peaks["tensor"], "unit": "TFLOP/s",
+                        "frac": top["tensor_frac"], "traffic": None}
+            else:
+                roof = {"bound": "hbm", "achieved": top["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": top["hbm_frac"], "traffic": None}
+            roof.update({"kernel": top["kernel"], "launches_per_step": top["calls_per_step"],
+                         "avg_launch_ms": round(d["ms"] / d["n"], 4), "peak_source": peaks["src"] + " (sustained; timed inside the step)",
+                         "cnx_kernels_ms_per_step": round(tot / bsteps, 3), "step_ms_with_events": round(ms_b / bsteps, 3)})
+
+    imgs = B * world * a.steps
+    out = {
+        "metric": METRIC, "value": round(imgs / (ms_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": round(ms_dev / a.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (randn images, random labels; random-init weights)",
+        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
+                   "params": n_params, "optimizer": "torch.optim.AdamW" if a.torch_adamw else "libcnx fused AdamW+EMA",
+                   "l2": "activation footprint per step >> 126 MB L2 (inputs larger than L2, no explicit flush)",
+                   "final_loss": stats.get("loss")},
+        "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e / a.steps, 3), "api": "imageclassification_b200.engine.train_one_epoch, pinned host batches"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
+    }
+    if rank == 0:
+        if not a.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_step_rate(a, steps=2, warmup=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU baseline
+def cpu_step_rate(a, steps, warmup):
+    """The oracle port of the reference step (oracle/engine.py <- engine.py:27-97) on the host cores, fp32, on a bounded
+    sample (batch `--cpu-sample-batch`) of the same workload."""
+    import numpy as np
+    import torch
+
+    from oracle import convnext as OC, ema as OE, engine as OEng, loss as OL, mixup as OM
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(88)
+    np.random.seed(88)
+    b = a.cpu_sample_batch
+    model = OC.create_model(a.model, num_classes=a.classes, drop_path_rate=0.05)
+    ema = OE.ModelEmaV3(model, decay=0.9995, device=torch.device("cpu"))
+    opt = torch.optim.AdamW([{"params": list(model.parameters()), "weight_decay": 5e-4}], lr=1e-3, weight_decay=0.0)
+    mix = OM.Mixup(mixup_alpha=0.8, label_smoothing=0.1, num_classes=a.classes)
+    crit = OL.SoftTargetCrossEntropy()
+    batch = [(torch.randn(b, 3, a.img, a.img), torch.randint(0, a.classes, (b,)))]
+    for _ in range(warmup):
+        OEng.train_one_epoch(model, crit, batch, opt, "cpu", 0, None, 0, ema, mix, num_classes=a.classes)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        OEng.train_one_epoch(model, crit, batch, opt, "cpu", 0, None, 0, ema, mix, num_classes=a.classes)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts)
+    return {"value": round(b * steps / sec, 2), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/engine.py step, fp32, batch {b} (not {a.batch}) of the same workload, {steps} timed + {warmup} warm-up steps, "
+                      f"{sec / steps:.2f} s/step", "ms_per_step": round(1e3 * sec / steps, 1)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 3))
+    warm = 1 if a.warmup > 0 else 0
+    cb = cpu_step_rate(a, steps=steps, warmup=warm)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic (randn images, random labels; random-init weights)",
+           "config": {"workload": workload_name(a), "note": "reference train.py CPU path: the reference cannot be installed "
+                      "(timm absent, no network); oracle port of engine.py's step on the host cores; each step is a bounded "
+                      f"sample of batch {a.cpu_sample_batch}; steps capped at 3 to bound the run"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -62,6 +62,60 @@ SIGNATURES = {
 }
 
 
+# C-ABI calls that launch kernels, and how many kernels one call launches (for bench.py's `gpu_launches`;
+# cnx_gemm_wgrad launches the GEMM + one partial reduction, + one more when the bias gradient is requested).
+KERNELS_PER_CALL = {
+    "cnx_ema_lerp_multi": 1, "cnx_adamw_ema_multi": 1, "cnx_soft_target_ce_fwd": 1, "cnx_soft_target_ce_bwd": 1,
+    "cnx_mixup_target": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1,
+    "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_gemm_bias_gelu_fwd": 1,
+    "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 3,
+    "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,
+}
+CALL_COUNTS = {k: 0 for k in KERNELS_PER_CALL}
+
+
+class KernelTimer:
+    """Optional per-call CUDA-event timing of selected C-ABI entry points (bench.py's roofline leg).  Events are
+    recorded on torch's current stream, which is the stream every launch is given."""
+
+    def __init__(self, names=None):
+        self.names = set(names) if names is not None else None
+        self.records = []   # (name, start_event, end_event, int args)
+
+    def summary(self):
+        out = {}
+        for name, s, e, a in self.records:
+            out.setdefault(name, []).append((s.elapsed_time(e), a))
+        return out
+
+
+TIMER: KernelTimer | None = None
+
+
+def _wrap(name, fn):
+    def call(*a):
+        CALL_COUNTS[name] += 1
+        t = TIMER
+        if t is not None and (t.names is None or name in t.names):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*a)
+            e.record()
+            t.records.append((name, s, e, tuple(x for x in a if isinstance(x, int) and not isinstance(x, bool))))
+            return rc
+        return fn(*a)
+    call.__name__ = name
+    return call
+
+
+def gpu_launches() -> int:
+    return sum(CALL_COUNTS[k] * KERNELS_PER_CALL[k] for k in CALL_COUNTS)
+
+
+class _Lib:
+    pass
+
+
 def load():
     """Load libcnx.so once; raise (never fall back) if it is not built."""
     global _lib
@@ -71,11 +125,14 @@ def load():
         raise RuntimeError(
             f"libcnx.so not found at {LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C imageclassification_b200/csrc`). There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    cdll = ctypes.CDLL(LIB_PATH)
+    lib = _Lib()
+    lib.cdll = cdll
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        fn = getattr(cdll, name)
         fn.restype = res
         fn.argtypes = args
+        setattr(lib, name, _wrap(name, fn) if name in KERNELS_PER_CALL else fn)
     _lib = lib
     return lib
 

@@ -72,8 +72,15 @@ class ModelEmaV3(nn.Module):
     def update(self, model, step=None):
         decay = self.get_decay(step)
         ema, mod, bufs = self._pairs(model)
+        fused = ()
+        if getattr(self, "_fused_done", False):
+            # imageclassification_b200.optim.AdamW.fuse_ema: the optimizer kernel already moved these EMA tensors
+            self._fused_done = False
+            fused = self._fused_optimizer._ema_ptrs
         fl_e, fl_m = [], []
         for e, m in zip(ema, mod):
+            if fused and e.data_ptr() in fused:
+                continue
             if e.is_floating_point():
                 fl_e.append(e)
                 fl_m.append(m)
@@ -115,6 +122,8 @@ class ModelEmaV3(nn.Module):
         st = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
         st = dict(st)
         st["_table_key"], st["_table"], st["_chunks"] = None, None, 0
+        st.pop("_fused_optimizer", None)
+        st.pop("_fused_done", None)
         return st
 
 

@@ -1,0 +1,147 @@
+"""train_one_epoch — the reference's step engine (engine.py:10-143) with the same signature, argument meaning and
+return value, for callers that want the step loop from this package instead of the reference's file.  The
+reference's own `engine.train_one_epoch` also works unmodified with this package's model / criterion / EMA / mixup
+objects (that is the drop-in boundary; INTEGRATION.md shows the two-line change in train.py).
+
+What is kept exactly (results identical to engine.py on the same inputs):
+  * lr / weight-decay schedule writes (engine.py:33-38), H2D copies (:40-41), mixup (:43-44), forward + loss (:46-52),
+    `loss.item()` + non-finite guard that skips the step (:54-59), `loss /= update_freq; backward; step every
+    update_freq; zero_grad; model_ema.update` (:61-77), the second no-grad forward on the un-mixed batch for train
+    accuracy when mixup is on (:89-97), per-class TP/FP/FN totals and the returned {loss, class_acc} global averages.
+What differs, without changing results:
+  * `use_amp=True` means bf16 autocast with no GradScaler (the BASELINE north-star precision; the reference's
+    torch.amp.autocast('cuda') defaults to fp16 + scaler).
+  * per-class TP/FP/FN are accumulated ON THE DEVICE with three bincounts per step instead of 3*num_classes
+    `.item()` host syncs (engine.py:84-87/93-96), and read back once at the end of the epoch.
+  * rich progress bar / tensorboard / wandb plumbing is the caller's business: `log_writer` / `wandb_logger` are
+    accepted and fed the same keys, but nothing is imported here.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Iterable, Optional
+
+import torch
+
+
+def _class_counts(preds, targets, num_classes):
+    """(true_pos, pred_count, target_count) per class as int64 device vectors."""
+    hit = preds[preds == targets]
+    return (torch.bincount(hit, minlength=num_classes)[:num_classes],
+            torch.bincount(preds, minlength=num_classes)[:num_classes],
+            torch.bincount(targets, minlength=num_classes)[:num_classes])
+
+
+def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loader: Iterable,
+                    optimizer: torch.optim.Optimizer, device: torch.device, epoch: int, loss_scaler=None,
+                    max_norm: float = 0, model_ema=None, mixup_fn=None, log_writer=None, wandb_logger=None,
+                    start_steps: Optional[int] = 0, lr_schedule_values=None, wd_schedule_values=None,
+                    num_training_steps_per_epoch: Optional[int] = None, update_freq: Optional[int] = 1,
+                    use_amp: bool = False, num_classes: int = 2, verbose: bool = True):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "
+                           "use oracle/engine.py for CPU reference numbers")
+    update_freq = update_freq or 1
+    start_steps = start_steps or 0
+    if num_training_steps_per_epoch is None:
+        num_training_steps_per_epoch = len(data_loader) // update_freq
+    model.train(True)
+    optimizer.zero_grad()
+    start_time = time.time()
+    tp = torch.zeros(num_classes, dtype=torch.int64, device=device)
+    pc = torch.zeros_like(tp)
+    tc = torch.zeros_like(tp)
+    acc_sum = torch.zeros((), dtype=torch.float32, device=device)
+    loss_total, n_updates = 0.0, 0
+
+    for data_iter_step, (samples, targets) in enumerate(data_loader):
+        step = data_iter_step // update_freq
+        if step >= num_training_steps_per_epoch:
+            continue
+        it = start_steps + step
+        if lr_schedule_values is not None or wd_schedule_values is not None and data_iter_step % update_freq == 0:
+            for group in optimizer.param_groups:
+                if lr_schedule_values is not None:
+                    group["lr"] = lr_schedule_values[it]
+                if wd_schedule_values is not None and group["weight_decay"] > 0:
+                    group["weight_decay"] = wd_schedule_values[it]
+
+        samples = samples.to(device, non_blocking=True)
+        targets = targets.to(device, non_blocking=True)
+        original_samples, original_targets = samples, targets
+        if mixup_fn is not None:
+            # the reference makes a second device copy (engine.py:40) because mixup mutates `samples` in place
+            original_samples = samples.clone() if samples.is_cuda else samples
+            samples, targets = mixup_fn(samples, targets)
+
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp)):
+            output = model(samples)
+            loss = criterion(output, targets)
+
+        loss_value = loss.item()
+        if not math.isfinite(loss_value):
+            print("Loss is {}, stopping training".format(loss_value))
+            optimizer.zero_grad()
+            continue
+
+        loss /= update_freq
+        loss.backward()
+        grad_norm = None
+        if (data_iter_step + 1) % update_freq == 0:
+            if max_norm:
+                grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+            if model_ema is not None:
+                model_ema.update(model)
+
+        with torch.no_grad():
+            if mixup_fn is None:
+                ref_out, ref_t = output, targets
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp)):
+                    ref_out = model(original_samples)
+                ref_t = original_targets
+            preds = ref_out.max(1)[1]
+            a, b, c = _class_counts(preds, ref_t, num_classes)
+            tp += a
+            pc += b
+            tc += c
+            class_acc = (preds == ref_t).float().mean()
+            acc_sum += class_acc
+
+        loss_total += loss_value
+        n_updates += 1
+        if log_writer is not None:
+            log_writer.update(loss=loss_value, head="loss")
+            log_writer.update(class_acc=class_acc, head="loss")
+            log_writer.update(lr=max(g["lr"] for g in optimizer.param_groups), head="opt")
+            log_writer.update(min_lr=min(g["lr"] for g in optimizer.param_groups), head="opt")
+            if grad_norm is not None:
+                log_writer.update(grad_norm=grad_norm, head="opt")
+            log_writer.set_step()
+        if wandb_logger:
+            wandb_logger._wandb.log({"Rank-0 Batch Wise/train_loss": loss_value,
+                                     "Rank-0 Batch Wise/global_train_step": it})
+
+    stats = {"loss": loss_total / max(n_updates, 1), "class_acc": (acc_sum / max(n_updates, 1)).item()}
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        # utils.py:80-88: global average over ranks of (count, total) per meter
+        t = torch.tensor([n_updates, loss_total, stats["class_acc"] * n_updates], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t)
+        n = max(t[0].item(), 1.0)
+        stats = {"loss": t[1].item() / n, "class_acc": t[2].item() / n}
+    tp_l, pc_l, tc_l = tp.tolist(), pc.tolist(), tc.tolist()
+    stats_extra = {"true_positives": tp_l, "false_positives": [p - t for p, t in zip(pc_l, tp_l)],
+                   "false_negatives": [c - t for c, t in zip(tc_l, tp_l)]}
+    if verbose:
+        print(f"Averaged stats:loss: {stats['loss']:.4f}  class_acc: {stats['class_acc']:.4f},Time:{time.time() - start_time}")
+        for i in range(num_classes if num_classes <= 16 else 0):
+            fp_i, fn_i = stats_extra["false_positives"][i], stats_extra["false_negatives"][i]
+            precision = tp_l[i] / (tp_l[i] + fp_i) if tp_l[i] + fp_i > 0 else 0
+            recall = tp_l[i] / (tp_l[i] + fn_i) if tp_l[i] + fn_i > 0 else 0
+            print(f"Class {i}: Precision: {precision:.5f}, Recall: {recall:.5f}")
+    train_one_epoch.last_class_counts = stats_extra
+    return stats

@@ -26,3 +26,12 @@ def pytest_collection_modifyitems(config, items):
 def lib():
     from imageclassification_b200 import _lib
     return _lib.load()
+
+
+@pytest.fixture(autouse=True)
+def _true_fp32():
+    """fp32 parity is judged against true fp32: cuDNN/cuBLAS TF32 paths are switched off for the oracle."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield

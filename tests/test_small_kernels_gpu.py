@@ -78,7 +78,7 @@ def test_ema_special_values_and_set():
     assert torch.equal(a[~nan_a].view(torch.int32), b[~nan_b].view(torch.int32))
     e.set(gpu_model)
     for a, b in zip(e.module.state_dict().values(), gpu_model.state_dict().values()):
-        assert torch.equal(a, b)
+        _assert_bit_equal(a, b)
 
 
 def test_ema_through_wrapper_and_decay_schedule():
