@@ -1,299 +1,416 @@
 // dwconv.cu — a1/a2: depthwise 7x7 conv (+fused channels-last LayerNorm) forward, backward-data
-// (+residual-gradient add) and backward-weights.  Channels-last, shared-memory halo tiles.
+// (+residual-gradient add) and backward-weights, channels-last.
 //
-// Tiling (all three kernels): a CTA owns TH x TW output pixels of one image and walks the channels in
-// chunks of 32 (lane == channel, so every shared-memory access is a conflict-free 128-byte row).  Each
-// warp owns CPW adjacent output columns and a vertical run of TH rows: an input value loaded from
-// shared memory feeds up to 7*CPW FMAs from registers (the 49 taps of the lane's channel live in
-// registers).  Halo pixels outside the image are zero-filled, which is the conv's padding=3.
-//
-// Forward additionally keeps the conv output tile [TH*TW, C] in shared memory (rounded to the
-// activation dtype, exactly what autocast's conv hands to layer_norm), then normalises it per pixel with
-// warp-shuffle reductions (two-pass mean / biased variance in fp32) and writes y and xn with 128-bit
-// stores.  Algorithmic bytes: 2*MC*e + 8M.
+// The 7x7 depthwise conv is 98 flop per 8-12 bytes: right at the fp32 ridge of a B200, so the kernels are built
+// to keep BOTH the FMA pipe and HBM busy:
+//   * halo tiles arrive by TMA (cp.async.bulk.tensor.4d over a {C, W, H, N} tensor map, box {32 ch, TW+6, TH+6,
+//     NB}); out-of-bounds box elements are zero-filled by the TMA unit, which IS the conv's padding=3 — no
+//     per-element address math, no bounds branches;
+//   * 2-stage mbarrier pipeline, persistent CTAs: the load of (tile, chunk) g+1 overlaps the FMAs of g, across
+//     tile boundaries;
+//   * a half-warp owns 32 channels as 16 channel PAIRS, so every shared-memory access is a conflict-free 8-byte
+//     (fp32) / 4-byte (bf16) row and every FMA is the packed fma.rn.f32x2 (2 channels per instruction);
+//   * each thread keeps the 49 tap pairs of its channels and a CPW x TH output strip in registers: an input
+//     value read once from shared memory feeds up to 7*CPW packed FMAs.
+// Forward writes y (conv + bias, rounded to the activation dtype — what autocast hands to layer_norm) straight
+// from registers, then the CTA normalises its own tile from L2 (one warp per pixel, two-pass fp32 statistics)
+// and writes xn, mean, rstd.  Weights are consumed tap-major ([49][C], cnx_dwconv7_weight_prep).
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
 
 namespace cnx {
+namespace dw {
 
-constexpr int CH = 32;        // channels per chunk == warp width
-constexpr int NWARP = 8;      // warps per CTA
+constexpr int CH = 32;          // channels per chunk (16 pairs per half-warp)
+constexpr int NTHREADS = 256;   // 8 warps = 16 half-warp workers
+constexpr int W_BYTES = 49 * CH * 4;          // one chunk of tap-major weights
+constexpr int W_STRIDE = 6400;                // padded to a multiple of 128 B
 
-enum { MODE_FWD_LN = 0, MODE_DGRAD = 1 };
+enum { MODE_FWD = 0, MODE_DGRAD = 1 };
 
-template <int TH, int CPW>
-struct DwTile {
-  static constexpr int TW = NWARP * CPW;
-  static constexpr int HH = TH + 6;
-  static constexpr int HW = TW + 6;
-  static constexpr int HALO_FLOATS = HH * HW * CH;
-  static constexpr int W_FLOATS = CH * 49;
+template <int TH_, int CPW_, int WX_, bool IMG_>
+struct Geo {
+  static constexpr int TH = TH_, CPW = CPW_, WX = WX_;
+  static constexpr bool IMG = IMG_;
+  static constexpr int WY = 16 / WX;
+  static constexpr int TW = WX * CPW;                 // output columns per tile
+  static constexpr int ROWS = IMG ? TH : WY * TH;     // output rows per tile (per image)
+  static constexpr int NB = IMG ? WY : 1;             // images per tile
+  static constexpr int HH = ROWS + 6, HW = TW + 6;
+  static constexpr int HALO_ELEMS = NB * HH * HW * CH;
+  static constexpr int TILE_ELEMS = NB * ROWS * TW * CH;
 };
 
-// load one 32-channel chunk of the halo tile into shared memory as fp32 (zero outside the image)
-template <typename TIN, int HH, int HW>
-__device__ __forceinline__ void load_halo(float* __restrict__ sm, const TIN* __restrict__ img, int64_t H, int64_t W,
-                                          int64_t C, int y0, int x0, int c0) {
-  // 8 lanes x 4 channels cover the 32-channel chunk of one pixel; a warp covers 4 pixels per pass
-  const int sub = threadIdx.x & 7;          // which 4-channel group
-  const int pl = threadIdx.x >> 3;          // pixel slot 0..31
-  for (int p = pl; p < HH * HW; p += 32) {
-    int iy = p / HW, ix = p - iy * HW;
-    int gy = y0 + iy - 3, gx = x0 + ix - 3;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) load4(img + ((int64_t)gy * W + gx) * C + c0 + sub * 4, v);
-    *reinterpret_cast<float4*>(sm + p * CH + sub * 4) = make_float4(v[0], v[1], v[2], v[3]);
-  }
+// ---- PTX wrappers (same idioms as gemm_tc.cu) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-// The register-tiled 7x7 correlation for one chunk: acc[q][r] for output column (CPW*warp+q), row r.
-template <int TH, int CPW, bool FLIP>
-__device__ __forceinline__ void conv_chunk(const float* __restrict__ halo, const float* __restrict__ wsm, int warp,
-                                           int lane, float (&acc)[CPW][TH]) {
-  constexpr int HW = NWARP * CPW + 6;
-  float wr[49];
-#pragma unroll
-  for (int t = 0; t < 49; ++t) wr[t] = wsm[lane * 49 + (FLIP ? 48 - t : t)];
-#pragma unroll
-  for (int q = 0; q < CPW; ++q)
-#pragma unroll
-    for (int r = 0; r < TH; ++r) acc[q][r] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 6 + CPW; ++j) {           // input column CPW*warp + j of the halo tile
-#pragma unroll
-    for (int iy = 0; iy < TH + 6; ++iy) {
-      float v = halo[(iy * HW + CPW * warp + j) * CH + lane];
-#pragma unroll
-      for (int q = 0; q < CPW; ++q) {
-        const int kx = j - q;                   // tap column for output column q
-        if (kx >= 0 && kx <= 6) {
-#pragma unroll
-          for (int ky = 0; ky < 7; ++ky) {
-            const int r = iy - ky;
-            if (r >= 0 && r < TH) acc[q][r] = fmaf(v, wr[ky * 7 + kx], acc[q][r]);
-          }
-        }
-      }
-    }
-  }
+// channel-pair loads from a [pixel][32 ch] shared-memory tile
+__device__ __forceinline__ float2 ld_pair(const float* sm, int idx) { return *reinterpret_cast<const float2*>(sm + idx); }
+__device__ __forceinline__ float2 ld_pair(const bf16* sm, int idx) {
+  uint32_t u = *reinterpret_cast<const uint32_t*>(sm + idx);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void st_pair(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void st_pair(bf16* p, float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162*>(p) = h;
+}
+__device__ __forceinline__ float2 ldg_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ldg_pair(const bf16* p) {
+  uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
-// ------------------------------------------------------------------------------------------------
-// forward: dwconv + bias + LayerNorm
-// grid = (tiles_x * tiles_y, N); dynamic smem = halo + weights + ytile[TH*TW][C] (TACT) + stats
-// ------------------------------------------------------------------------------------------------
-template <typename TIN, typename TACT, int TH, int CPW>
-__global__ void __launch_bounds__(NWARP * 32) dwconv7_ln_fwd_kernel(
-    const TIN* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int64_t H, int64_t W, int64_t C,
-    int tiles_x, TACT* __restrict__ y, TACT* __restrict__ xn, float* __restrict__ mean_out,
-    float* __restrict__ rstd_out) {
-  typedef DwTile<TH, CPW> T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* halo = reinterpret_cast<float*>(smem_raw);
-  float* wsm = halo + T::HALO_FLOATS;
-  float* stat = wsm + T::W_FLOATS;                       // [TH*TW][2] mean, rstd
-  TACT* ytile = reinterpret_cast<TACT*>(stat + TH * T::TW * 2);
+struct TileCoord { int n0, y0, x0; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * TH, x0 = tx * T::TW;
-  const int64_t n = blockIdx.y;
-  const TIN* img = x + n * H * W * C;
-
-  for (int c0 = 0; c0 < C; c0 += CH) {
-    __syncthreads();                                     // previous chunk's readers are done
-    load_halo<TIN, T::HH, T::HW>(halo, img, H, W, C, y0, x0, c0);
-    for (int i = threadIdx.x; i < T::W_FLOATS; i += NWARP * 32) wsm[i] = w[(int64_t)c0 * 49 + i];
-    __syncthreads();
-    float acc[CPW][TH];
-    conv_chunk<TH, CPW, false>(halo, wsm, warp, lane, acc);
-    const float b = bias[c0 + lane];
-#pragma unroll
-    for (int q = 0; q < CPW; ++q)
-#pragma unroll
-      for (int r = 0; r < TH; ++r) {
-        int p = r * T::TW + CPW * warp + q;
-        ytile[(int64_t)p * C + c0 + lane] = from_f32<TACT>(acc[q][r] + b);
-      }
-  }
-  __syncthreads();
-
-  // per-pixel statistics: one warp per pixel, two-pass (mean, then biased variance) in fp32
-  for (int p = warp; p < TH * T::TW; p += NWARP) {
-    const TACT* row = ytile + (int64_t)p * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += to_f32(row[c]);
-    s = warp_sum(s);
-    const float mu = s / (float)C;
-    float q = 0.f;
-    for (int c = lane; c < C; c += 32) { float d = to_f32(row[c]) - mu; q = fmaf(d, d, q); }
-    q = warp_sum(q);
-    const float rs = rsqrtf(q / (float)C + eps);
-    if (lane == 0) {
-      stat[2 * p] = mu;
-      stat[2 * p + 1] = rs;
-      int r = p / T::TW, cx = p - r * T::TW;
-      int gy = y0 + r, gx = x0 + cx;
-      if (gy < H && gx < W) {
-        int64_t m = (n * H + gy) * W + gx;
-        mean_out[m] = mu;
-        rstd_out[m] = rs;
-      }
-    }
-  }
-  __syncthreads();
-
-  // write y and xn: flattened (pixel, 8-channel vector) so every lane stores 16 B (bf16) / 32 B (fp32)
-  const int vec_per_px = (int)(C >> 3);
-  const int total = TH * T::TW * vec_per_px;
-  for (int i = threadIdx.x; i < total; i += NWARP * 32) {
-    int p = i / vec_per_px, cv = (i - p * vec_per_px) << 3;
-    int r = p / T::TW, cx = p - r * T::TW;
-    int gy = y0 + r, gx = x0 + cx;
-    if (gy >= H || gx >= W) continue;
-    float v[8], o[8];
-    load8(ytile + (int64_t)p * C + cv, v);
-    const float mu = stat[2 * p], rs = stat[2 * p + 1];
-    float lw[8], lb[8];
-    load8(ln_w + cv, lw);
-    load8(ln_b + cv, lb);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf((v[k] - mu) * rs, lw[k], lb[k]);
-    int64_t off = ((n * H + gy) * W + gx) * C + cv;
-    store8(y + off, v);
-    store8(xn + off, o);
-  }
+template <class G>
+__device__ __forceinline__ TileCoord decode_tile(int tile, int tiles_x, int tiles_y) {
+  TileCoord t;
+  int tx = tile % tiles_x;
+  int r = tile / tiles_x;
+  int ty = r % tiles_y;
+  t.n0 = (r / tiles_y) * G::NB;
+  t.y0 = ty * G::ROWS;
+  t.x0 = tx * G::TW;
+  return t;
 }
 
-// ------------------------------------------------------------------------------------------------
-// backward-data: dx = dres + corr(dy, flipped w).  Output written straight from registers
-// (32 lanes x 4 B = one 128-byte line per pixel-chunk for an fp32 residual stream).
-// ------------------------------------------------------------------------------------------------
-template <typename TIN, typename TOUT, int TH, int CPW>
-__global__ void __launch_bounds__(NWARP * 32) dwconv7_dgrad_kernel(const TIN* __restrict__ dy,
-                                                                    const float* __restrict__ w,
-                                                                    const TOUT* __restrict__ dres, int64_t H, int64_t W,
-                                                                    int64_t C, int tiles_x, TOUT* __restrict__ dx) {
-  typedef DwTile<TH, CPW> T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* halo = reinterpret_cast<float*>(smem_raw);
-  float* wsm = halo + T::HALO_FLOATS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * TH, x0 = tx * T::TW;
-  const int64_t n = blockIdx.y;
-  const TIN* img = dy + n * H * W * C;
-  for (int c0 = 0; c0 < C; c0 += CH) {
-    __syncthreads();
-    load_halo<TIN, T::HH, T::HW>(halo, img, H, W, C, y0, x0, c0);
-    for (int i = threadIdx.x; i < T::W_FLOATS; i += NWARP * 32) wsm[i] = w[(int64_t)c0 * 49 + i];
-    __syncthreads();
-    float acc[CPW][TH];
-    conv_chunk<TH, CPW, true>(halo, wsm, warp, lane, acc);
+// The register-tiled 7x7 correlation for one 32-channel chunk: acc[q][r] for output column (col0+q), row (row0+r).
+template <class G, typename TS, bool FLIP>
+__device__ __forceinline__ void conv_chunk(const TS* __restrict__ halo, const float* __restrict__ wsm, int base, int cp,
+                                           float2 (&acc)[G::CPW][G::TH]) {
+  float2 wr[49];
 #pragma unroll
-    for (int q = 0; q < CPW; ++q) {
-      int gx = x0 + CPW * warp + q;
-      if (gx >= W) continue;
+  for (int t = 0; t < 49; ++t) wr[t] = *reinterpret_cast<const float2*>(wsm + (FLIP ? 48 - t : t) * CH + 2 * cp);
 #pragma unroll
-      for (int r = 0; r < TH; ++r) {
-        int gy = y0 + r;
-        if (gy >= H) continue;
-        int64_t off = ((n * H + gy) * W + gx) * C + c0 + lane;
-        float v = acc[q][r];
-        if (dres) v += to_f32(dres[off]);
-        dx[off] = from_f32<TOUT>(v);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward-weights (+bias): persistent CTAs, each bound to one 32-channel chunk; 49 tap accumulators
-// + 1 bias accumulator per thread live in registers across all the tiles the CTA visits, then the 8
-// warps are summed through shared memory and one partial row [50, 32] is written per CTA.
-// grid = rows * nchunks;  CTA b: chunk = b % nchunks, row = b / nchunks.
-// ------------------------------------------------------------------------------------------------
-template <typename TDY, typename TX, int TH, int CPW>
-__global__ void __launch_bounds__(NWARP * 32) dwconv7_wgrad_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x,
-                                                                    int64_t N, int64_t H, int64_t W, int64_t C,
-                                                                    int tiles_x, int tiles_y, int rows,
-                                                                    float* __restrict__ partial) {
-  typedef DwTile<TH, CPW> T;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* halo = reinterpret_cast<float*>(smem_raw);                 // x halo tile
-  float* dsm = halo + T::HALO_FLOATS;                                // dy tile [TH][TW][32]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunks = (int)(C / CH);
-  const int chunk = blockIdx.x % nchunks, row = blockIdx.x / nchunks;
-  const int c0 = chunk * CH;
-  const int64_t tiles_per_img = (int64_t)tiles_x * tiles_y;
-  const int64_t ntiles = N * tiles_per_img;
-
-  float accw[49];
+  for (int q = 0; q < G::CPW; ++q)
 #pragma unroll
-  for (int t = 0; t < 49; ++t) accw[t] = 0.f;
-  float accb = 0.f;
-
-  for (int64_t tile = row; tile < ntiles; tile += rows) {
-    const int64_t n = tile / tiles_per_img;
-    const int tt = (int)(tile - n * tiles_per_img);
-    const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-    const int y0 = ty * TH, x0 = tx * T::TW;
-    __syncthreads();
-    load_halo<TX, T::HH, T::HW>(halo, x + n * H * W * C, H, W, C, y0, x0, c0);
-    {
-      const TDY* img = dy + n * H * W * C;
-      const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-      for (int p = pl; p < TH * T::TW; p += 32) {
-        int r = p / T::TW, cx = p - r * T::TW;
-        int gy = y0 + r, gx = x0 + cx;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (gy < H && gx < W) load4(img + ((int64_t)gy * W + gx) * C + c0 + sub * 4, v);
-        *reinterpret_cast<float4*>(dsm + p * CH + sub * 4) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-    }
-    __syncthreads();
-    float d[CPW][TH];
+    for (int r = 0; r < G::TH; ++r) acc[q][r] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < CPW; ++q)
+  for (int j = 0; j < 6 + G::CPW; ++j) {
 #pragma unroll
-      for (int r = 0; r < TH; ++r) {
-        d[q][r] = dsm[(r * T::TW + CPW * warp + q) * CH + lane];
-        accb += d[q][r];
-      }
+    for (int iy = 0; iy < G::TH + 6; ++iy) {
+      const float2 v = ld_pair(halo, base + (iy * G::HW + j) * CH);
 #pragma unroll
-    for (int j = 0; j < 6 + CPW; ++j) {
-      float xc[TH + 6];
-#pragma unroll
-      for (int iy = 0; iy < TH + 6; ++iy) xc[iy] = halo[(iy * T::HW + CPW * warp + j) * CH + lane];
-#pragma unroll
-      for (int q = 0; q < CPW; ++q) {
+      for (int q = 0; q < G::CPW; ++q) {
         const int kx = j - q;
         if (kx >= 0 && kx <= 6) {
 #pragma unroll
           for (int ky = 0; ky < 7; ++ky) {
-            float s = accw[ky * 7 + kx];
-#pragma unroll
-            for (int r = 0; r < TH; ++r) s = fmaf(d[q][r], xc[r + ky], s);
-            accw[ky * 7 + kx] = s;
+            const int r = iy - ky;
+            if (r >= 0 && r < G::TH) acc[q][r] = __ffma2_rn(v, wr[ky * 7 + kx], acc[q][r]);
           }
         }
       }
     }
   }
-  // cross-warp reduction through shared memory (fixed order), then one partial row per CTA
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward (MODE_FWD):  y = conv(x) + bias -> TOUT ; then per-tile LayerNorm -> xn, mean, rstd
+// dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT
+// ------------------------------------------------------------------------------------------------
+template <class G, int MODE, typename TIN, typename TOUT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int N, int H, int W, int C,
+               int tiles_x, int tiles_y, int ntiles, const float* __restrict__ bias, const TOUT* __restrict__ dres,
+               TOUT* __restrict__ out, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+               TOUT* __restrict__ xn, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int HALO_BYTES = G::HALO_ELEMS * (int)sizeof(TIN);
+  constexpr int STAGE_BYTES = ((HALO_BYTES + 127) / 128) * 128 + W_STRIDE;
+  const uint32_t base_u = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* base_p = smem_raw + (base_u - smem_u32(smem_raw));
+  const uint32_t bars = base_u + 2 * STAGE_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int worker = warp * 2 + (lane >> 4), cp = lane & 15;
+  const int wx = worker % G::WX, wy = worker / G::WX;
+  const int row0 = G::IMG ? 0 : wy * G::TH;
+  const int img = G::IMG ? wy : 0;
+  const int col0 = wx * G::CPW;
+  const int hbase = ((img * G::HH + row0) * G::HW + col0) * CH + 2 * cp;
+
+  const int nchunks = C / CH;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = my_tiles * nchunks;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
-  float* red = halo;                       // [NWARP][50][32]
+
+  auto issue = [&](int g) {
+    const int i = g / nchunks, k = g - i * nchunks;
+    const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
+    const int s = g & 1;
+    const uint32_t dst = base_u + s * STAGE_BYTES;
+    mbar_expect_tx(bars + 8 * s, HALO_BYTES + W_BYTES);
+    tma_load_4d(dst, &tmX, bars + 8 * s, k * CH, t.x0 - 3, t.y0 - 3, t.n0);
+    tma_load_2d(dst + STAGE_BYTES - W_STRIDE, &tmW, bars + 8 * s, k * CH, 0);
+  };
+  if (tid == 0) {
+    if (total > 0) issue(0);
+    if (total > 1) issue(1);
+  }
+
+  for (int g = 0; g < total; ++g) {
+    const int i = g / nchunks, k = g - i * nchunks;
+    const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
+    const int s = g & 1;
+    mbar_wait(bars + 8 * s, (uint32_t)((g >> 1) & 1));
+    const TIN* halo = reinterpret_cast<const TIN*>(base_p + s * STAGE_BYTES);
+    const float* wsm = reinterpret_cast<const float*>(base_p + s * STAGE_BYTES + STAGE_BYTES - W_STRIDE);
+    float2 acc[G::CPW][G::TH];
+    conv_chunk<G, TIN, MODE == MODE_DGRAD>(halo, wsm, hbase, cp, acc);
+
+    const int c = k * CH + 2 * cp;
+    const int n = t.n0 + img;
+    float2 b2 = make_float2(0.f, 0.f);
+    if (MODE == MODE_FWD) b2 = __ldg(reinterpret_cast<const float2*>(bias + c));
+    if (n < N) {
 #pragma unroll
-  for (int t = 0; t < 49; ++t) red[(warp * 50 + t) * CH + lane] = accw[t];
-  red[(warp * 50 + 49) * CH + lane] = accb;
+      for (int q = 0; q < G::CPW; ++q) {
+        const int gx = t.x0 + col0 + q;
+        if (gx < W) {
+#pragma unroll
+          for (int r = 0; r < G::TH; ++r) {
+            const int gy = t.y0 + row0 + r;
+            if (gy < H) {
+              const int64_t off = (((int64_t)n * H + gy) * W + gx) * C + c;
+              float2 v = acc[q][r];
+              if (MODE == MODE_FWD) { v.x += b2.x; v.y += b2.y; }
+              else if (dres) { float2 d = ldg_pair(dres + off); v.x += d.x; v.y += d.y; }
+              st_pair(out + off, v);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                     // every warp is done with stage s (and y of this chunk is written)
+    if (tid == 0 && g + 2 < total) issue(g + 2);
+
+    if (MODE == MODE_FWD && k == nchunks - 1) {
+      // ---- LayerNorm over C for the pixels of this tile: one warp per pixel, 4 pixels in flight per warp ----
+      constexpr int P = G::NB * G::ROWS * G::TW;
+      const int nvec = C >> 2;           // 4-element vectors per pixel row
+      for (int p0 = warp * 4; p0 < P; p0 += 8 * 4) {
+        // up to 4 pixels; rows of up to 2048 channels are walked in 128-channel steps
+        float s1[4] = {0.f, 0.f, 0.f, 0.f};
+        int64_t moff[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u;
+          const int b = p / (G::ROWS * G::TW), rr = (p / G::TW) % G::ROWS, cx = p % G::TW;
+          const int nn = t.n0 + b, gy = t.y0 + rr, gx = t.x0 + cx;
+          ok[u] = (p < P) && nn < N && gy < H && gx < W;
+          moff[u] = ok[u] ? (((int64_t)nn * H + gy) * W + gx) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const TOUT* row = out + moff[u] * C;
+          for (int v = lane; v < nvec; v += 32) {
+            float a[4];
+            if (sizeof(TOUT) == 2) {
+              uint2 raw = __ldcg(reinterpret_cast<const uint2*>(row + v * 4));
+              a[0] = __uint_as_float(raw.x << 16); a[1] = __uint_as_float(raw.x & 0xffff0000u);
+              a[2] = __uint_as_float(raw.y << 16); a[3] = __uint_as_float(raw.y & 0xffff0000u);
+            } else {
+              float4 raw = __ldcg(reinterpret_cast<const float4*>(row + v * 4));
+              a[0] = raw.x; a[1] = raw.y; a[2] = raw.z; a[3] = raw.w;
+            }
+            s1[u] += (a[0] + a[1]) + (a[2] + a[3]);
+          }
+        }
+        float mu[4], rs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mu[u] = warp_sum(s1[u]) / (float)C;
+        float s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const TOUT* row = out + moff[u] * C;
+          for (int v = lane; v < nvec; v += 32) {
+            float a[4];
+            load4(row + v * 4, a);      // second pass: L1/L2 hit
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { float d = a[e] - mu[u]; s2[u] = fmaf(d, d, s2[u]); }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) rs[u] = rsqrtf(warp_sum(s2[u]) / (float)C + eps);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const TOUT* row = out + moff[u] * C;
+          TOUT* orow = xn + moff[u] * C;
+          for (int v = lane; v < nvec; v += 32) {
+            float a[4], lw[4], lb[4], o[4];
+            load4(row + v * 4, a);
+            load4(ln_w + v * 4, lw);
+            load4(ln_b + v * 4, lb);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = fmaf((a[e] - mu[u]) * rs[u], lw[e], lb[e]);
+            store4(orow + v * 4, o);
+          }
+          if (lane == 0) { mean_out[moff[u]] = mu[u]; rstd_out[moff[u]] = rs[u]; }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward-weights (+bias): persistent CTAs, each bound to one 32-channel chunk; 49 tap-pair accumulators
+// + 1 bias pair per thread live in registers across all the tiles the CTA visits (x halo tile and dy tile
+// arrive by TMA, double-buffered), then the 16 workers are summed through shared memory in a fixed order
+// and one partial row [50, 32] is written per CTA.   grid = rows * nchunks: chunk = b % nchunks, row = b / nchunks.
+// ------------------------------------------------------------------------------------------------
+template <class G, typename TDY, typename TX>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, int N, int H, int W,
+                     int C, int tiles_x, int tiles_y, int ntiles, int rows, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int HALO_BYTES = G::HALO_ELEMS * (int)sizeof(TX);
+  constexpr int DY_BYTES = G::TILE_ELEMS * (int)sizeof(TDY);
+  constexpr int HALO_PAD = ((HALO_BYTES + 127) / 128) * 128;
+  constexpr int STAGE_BYTES = HALO_PAD + ((DY_BYTES + 127) / 128) * 128;
+  const uint32_t base_u = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* base_p = smem_raw + (base_u - smem_u32(smem_raw));
+  const uint32_t bars = base_u + 2 * STAGE_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int worker = warp * 2 + (lane >> 4), cp = lane & 15;
+  const int wx = worker % G::WX, wy = worker / G::WX;
+  const int row0 = G::IMG ? 0 : wy * G::TH;
+  const int img = G::IMG ? wy : 0;
+  const int col0 = wx * G::CPW;
+  const int hbase = ((img * G::HH + row0) * G::HW + col0) * CH + 2 * cp;
+  const int dbase = ((img * G::ROWS + row0) * G::TW + col0) * CH + 2 * cp;
+
+  const int nchunks = C / CH;
+  const int chunk = (int)blockIdx.x % nchunks, row = (int)blockIdx.x / nchunks;
+  const int my_tiles = (row < ntiles) ? (ntiles - row + rows - 1) / rows : 0;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    mbar_init(bars, 1);
+    mbar_init(bars + 8, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 50 * CH; i += NWARP * 32) {
-    float s = 0.f;
+
+  auto issue = [&](int g) {
+    const TileCoord t = decode_tile<G>(row + g * rows, tiles_x, tiles_y);
+    const int s = g & 1;
+    const uint32_t dst = base_u + s * STAGE_BYTES;
+    mbar_expect_tx(bars + 8 * s, HALO_BYTES + DY_BYTES);
+    tma_load_4d(dst, &tmX, bars + 8 * s, chunk * CH, t.x0 - 3, t.y0 - 3, t.n0);
+    tma_load_4d(dst + HALO_PAD, &tmDY, bars + 8 * s, chunk * CH, t.x0, t.y0, t.n0);
+  };
+  if (tid == 0) {
+    if (my_tiles > 0) issue(0);
+    if (my_tiles > 1) issue(1);
+  }
+
+  float2 accw[49];
 #pragma unroll
-    for (int wv = 0; wv < NWARP; ++wv) s += red[wv * 50 * CH + i];
-    int t = i / CH, l = i - t * CH;
-    partial[((int64_t)row * 50 + t) * C + c0 + l] = s;
+  for (int t = 0; t < 49; ++t) accw[t] = make_float2(0.f, 0.f);
+  float2 accb = make_float2(0.f, 0.f);
+
+  for (int g = 0; g < my_tiles; ++g) {
+    const int s = g & 1;
+    mbar_wait(bars + 8 * s, (uint32_t)((g >> 1) & 1));
+    const TX* halo = reinterpret_cast<const TX*>(base_p + s * STAGE_BYTES);
+    const TDY* dsm = reinterpret_cast<const TDY*>(base_p + s * STAGE_BYTES + HALO_PAD);
+    // dy outside the image is zero-filled by TMA, so no masking is needed
+    float2 d[G::CPW][G::TH];
+#pragma unroll
+    for (int q = 0; q < G::CPW; ++q)
+#pragma unroll
+      for (int r = 0; r < G::TH; ++r) {
+        d[q][r] = ld_pair(dsm, dbase + (r * G::TW + q) * CH);
+        accb.x += d[q][r].x;
+        accb.y += d[q][r].y;
+      }
+#pragma unroll
+    for (int j = 0; j < 6 + G::CPW; ++j) {
+#pragma unroll
+      for (int iy = 0; iy < G::TH + 6; ++iy) {
+        const float2 v = ld_pair(halo, hbase + (iy * G::HW + j) * CH);
+#pragma unroll
+        for (int q = 0; q < G::CPW; ++q) {
+          const int kx = j - q;
+          if (kx >= 0 && kx <= 6) {
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) {
+              const int r = iy - ky;
+              if (r >= 0 && r < G::TH) accw[ky * 7 + kx] = __ffma2_rn(d[q][r], v, accw[ky * 7 + kx]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && g + 2 < my_tiles) issue(g + 2);
+  }
+  // cross-worker reduction through shared memory (fixed order), then one partial row per CTA
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(base_p);          // [16 workers][50][32]  = 102400 B (fits in the two stages)
+#pragma unroll
+  for (int t = 0; t < 49; ++t) *reinterpret_cast<float2*>(red + (worker * 50 + t) * CH + 2 * cp) = accw[t];
+  *reinterpret_cast<float2*>(red + (worker * 50 + 49) * CH + 2 * cp) = accb;
+  __syncthreads();
+  for (int i = tid; i < 50 * CH; i += NTHREADS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 16; ++wv) sum += red[wv * 50 * CH + i];
+    const int t = i / CH, l = i - t * CH;
+    partial[((int64_t)row * 50 + t) * C + chunk * CH + l] = sum;
   }
 }
 
@@ -321,24 +438,66 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_finalize_kernel(const float
   }
 }
 
-// ---- host-side configuration ------------------------------------------------------------------
-struct DwCfg { int th, cpw; };
+// w [C][49] -> wt [49][C]
+__global__ void __launch_bounds__(256) weight_transpose_kernel(const float* __restrict__ w, int64_t C, float* __restrict__ wt) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= 49 * C) return;
+  int64_t t = i / C, c = i - t * C;
+  wt[i] = w[c * 49 + t];
+}
 
-static inline size_t fwd_smem(int th, int cpw, int64_t C, int act_size) {
-  int tw = NWARP * cpw;
-  return (size_t)((th + 6) * (tw + 6) * CH + CH * 49 + th * tw * 2) * 4 + (size_t)th * tw * C * act_size;
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
 }
-static inline size_t dgrad_smem(int th, int cpw) {
-  int tw = NWARP * cpw;
-  return (size_t)((th + 6) * (tw + 6) * CH + CH * 49) * 4;
+
+// channels-last activation [N][H][W][C]: 4-D map {C, W, H, N}, box {32, bw, bh, bn}, no swizzle, OOB -> zeros
+static int make_map_nhwc(CUtensorMap* map, const void* ptr, int dtype, int64_t N, int64_t H, int64_t W, int64_t C, int bw,
+                         int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  CNX_REQUIRE(enc != nullptr, CNX_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  CNX_REQUIRE((((uintptr_t)ptr) & 15) == 0, CNX_E_SHAPE, "dwconv: activation pointer must be 16-byte aligned");
+  const cuuint64_t e = (cuuint64_t)dtype_size(dtype);
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * e, (cuuint64_t)W * C * e, (cuuint64_t)H * W * C * e};
+  cuuint32_t box[4] = {CH, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, dtype == CNX_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CNX_REQUIRE(r == CUDA_SUCCESS, CNX_E_DRIVER, "cuTensorMapEncodeTiled(nhwc) failed (%d) N=%lld H=%lld W=%lld C=%lld box=%dx%dx%d",
+              (int)r, (long long)N, (long long)H, (long long)W, (long long)C, bw, bh, bn);
+  return 0;
 }
-static inline size_t wgrad_smem(int th, int cpw) {
-  int tw = NWARP * cpw;
-  size_t a = (size_t)((th + 6) * (tw + 6) * CH + th * tw * CH) * 4;
-  size_t b = (size_t)NWARP * 50 * CH * 4;
-  return a > b ? a : b;
+// tap-major weights [49][C] fp32: 2-D map {C, 49}, box {32, 49}
+static int make_map_wt(CUtensorMap* map, const float* wt, int64_t C) {
+  EncodeTiledFn enc = get_encode();
+  CNX_REQUIRE(enc != nullptr, CNX_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  CNX_REQUIRE((((uintptr_t)wt) & 15) == 0, CNX_E_SHAPE, "dwconv: weight pointer must be 16-byte aligned");
+  cuuint64_t gdim[2] = {(cuuint64_t)C, 49};
+  cuuint64_t gstr[1] = {(cuuint64_t)C * 4};
+  cuuint32_t box[2] = {CH, 49};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(wt), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CNX_REQUIRE(r == CUDA_SUCCESS, CNX_E_DRIVER, "cuTensorMapEncodeTiled(wt) failed (%d) C=%lld", (int)r, (long long)C);
+  return 0;
 }
-constexpr size_t kMaxSmem = 227 * 1024;
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -350,104 +509,112 @@ static int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
-template <typename TIN, typename TACT, int TH, int CPW>
-static int launch_fwd(const void* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
-                      int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn, float* mean, float* rstd,
-                      cudaStream_t s) {
-  constexpr int TW = NWARP * CPW;
-  int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
-  size_t smem = fwd_smem(TH, CPW, C, sizeof(TACT));
-  auto k = dwconv7_ln_fwd_kernel<TIN, TACT, TH, CPW>;
-  if (int rc = set_smem(k, smem)) return rc;
-  dim3 grid(tiles_x * tiles_y, (unsigned)N);
-  k<<<grid, NWARP * 32, smem, s>>>((const TIN*)x, w, bias, ln_w, ln_b, eps, H, W, C, tiles_x, (TACT*)y, (TACT*)xn,
-                                   mean, rstd);
-  return check_launch("dwconv7_ln_fwd");
+// tile geometries: A = wide feature maps, B = 9..16 wide, I = whole small images (<= 8x8), 2 per tile
+typedef Geo<8, 2, 16, false> GeoA;   // 32 x 8
+typedef Geo<8, 2, 8, false> GeoB;    // 16 x 16
+typedef Geo<8, 1, 8, true> GeoI;     // 8 x 8 x 2 images
+
+template <class G, int MODE, typename TIN, typename TOUT>
+static int launch_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
+                       const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
+                       int64_t H, int64_t W, int64_t C, cudaStream_t s) {
+  CUtensorMap tmX, tmW;
+  if (int rc = make_map_nhwc(&tmX, x, x_dtype, N, H, W, C, G::HW, G::HH, G::NB)) return rc;
+  if (int rc = make_map_wt(&tmW, wt, C)) return rc;
+  constexpr size_t HALO_BYTES = (size_t)G::HALO_ELEMS * sizeof(TIN);
+  constexpr size_t STAGE = ((HALO_BYTES + 127) / 128) * 128 + W_STRIDE;
+  constexpr size_t SMEM = 2 * STAGE + 16 + 128;
+  static_assert(SMEM <= 227 * 1024, "dwconv tile does not fit in shared memory");
+  auto k = dwconv7_kernel<G, MODE, TIN, TOUT>;
+  if (int rc = set_smem(k, SMEM)) return rc;
+  const int tiles_x = (int)((W + G::TW - 1) / G::TW), tiles_y = (int)((H + G::ROWS - 1) / G::ROWS);
+  const int64_t nt = (int64_t)tiles_x * tiles_y * ((N + G::NB - 1) / G::NB);
+  CNX_REQUIRE(nt < (1ll << 30), CNX_E_SHAPE, "dwconv: too many tiles");
+  int grid = sm_count();
+  if (grid > nt) grid = (int)nt;
+  k<<<grid, NTHREADS, SMEM, s>>>(tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias, (const TOUT*)dres,
+                                 (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd);
+  return check_launch(MODE == MODE_FWD ? "dwconv7_ln_fwd" : "dwconv7_dgrad");
 }
 
-template <typename TIN, typename TACT>
-static int pick_fwd(const void* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
-                    int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn, float* mean, float* rstd,
-                    cudaStream_t s) {
-  const int es = sizeof(TACT);
-  // widest tile that fits in shared memory and is not mostly padding for this feature map
-  if (W > 8 && fwd_smem(8, 2, C, es) <= kMaxSmem)
-    return launch_fwd<TIN, TACT, 8, 2>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
-  if (H > 4 && fwd_smem(8, 1, C, es) <= kMaxSmem)
-    return launch_fwd<TIN, TACT, 8, 1>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
-  if (fwd_smem(4, 1, C, es) <= kMaxSmem)
-    return launch_fwd<TIN, TACT, 4, 1>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
-  set_error("dwconv7_ln_fwd: C=%lld does not fit in shared memory", (long long)C);
-  return CNX_E_SHAPE;
+template <int MODE, typename TIN, typename TOUT>
+static int pick_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
+                     const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
+                     int64_t H, int64_t W, int64_t C, cudaStream_t s) {
+  if (W <= 8 && H <= 8)
+    return launch_conv<GeoI, MODE, TIN, TOUT>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
+  if (W <= 16)
+    return launch_conv<GeoB, MODE, TIN, TOUT>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
+  return launch_conv<GeoA, MODE, TIN, TOUT>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
 }
 
-template <typename TIN, typename TOUT, int TH, int CPW>
-static int launch_dgrad(const void* dy, const float* w, const void* dres, void* dx, int64_t N, int64_t H, int64_t W,
-                        int64_t C, cudaStream_t s) {
-  constexpr int TW = NWARP * CPW;
-  int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
-  size_t smem = dgrad_smem(TH, CPW);
-  auto k = dwconv7_dgrad_kernel<TIN, TOUT, TH, CPW>;
-  if (int rc = set_smem(k, smem)) return rc;
-  dim3 grid(tiles_x * tiles_y, (unsigned)N);
-  k<<<grid, NWARP * 32, smem, s>>>((const TIN*)dy, w, (const TOUT*)dres, H, W, C, tiles_x, (TOUT*)dx);
-  return check_launch("dwconv7_dgrad");
-}
-
-template <typename TDY, typename TX, int TH, int CPW>
-static int launch_wgrad(const void* dy, const void* x, int64_t N, int64_t H, int64_t W, int64_t C, float* partial,
-                        int P, cudaStream_t s) {
-  constexpr int TW = NWARP * CPW;
-  int tiles_x = (int)((W + TW - 1) / TW), tiles_y = (int)((H + TH - 1) / TH);
-  size_t smem = wgrad_smem(TH, CPW);
-  auto k = dwconv7_wgrad_kernel<TDY, TX, TH, CPW>;
-  if (int rc = set_smem(k, smem)) return rc;
-  int nchunks = (int)(C / CH);
-  k<<<(unsigned)(P * nchunks), NWARP * 32, smem, s>>>((const TDY*)dy, (const TX*)x, N, H, W, C, tiles_x, tiles_y, P,
-                                                       partial);
+template <class G, typename TDY, typename TX>
+static int launch_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W, int64_t C,
+                        float* partial, int P, cudaStream_t s) {
+  CUtensorMap tmX, tmDY;
+  if (int rc = make_map_nhwc(&tmX, x, x_dtype, N, H, W, C, G::HW, G::HH, G::NB)) return rc;
+  if (int rc = make_map_nhwc(&tmDY, dy, dy_dtype, N, H, W, C, G::TW, G::ROWS, G::NB)) return rc;
+  constexpr size_t HALO_PAD = (((size_t)G::HALO_ELEMS * sizeof(TX) + 127) / 128) * 128;
+  constexpr size_t STAGE = HALO_PAD + (((size_t)G::TILE_ELEMS * sizeof(TDY) + 127) / 128) * 128;
+  constexpr size_t RED = (size_t)16 * 50 * CH * 4;
+  constexpr size_t SMEM = (2 * STAGE > RED ? 2 * STAGE : RED) + 16 + 128;
+  static_assert(SMEM <= 227 * 1024, "dwconv wgrad tile does not fit in shared memory");
+  auto k = dwconv7_wgrad_kernel<G, TDY, TX>;
+  if (int rc = set_smem(k, SMEM)) return rc;
+  const int tiles_x = (int)((W + G::TW - 1) / G::TW), tiles_y = (int)((H + G::ROWS - 1) / G::ROWS);
+  const int64_t nt = (int64_t)tiles_x * tiles_y * ((N + G::NB - 1) / G::NB);
+  CNX_REQUIRE(nt < (1ll << 30), CNX_E_SHAPE, "dwconv wgrad: too many tiles");
+  const int nchunks = (int)(C / CH);
+  k<<<(unsigned)(P * nchunks), NTHREADS, SMEM, s>>>(tmX, tmDY, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, P,
+                                                     partial);
   return check_launch("dwconv7_wgrad");
 }
 
+}  // namespace dw
 }  // namespace cnx
 
 using namespace cnx;
+using namespace cnx::dw;
 
 extern "C" {
 
-int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w,
+int cnx_dwconv7_weight_prep(const float* w, int64_t C, float* wt, void* stream) {
+  CNX_REQUIRE(w && wt && C > 0, CNX_E_BADARG, "dwconv7_weight_prep: bad argument");
+  weight_transpose_kernel<<<(unsigned)((49 * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, C, wt);
+  return check_launch("dwconv7_weight_prep");
+}
+
+int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* wt, const float* bias, const float* ln_w,
                        const float* ln_b, float eps, int64_t N, int64_t H, int64_t W, int64_t C, void* y,
                        void* xn, int act_dtype, float* mean, float* rstd, void* stream) {
-  CNX_REQUIRE(x && w && bias && ln_w && ln_b && y && xn && mean && rstd, CNX_E_BADARG, "dwconv7_ln_fwd: null pointer");
+  CNX_REQUIRE(x && wt && bias && ln_w && ln_b && y && xn && mean && rstd, CNX_E_BADARG, "dwconv7_ln_fwd: null pointer");
   CNX_REQUIRE(dtype_ok(x_dtype) && dtype_ok(act_dtype), CNX_E_BADARG, "dwconv7_ln_fwd: bad dtype");
-  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && N < 65536, CNX_E_BADARG, "dwconv7_ln_fwd: bad shape");
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_ln_fwd: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_ln_fwd: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == CNX_F32 && act_dtype == CNX_F32) return pick_fwd<float, float>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
-  if (x_dtype == CNX_F32 && act_dtype == CNX_BF16) return pick_fwd<float, bf16>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
-  if (x_dtype == CNX_BF16 && act_dtype == CNX_BF16) return pick_fwd<bf16, bf16>(x, w, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, mean, rstd, s);
+  if (x_dtype == CNX_F32 && act_dtype == CNX_F32)
+    return pick_conv<MODE_FWD, float, float>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
+  if (x_dtype == CNX_F32 && act_dtype == CNX_BF16)
+    return pick_conv<MODE_FWD, float, bf16>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
+  if (x_dtype == CNX_BF16 && act_dtype == CNX_BF16)
+    return pick_conv<MODE_FWD, bf16, bf16>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
   set_error("dwconv7_ln_fwd: bf16 stream with fp32 activations is not a supported combination");
   return CNX_E_BADARG;
 }
 
-int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* w, const void* dres, void* dx, int stream_dtype,
+int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype,
                       int64_t N, int64_t H, int64_t W, int64_t C, void* stream) {
-  CNX_REQUIRE(dy && w && dx, CNX_E_BADARG, "dwconv7_dgrad: null pointer");
+  CNX_REQUIRE(dy && wt && dx, CNX_E_BADARG, "dwconv7_dgrad: null pointer");
   CNX_REQUIRE(dtype_ok(dy_dtype) && dtype_ok(stream_dtype), CNX_E_BADARG, "dwconv7_dgrad: bad dtype");
-  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && N < 65536, CNX_E_BADARG, "dwconv7_dgrad: bad shape");
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_dgrad: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_dgrad: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool wide = W > 8;
-  const bool tall = H > 4;
-#define CNX_DG(TI, TO)                                                                              \
-  do {                                                                                              \
-    if (wide) return launch_dgrad<TI, TO, 8, 2>(dy, w, dres, dx, N, H, W, C, s);                    \
-    if (tall) return launch_dgrad<TI, TO, 8, 1>(dy, w, dres, dx, N, H, W, C, s);                    \
-    return launch_dgrad<TI, TO, 4, 1>(dy, w, dres, dx, N, H, W, C, s);                              \
-  } while (0)
-  if (dy_dtype == CNX_F32 && stream_dtype == CNX_F32) CNX_DG(float, float);
-  if (dy_dtype == CNX_BF16 && stream_dtype == CNX_F32) CNX_DG(bf16, float);
-  if (dy_dtype == CNX_BF16 && stream_dtype == CNX_BF16) CNX_DG(bf16, bf16);
-#undef CNX_DG
+  if (dy_dtype == CNX_F32 && stream_dtype == CNX_F32)
+    return pick_conv<MODE_DGRAD, float, float>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
+  if (dy_dtype == CNX_BF16 && stream_dtype == CNX_F32)
+    return pick_conv<MODE_DGRAD, bf16, float>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
+  if (dy_dtype == CNX_BF16 && stream_dtype == CNX_BF16)
+    return pick_conv<MODE_DGRAD, bf16, bf16>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
   set_error("dwconv7_dgrad: fp32 activations with a bf16 stream is not a supported combination");
   return CNX_E_BADARG;
 }
@@ -459,11 +626,11 @@ int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, 
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_wgrad: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_wgrad: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool wide = W > 8;
-#define CNX_WG(TD, TX)                                                                 \
-  do {                                                                                 \
-    if (wide) return launch_wgrad<TD, TX, 8, 2>(dy, x, N, H, W, C, partial, P, s);     \
-    return launch_wgrad<TD, TX, 8, 1>(dy, x, N, H, W, C, partial, P, s);               \
+#define CNX_WG(TD, TX)                                                                                  \
+  do {                                                                                                  \
+    if (W <= 8 && H <= 8) return launch_wgrad<GeoI, TD, TX>(dy, dy_dtype, x, x_dtype, N, H, W, C, partial, P, s); \
+    if (W <= 16) return launch_wgrad<GeoB, TD, TX>(dy, dy_dtype, x, x_dtype, N, H, W, C, partial, P, s);          \
+    return launch_wgrad<GeoA, TD, TX>(dy, dy_dtype, x, x_dtype, N, H, W, C, partial, P, s);                       \
   } while (0)
   if (dy_dtype == CNX_F32 && x_dtype == CNX_F32) CNX_WG(float, float);
   if (dy_dtype == CNX_BF16 && x_dtype == CNX_F32) CNX_WG(bf16, float);

@@ -10,6 +10,8 @@ Reference ops replaced:
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -40,13 +42,48 @@ def _num_partials() -> int:
     return L.load().cnx_sm_count() * 2
 
 
+# Kernel-side layouts of the canonical fp32 parameters (bf16 copies, transposes, tap-major conv weights) are derived
+# on the device and cached per parameter *version*: they are rebuilt only after the optimizer (or load_state_dict)
+# has written the parameter, not on every forward / accuracy-forward / backward of the same step.
+_DERIVED: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _derived(params, tag, build):
+    """params: tuple of source tensors (first one owns the cache entry)."""
+    owner = params[0]
+    key = (tag,) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
+    slot = _DERIVED.get(owner)
+    if slot is None:
+        slot = {}
+        _DERIVED[owner] = slot
+    hit = slot.get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = build()
+    slot[tag] = (key, val)
+    return val
+
+
 def _weight_prep(w: torch.Tensor, mode: int, row_scale, out_dtype) -> torch.Tensor:
-    lib = L.load()
-    R, Cc = w.shape
-    out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
-    L.check(lib.cnx_weight_prep(L.ptr(w), R, Cc, L.ptr(row_scale), mode, L.ptr(out), L.dt(out_dtype), L.stream()),
-            "weight_prep")
-    return out
+    def build():
+        lib = L.load()
+        R, Cc = w.shape
+        out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
+        L.check(lib.cnx_weight_prep(L.ptr(w), R, Cc, L.ptr(row_scale), mode, L.ptr(out), L.dt(out_dtype), L.stream()),
+                "weight_prep")
+        return out
+    return _derived((w, row_scale), ("wprep", mode, out_dtype), build)
+
+
+def _conv_weight_tap_major(conv_w: torch.Tensor) -> torch.Tensor:
+    """[C,1,7,7] -> [49,C] fp32 (what the dwconv kernels fetch by TMA)."""
+    def build():
+        lib = L.load()
+        C = conv_w.shape[0]
+        wt = torch.empty((49, C), dtype=torch.float32, device=conv_w.device)
+        L.check(lib.cnx_dwconv7_weight_prep(L.ptr(conv_w), C, L.ptr(wt), L.stream()), "dwconv7_weight_prep")
+        return wt
+    return _derived((conv_w,), ("tapmajor",), build)
 
 
 def _wgrad(X, Y, M, N1, N2, want_colsum: bool):
@@ -80,7 +117,8 @@ class _BlockFn(torch.autograd.Function):
         xn = torch.empty((M, C), dtype=act_dtype, device=dev)
         mean = torch.empty((M,), dtype=torch.float32, device=dev)
         rstd = torch.empty((M,), dtype=torch.float32, device=dev)
-        L.check(lib.cnx_dwconv7_ln_fwd(L.ptr(xl), sd, L.ptr(conv_w), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps,
+        wt = _conv_weight_tap_major(conv_w)
+        L.check(lib.cnx_dwconv7_ln_fwd(L.ptr(xl), sd, L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps,
                                        N, H, W, C, L.ptr(y), L.ptr(xn), ad, L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd")
         if act_dtype == torch.float32:
             w1a, w2a = w1, w2
@@ -160,7 +198,7 @@ class _BlockFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dxl = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
-            L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(conv_w), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
+            L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
                     "dwconv7_dgrad")
             dx = dxl.permute(0, 3, 1, 2)
         return (dx, dconv_w, dconv_b, dln[:C], dln[C:], dW1, db1, dW2, db2, dgamma, None, None, None)

@@ -119,6 +119,8 @@ class AdamW(torch.optim.Optimizer):
             L.check(lib.cnx_adamw_ema_multi(L.ptr(table), n, chunks, f(group["lr"]), f(b1), f(b2), f(group["eps"]),
                                             f(group["weight_decay"]), f(bc1), f(bc2_sqrt), f(ema_w), L.stream()),
                     "adamw_ema_multi")
+            # the kernel wrote the parameters through raw pointers: tell autograd / the derived-weight cache
+            torch.autograd.graph.increment_version(ps)
         if self._ema is not None:
             self._ema._fused_done = True
         return loss

@@ -100,10 +100,13 @@ CNX_API int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double
  * a1+a2  Block.dwconv + Block.norm (semantic_segmentation/backbone/convnext.py:34-35,45-47)
  *   y  = dwconv7x7(x) + bias              (rounded to act dtype, as autocast's conv output is)
  *   xn = LayerNorm_C(y) * ln_w + ln_b     (eps, biased variance, fp32 math; rounded to act dtype)
- *   x [N,H,W,C] stream dtype; w [C,49] fp32 (the canonical [C,1,7,7] parameter, contiguous);
+ *   x [N,H,W,C] stream dtype; wt [49,C] fp32 = the canonical [C,1,7,7] parameter in TAP-MAJOR order (made by
+ *   cnx_dwconv7_weight_prep once per weight update; the kernels fetch 32-channel slices of it by TMA);
  *   outputs y, xn [M,C] act dtype; mean, rstd [M] fp32.
  * ---------------------------------------------------------------------------------------------- */
-CNX_API int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w,
+/* w [C,49] -> wt [49,C] */
+CNX_API int cnx_dwconv7_weight_prep(const float* w, int64_t C, float* wt, void* stream);
+CNX_API int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* wt, const float* bias, const float* ln_w,
                        const float* ln_b, float eps, int64_t N, int64_t H, int64_t W, int64_t C, void* y,
                        void* xn, int act_dtype, float* mean, float* rstd, void* stream);
 
@@ -123,9 +126,9 @@ CNX_API int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtyp
 CNX_API int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream);
 
-/* dwconv backward-data (+ residual-gradient add): dx = dres + dwconv7x7_flipped(dy).  dres may be NULL.
+/* dwconv backward-data (+ residual-gradient add): dx = dres + dwconv7x7_flipped(dy).  dres may be NULL.  wt tap-major.
  * dy [M,C] act dtype; dres, dx [M,C] stream dtype. */
-CNX_API int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* w, const void* dres, void* dx, int stream_dtype,
+CNX_API int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype,
                       int64_t N, int64_t H, int64_t W, int64_t C, void* stream);
 
 /* dwconv backward-weights + bias grad: partial [P, 50, C] fp32 (taps 0..48 then bias), P CTAs (persistent). */

@@ -8,8 +8,17 @@ def _st():
     return L.stream()
 
 
+def tap_major(w):
+    lib = L.load()
+    C = w.shape[0]
+    wt = torch.empty((49, C), dtype=torch.float32, device=w.device)
+    L.check(lib.cnx_dwconv7_weight_prep(L.ptr(w.contiguous()), C, L.ptr(wt), _st()), "dwconv7_weight_prep")
+    return wt
+
+
 def dwconv7_ln_fwd(x_nhwc, w, b, ln_w, ln_b, eps, act_dtype):
     lib = L.load()
+    w = tap_major(w)
     N, H, W, C = x_nhwc.shape
     M = N * H * W
     y = torch.empty((M, C), dtype=act_dtype, device=x_nhwc.device)
@@ -46,6 +55,7 @@ def ln_bwd(dxn, y, mean, rstd, ln_w, dy_dtype, P=64):
 
 def dwconv7_dgrad(dy2, w, dres_nhwc, shape, stream_dtype):
     lib = L.load()
+    w = tap_major(w)
     N, H, W, C = shape
     dx = torch.empty((N, H, W, C), dtype=stream_dtype, device=dy2.device)
     L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy2), L.dt(dy2), L.ptr(w), L.ptr(dres_nhwc), L.ptr(dx), L.dt(stream_dtype), N, H, W, C,
