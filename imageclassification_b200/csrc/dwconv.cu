@@ -143,6 +143,79 @@ __device__ __forceinline__ void conv_chunk(const TS* __restrict__ halo, const fl
   }
 }
 
+
+// LayerNorm over C for the pixels of one tile, rows held in registers: one warp per pixel, U pixels in flight per
+// warp so that a single L2 round trip covers U rows.  NV = 128-channel steps per row (C <= 128*NV).
+template <class G, int NV, int U, typename TOUT>
+__device__ __forceinline__ void ln_tile_regs(const TileCoord& t, int N, int H, int W, int C, const TOUT* __restrict__ y,
+                                             const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
+                                             TOUT* __restrict__ xn, float* __restrict__ mean_out,
+                                             float* __restrict__ rstd_out, int warp, int lane) {
+  constexpr int P = G::NB * G::ROWS * G::TW;
+  const int nvec = C >> 2;
+  float lw[NV][4], lb[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nvec) { load4(ln_w + v * 4, lw[j]); load4(ln_b + v * 4, lb[j]); }
+  }
+  const float invC = 1.0f / (float)C;
+  for (int p0 = warp * U; p0 < P; p0 += 8 * U) {
+    float a[U][NV][4];
+    int64_t moff[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u;
+      const int b = p / (G::ROWS * G::TW), rr = (p / G::TW) % G::ROWS, cx = p % G::TW;
+      const int nn = t.n0 + b, gy = t.y0 + rr, gx = t.x0 + cx;
+      ok[u] = (p < P) && nn < N && gy < H && gx < W;
+      moff[u] = ok[u] ? (((int64_t)nn * H + gy) * W + gx) : 0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int v = lane + 32 * j;
+        if (ok[u] && v < nvec) load4(y + moff[u] * C + v * 4, a[u][j]);
+        else { a[u][j][0] = a[u][j][1] = a[u][j][2] = a[u][j][3] = 0.f; }
+      }
+    }
+    float mu[U], rs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) s1 += (a[u][j][0] + a[u][j][1]) + (a[u][j][2] + a[u][j][3]);
+      mu[u] = warp_sum(s1) * invC;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (lane + 32 * j < nvec) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float d = a[u][j][e] - mu[u]; s2 = fmaf(d, d, s2); }
+        }
+      }
+      rs[u] = rsqrtf(warp_sum(s2) * invC + eps);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int v = lane + 32 * j;
+        if (v < nvec) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = fmaf((a[u][j][e] - mu[u]) * rs[u], lw[j][e], lb[j][e]);
+          store4(xn + moff[u] * C + v * 4, o);
+        }
+      }
+      if (lane == 0) { mean_out[moff[u]] = mu[u]; rstd_out[moff[u]] = rs[u]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward (MODE_FWD):  y = conv(x) + bias -> TOUT ; then per-tile LayerNorm -> xn, mean, rstd
 // dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT
@@ -202,13 +275,29 @@ dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     mbar_wait(bars + 8 * s, (uint32_t)((g >> 1) & 1));
     const TIN* halo = reinterpret_cast<const TIN*>(base_p + s * STAGE_BYTES);
     const float* wsm = reinterpret_cast<const float*>(base_p + s * STAGE_BYTES + STAGE_BYTES - W_STRIDE);
-    float2 acc[G::CPW][G::TH];
-    conv_chunk<G, TIN, MODE == MODE_DGRAD>(halo, wsm, hbase, cp, acc);
-
     const int c = k * CH + 2 * cp;
     const int n = t.n0 + img;
     float2 b2 = make_float2(0.f, 0.f);
     if (MODE == MODE_FWD) b2 = __ldg(reinterpret_cast<const float2*>(bias + c));
+    // dgrad: the residual-gradient values are fetched BEFORE the FMAs (clamped addresses, no branches), so their
+    // DRAM latency hides under the 784 packed FMAs instead of serialising 16 load->add->store chains after them
+    float2 dr[G::CPW][G::TH];
+    if (MODE == MODE_DGRAD && dres != nullptr) {
+      const int nc = n < N ? n : N - 1;
+#pragma unroll
+      for (int q = 0; q < G::CPW; ++q) {
+        int gx = t.x0 + col0 + q;
+        gx = gx < W ? gx : W - 1;
+#pragma unroll
+        for (int r = 0; r < G::TH; ++r) {
+          int gy = t.y0 + row0 + r;
+          gy = gy < H ? gy : H - 1;
+          dr[q][r] = ldg_pair(dres + (((int64_t)nc * H + gy) * W + gx) * C + c);
+        }
+      }
+    }
+    float2 acc[G::CPW][G::TH];
+    conv_chunk<G, TIN, MODE == MODE_DGRAD>(halo, wsm, hbase, cp, acc);
     if (n < N) {
 #pragma unroll
       for (int q = 0; q < G::CPW; ++q) {
@@ -221,7 +310,7 @@ dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               const int64_t off = (((int64_t)n * H + gy) * W + gx) * C + c;
               float2 v = acc[q][r];
               if (MODE == MODE_FWD) { v.x += b2.x; v.y += b2.y; }
-              else if (dres) { float2 d = ldg_pair(dres + off); v.x += d.x; v.y += d.y; }
+              else if (dres != nullptr) { v.x += dr[q][r].x; v.y += dr[q][r].y; }
               st_pair(out + off, v);
             }
           }
@@ -232,73 +321,12 @@ dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (tid == 0 && g + 2 < total) issue(g + 2);
 
     if (MODE == MODE_FWD && k == nchunks - 1) {
-      // ---- LayerNorm over C for the pixels of this tile: one warp per pixel, 4 pixels in flight per warp ----
-      constexpr int P = G::NB * G::ROWS * G::TW;
-      const int nvec = C >> 2;           // 4-element vectors per pixel row
-      for (int p0 = warp * 4; p0 < P; p0 += 8 * 4) {
-        // up to 4 pixels; rows of up to 2048 channels are walked in 128-channel steps
-        float s1[4] = {0.f, 0.f, 0.f, 0.f};
-        int64_t moff[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int p = p0 + u;
-          const int b = p / (G::ROWS * G::TW), rr = (p / G::TW) % G::ROWS, cx = p % G::TW;
-          const int nn = t.n0 + b, gy = t.y0 + rr, gx = t.x0 + cx;
-          ok[u] = (p < P) && nn < N && gy < H && gx < W;
-          moff[u] = ok[u] ? (((int64_t)nn * H + gy) * W + gx) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          const TOUT* row = out + moff[u] * C;
-          for (int v = lane; v < nvec; v += 32) {
-            float a[4];
-            if (sizeof(TOUT) == 2) {
-              uint2 raw = __ldcg(reinterpret_cast<const uint2*>(row + v * 4));
-              a[0] = __uint_as_float(raw.x << 16); a[1] = __uint_as_float(raw.x & 0xffff0000u);
-              a[2] = __uint_as_float(raw.y << 16); a[3] = __uint_as_float(raw.y & 0xffff0000u);
-            } else {
-              float4 raw = __ldcg(reinterpret_cast<const float4*>(row + v * 4));
-              a[0] = raw.x; a[1] = raw.y; a[2] = raw.z; a[3] = raw.w;
-            }
-            s1[u] += (a[0] + a[1]) + (a[2] + a[3]);
-          }
-        }
-        float mu[4], rs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mu[u] = warp_sum(s1[u]) / (float)C;
-        float s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          const TOUT* row = out + moff[u] * C;
-          for (int v = lane; v < nvec; v += 32) {
-            float a[4];
-            load4(row + v * 4, a);      // second pass: L1/L2 hit
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { float d = a[e] - mu[u]; s2[u] = fmaf(d, d, s2[u]); }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) rs[u] = rsqrtf(warp_sum(s2[u]) / (float)C + eps);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          const TOUT* row = out + moff[u] * C;
-          TOUT* orow = xn + moff[u] * C;
-          for (int v = lane; v < nvec; v += 32) {
-            float a[4], lw[4], lb[4], o[4];
-            load4(row + v * 4, a);
-            load4(ln_w + v * 4, lw);
-            load4(ln_b + v * 4, lb);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fmaf((a[e] - mu[u]) * rs[u], lw[e], lb[e]);
-            store4(orow + v * 4, o);
-          }
-          if (lane == 0) { mean_out[moff[u]] = mu[u]; rstd_out[moff[u]] = rs[u]; }
-        }
-      }
+      // ---- LayerNorm over C for the pixels of this tile (rows are L2-resident: this CTA just wrote them) ----
+      if (C <= 128) ln_tile_regs<G, 1, 8, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
+      else if (C <= 256) ln_tile_regs<G, 2, 8, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
+      else if (C <= 512) ln_tile_regs<G, 4, 4, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
+      else if (C <= 1024) ln_tile_regs<G, 8, 2, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
+      else ln_tile_regs<G, 16, 1, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
     }
   }
 }

@@ -274,6 +274,259 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+
+// ================================================================================================
+// Staged-epilogue variant for the two N = 4C GEMMs whose epilogue is the whole cost (fc1 + bias + GELU, and the
+// fc2 data gradient times GELU'): at K = C = 96 a 128x128 tile needs 6 MMAs but 16 K-elements of epilogue math.
+//   * 16 epilogue warps (4 per SM sub-partition) instead of 8: each owns one 32-lane TMEM quarter x 32 columns;
+//   * results are packed to bf16 in registers, written to a 128B-swizzled shared-memory staging tile (conflict-free
+//     16-byte stores) and leave the SM as TMA stores (cp.async.bulk.tensor) — no per-thread global addressing, ragged
+//     M tiles are clipped by the tensor map;
+//   * the GELU' input tile h[m,n] is prefetched by the TMA producer into shared memory (same swizzle) while the MMAs
+//     of the tile run;
+//   * GELU uses an erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26 on MUFU rcp/ex2): far below bf16 resolution
+//     of the stored result, a third of the instructions of erff().
+// Requires N % 128 == 0 (4C always is), bf16 operands and outputs.
+// ================================================================================================
+constexpr int kStEpiWarps = 16;
+constexpr int kStThreads = (kFirstEpiWarp + kStEpiWarps) * 32;   // 640
+constexpr int kStStages = 4;
+constexpr int kStBN = 128;
+constexpr int kStABytes = BM * BK * 2, kStBBytes = kStBN * BK * 2;
+constexpr int kStBoxBytes = BM * 128;                            // [128 rows][64 bf16] = 16 KB
+constexpr int kStSmem = kStStages * (kStABytes + kStBBytes) + 4 * kStBoxBytes + 1024 + 256;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// erf(x/sqrt2) pieces shared by GELU and GELU': returns Phi(x) and sets pdf_e = exp(-x^2/2)
+__device__ __forceinline__ float phi_fast(float x, float& pdf_e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  pdf_e = __expf(-z * z);
+  const float half_erfc = 0.5f * poly * pdf_e;             // 0.5 * erfc(|z|)
+  return x >= 0.f ? 1.0f - half_erfc : half_erfc;          // Phi(x)
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kStThreads, 1)
+gemm_tn_tc_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, int64_t M,
+                         int64_t N, int64_t K, const float* __restrict__ bias, int write_o0) {
+  constexpr int STAGES = kStStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * kStABytes;
+  const uint32_t sO0 = sB + STAGES * kStBBytes;            // 2 boxes: out0 (h / dh), one per column half
+  const uint32_t sO1 = sO0 + 2 * kStBoxBytes;              // 2 boxes: out1 (g) for BIAS_GELU, aux-in (h) for DGELU
+  const uint32_t bars = sO1 + 2 * kStBoxBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t aux_full = bars + 8u * (2 * STAGES + 4);
+  const uint32_t aux_empty = bars + 8u * (2 * STAGES + 5);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = N / kStBN;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int nkb = (int)((K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO0);
+    tma_prefetch_desc(&tmO1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kStEpiWarps); }
+    mbar_init(aux_full, 1);
+    mbar_init(aux_empty, kStEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: operand ring + (DGELU) the h tile of each output tile =====
+      int s = 0; uint32_t ph = 0; uint32_t xph = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        if (KIND == EPI_DGELU) {
+          mbar_wait(aux_empty, xph ^ 1);
+          mbar_expect_tx(aux_full, 2 * kStBoxBytes);
+          tma_load_2d(sO1, &tmO1, aux_full, (int32_t)(nt * kStBN), (int32_t)(mt * BM));
+          tma_load_2d(sO1 + kStBoxBytes, &tmO1, aux_full, (int32_t)(nt * kStBN + 64), (int32_t)(mt * BM));
+          xph ^= 1;
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kStABytes + kStBBytes);
+          tma_load_2d(sA + s * kStABytes, &tmA, full_bar(s), kb * BK, (int32_t)(mt * BM));
+          tma_load_2d(sB + s * kStBBytes, &tmB, full_bar(s), kb * BK, (int32_t)(nt * kStBN));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc(BM, kStBN, 0, 0);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(sA + s * kStABytes, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sB + s * kStBBytes, 16, 1024);
+          int64_t krem = K - (int64_t)kb * BK;
+          const int kmma = krem >= BK ? BK / 16 : (int)((krem + 15) / 16);
+          for (int k = 0; k < kmma; ++k)
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull_bar(as));
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    // ===== epilogue =====
+    const int ew = warp - kFirstEpiWarp;
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
+    const int colgroup = ew >> 2;                  // 32 columns each
+    const int boxg = colgroup >> 1, half = colgroup & 1;
+    const bool elected = (ew == boxg * 8) && lane == 0;      // one store issuer per column half
+    const int r = quarter * 32 + lane;             // row within the tile
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t o0 = sO0 + boxg * kStBoxBytes + row_off;
+    const uint32_t o1 = sO1 + boxg * kStBoxBytes + row_off;
+    int as = 0; uint32_t aph = 0; uint32_t xph = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + as * 128 + ((uint32_t)(quarter * 32) << 16) + colgroup * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));            // accumulator buffer is free for tile+2
+      if (++as == 2) { as = 0; aph ^= 1; }
+
+      uint32_t p0[16], p1[16];
+      if (KIND == EPI_BIAS_GELU) {
+        const float* bp = bias + nt * kStBN + colgroup * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+          const uint32_t ha = pack_bf16(v[i] + b4.x, v[i + 1] + b4.y);     // h rounded to bf16, as autocast's Linear output
+          const uint32_t hb = pack_bf16(v[i + 2] + b4.z, v[i + 3] + b4.w);
+          p0[i / 2] = ha;
+          p0[i / 2 + 1] = hb;
+          float e;
+          const float x0 = bf16_lo(ha), x1 = bf16_hi(ha), x2 = bf16_lo(hb), x3 = bf16_hi(hb);
+          p1[i / 2] = pack_bf16(x0 * phi_fast(x0, e), x1 * phi_fast(x1, e));
+          p1[i / 2 + 1] = pack_bf16(x2 * phi_fast(x2, e), x3 * phi_fast(x3, e));
+        }
+      } else {   // EPI_DGELU: out0 = acc * GELU'(h), h tile in shared memory (TMA, same 128B swizzle)
+        mbar_wait(aux_full, xph);
+        xph ^= 1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(half * 4 + c);
+          lds128(o1 + ((chunk ^ swz) << 4), p1[4 * c], p1[4 * c + 1], p1[4 * c + 2], p1[4 * c + 3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(aux_empty);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float h0 = bf16_lo(p1[i]), h1 = bf16_hi(p1[i]);
+          float e0, e1;
+          const float c0 = phi_fast(h0, e0), c1 = phi_fast(h1, e1);
+          const float g0 = fmaf(h0 * 0.39894228040143267794f, e0, c0);     // Phi(x) + x * pdf(x)
+          const float g1 = fmaf(h1 * 0.39894228040143267794f, e1, c1);
+          p0[i] = pack_bf16(v[2 * i] * g0, v[2 * i + 1] * g1);
+        }
+      }
+
+      // staging tile must not be overwritten while the previous tile's TMA store is still reading it
+      if (elected) bulk_wait_read0();
+      named_bar(1 + 2 * boxg, 256);
+      const bool st0 = (KIND == EPI_DGELU) || write_o0;
+      if (st0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(half * 4 + c);
+          sts128(o0 + ((chunk ^ swz) << 4), p0[4 * c], p0[4 * c + 1], p0[4 * c + 2], p0[4 * c + 3]);
+        }
+      }
+      if (KIND == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t chunk = (uint32_t)(half * 4 + c);
+          sts128(o1 + ((chunk ^ swz) << 4), p1[4 * c], p1[4 * c + 1], p1[4 * c + 2], p1[4 * c + 3]);
+        }
+      }
+      fence_proxy_async();
+      named_bar(2 + 2 * boxg, 256);
+      if (elected) {
+        const int32_t c0 = (int32_t)(nt * kStBN + boxg * 64), c1 = (int32_t)(mt * BM);
+        if (st0) tma_store_2d(&tmO0, sO0 + boxg * kStBoxBytes, c0, c1);
+        if (KIND == EPI_BIAS_GELU) tma_store_2d(&tmO1, sO1 + boxg * kStBoxBytes, c0, c1);
+        bulk_commit();
+      }
+    }
+    if (elected) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ================================================================================================
 // wgrad: part[split][i][j] = sum_{m in split} X[m,i] * Y[m,j] ; cs_part[split][i] = sum_m X[m,i]
 // grid = (i_tiles * j_tiles, splits).  A = X^T and B = Y^T are both MN-major operands: the TMA box is
@@ -490,12 +743,35 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
   return check_launch("gemm_tn_tc");
 }
 
+
+template <int KIND>
+static int launch_tn_staged(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  CUtensorMap tmA, tmB, tmO0, tmO1;
+  if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
+  if (int rc = make_map(&tmB, B, N, K, kStBN)) return rc;
+  // BIAS_GELU: out0 = h (optional), out1 = g.   DGELU: out0 = dh, aux = h (loaded, same box shape)
+  void* o0 = ep.out0 ? ep.out0 : ep.out1;
+  const void* o1 = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.aux;
+  if (int rc = make_map(&tmO0, o0, M, N, BM)) return rc;
+  if (int rc = make_map(&tmO1, o1, M, N, BM)) return rc;
+  auto k = gemm_tn_tc_staged_kernel<KIND>;
+  if (int rc = set_smem(k, kStSmem)) return rc;
+  int64_t tiles = ((M + BM - 1) / BM) * (N / kStBN);
+  int64_t grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  k<<<(unsigned)grid, kStThreads, kStSmem, s>>>(tmA, tmB, tmO0, tmO1, M, N, K, ep.bias, ep.out0 != nullptr ? 1 : 0);
+  return check_launch("gemm_tn_tc_staged");
+}
+
 }  // namespace tc
 
 template <int KIND, typename TOUT>
 int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
   CNX_REQUIRE(N % 8 == 0 && K % 8 == 0, CNX_E_SHAPE, "gemm_tc: N=%lld and K=%lld must be multiples of 8", (long long)N,
               (long long)K);
+  if constexpr ((KIND == EPI_BIAS_GELU || KIND == EPI_DGELU) && sizeof(TOUT) == 2) {
+    if (N % 128 == 0) return tc::launch_tn_staged<KIND>(A, B, M, N, K, ep, s);
+  }
   if (N % 128 == 0) return tc::launch_tn<128, KIND, TOUT>(A, B, M, N, K, ep, s);
   if (N % 96 == 0) return tc::launch_tn<96, KIND, TOUT>(A, B, M, N, K, ep, s);
   if (N % 64 == 0) return tc::launch_tn<64, KIND, TOUT>(A, B, M, N, K, ep, s);

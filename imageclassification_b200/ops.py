@@ -45,17 +45,18 @@ def _num_partials() -> int:
 # Kernel-side layouts of the canonical fp32 parameters (bf16 copies, transposes, tap-major conv weights) are derived
 # on the device and cached per parameter *version*: they are rebuilt only after the optimizer (or load_state_dict)
 # has written the parameter, not on every forward / accuracy-forward / backward of the same step.
-_DERIVED: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_DERIVED: dict = {}          # id(owner tensor) -> {tag: (key, derived tensor)}; entry dropped when the owner dies
 
 
 def _derived(params, tag, build):
     """params: tuple of source tensors (first one owns the cache entry)."""
     owner = params[0]
     key = (tag,) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
-    slot = _DERIVED.get(owner)
+    slot = _DERIVED.get(id(owner))
     if slot is None:
         slot = {}
-        _DERIVED[owner] = slot
+        _DERIVED[id(owner)] = slot
+        weakref.finalize(owner, _DERIVED.pop, id(owner), None)
     hit = slot.get(tag)
     if hit is not None and hit[0] == key:
         return hit[1]
