@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint,
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcnx.so")
+LIB_PATH = os.environ.get("CNX_LIB", os.path.join(_HERE, "lib", "libcnx.so"))   # CNX_LIB: kernel-variant experiments
 
 CNX_F32, CNX_BF16 = 0, 1
 CNX_GEMM_FORCE_SIMT = 1

@@ -221,7 +221,10 @@ __device__ __forceinline__ void ln_tile_regs(const TileCoord& t, int N, int H, i
 // dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT
 // ------------------------------------------------------------------------------------------------
 template <class G, int MODE, typename TIN, typename TOUT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+#ifndef CNX_DW_MINB
+#define CNX_DW_MINB 1
+#endif
+__global__ void __launch_bounds__(NTHREADS, (MODE == MODE_DGRAD ? CNX_DW_MINB : 1))
 dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int N, int H, int W, int C,
                int tiles_x, int tiles_y, int ntiles, const float* __restrict__ bias, const TOUT* __restrict__ dres,
                TOUT* __restrict__ out, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps,
@@ -320,7 +323,10 @@ dwconv7_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     __syncthreads();                     // every warp is done with stage s (and y of this chunk is written)
     if (tid == 0 && g + 2 < total) issue(g + 2);
 
-    if (MODE == MODE_FWD && k == nchunks - 1) {
+#ifndef CNX_DW_NOLN
+#define CNX_DW_NOLN 0
+#endif
+    if (MODE == MODE_FWD && k == nchunks - 1 && !CNX_DW_NOLN) {
       // ---- LayerNorm over C for the pixels of this tile (rows are L2-resident: this CTA just wrote them) ----
       if (C <= 128) ln_tile_regs<G, 1, 8, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
       else if (C <= 256) ln_tile_regs<G, 2, 8, TOUT>(t, N, H, W, C, out, ln_w, ln_b, eps, xn, mean_out, rstd_out, warp, lane);
@@ -558,7 +564,7 @@ static int launch_conv(const void* x, int x_dtype, const float* wt, const float*
   const int tiles_x = (int)((W + G::TW - 1) / G::TW), tiles_y = (int)((H + G::ROWS - 1) / G::ROWS);
   const int64_t nt = (int64_t)tiles_x * tiles_y * ((N + G::NB - 1) / G::NB);
   CNX_REQUIRE(nt < (1ll << 30), CNX_E_SHAPE, "dwconv: too many tiles");
-  int grid = sm_count();
+  int grid = sm_count() * (MODE == MODE_DGRAD ? CNX_DW_MINB : 1);
   if (grid > nt) grid = (int)nt;
   k<<<grid, NTHREADS, SMEM, s>>>(tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias, (const TOUT*)dres,
                                  (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd);

@@ -23,6 +23,7 @@ ap.add_argument("--n", type=int, default=256)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--only", default="")
 ap.add_argument("--stages", default="0,1,2,3")
+ap.add_argument("--warmup", type=int, default=3)
 args = ap.parse_args()
 dev = "cuda"
 peaks = bench._peaks()
@@ -33,7 +34,7 @@ only = set(args.only.split(",")) if args.only else None
 
 def timeit(tag, fn):
     L.TIMER = None
-    for _ in range(3):
+    for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
     recs = []
