@@ -9,9 +9,9 @@ namespace cnx {
 
 enum {
   EPI_PLAIN = 0,        // out0 = acc (+bias)                                  [out dtype = TOUT]
-  EPI_BIAS_GELU = 1,    // h = acc + b1 -> out0 (optional), g = GELU(h) -> out1 [act dtype]
+  EPI_BIAS_GELU = 1,    // h = round(acc + b1); GELU'(h) -> out0 (optional, saved for backward), g = GELU(h) -> out1 [act dtype]
   EPI_SCALE_RES = 2,    // out0 = shortcut + dp[row/rps] * gamma[n] * (acc + b2[n])  [stream dtype]
-  EPI_DGELU = 3         // out0 = acc * GELU'(h[m,n])                           [act dtype], aux = h
+  EPI_DGELU = 3         // out0 = acc * gp[m,n]                                 [act dtype], aux = gp = GELU'(h) saved by BIAS_GELU
 };
 
 struct EpiParams {
@@ -19,7 +19,7 @@ struct EpiParams {
   const float* gamma;       // [N] or null
   const float* dp;          // [num_samples] or null
   int64_t rows_per_sample;  // H*W
-  const void* aux;          // shortcut (TOUT) for SCALE_RES, h (TOUT) for DGELU
+  const void* aux;          // shortcut (TOUT) for SCALE_RES, GELU'(h) (TOUT) for DGELU
   void* out0;
   void* out1;
   int64_t ld;               // row stride of out0/out1/aux (= N)
@@ -46,8 +46,13 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int64_t m, i
       acc[i] = round_to<TOUT>(acc[i] + b[i]);
       g[i] = gelu_erf(acc[i]);
     }
-    if (p.out0) store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
     store8(reinterpret_cast<TOUT*>(p.out1) + off, g);
+    if (p.out0) {
+      // what backward needs of h is only GELU'(h): saved instead of h, so the dgrad epilogue is one multiply
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = gelu_erf_grad(acc[i]);
+      store8(reinterpret_cast<TOUT*>(p.out0) + off, g);
+    }
   } else if (KIND == EPI_SCALE_RES) {
     float s = 1.0f;
     if (p.dp) s = p.dp[m / p.rows_per_sample];
@@ -71,10 +76,10 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int64_t m, i
     for (int i = 0; i < 8; ++i) acc[i] = sc[i] + s * (gm[i] * (acc[i] + b[i]));
     store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
   } else {  // EPI_DGELU
-    float h[8];
-    load8(reinterpret_cast<const TOUT*>(p.aux) + off, h);
+    float gp[8];
+    load8(reinterpret_cast<const TOUT*>(p.aux) + off, gp);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= gelu_erf_grad(h[i]);
+    for (int i = 0; i < 8; ++i) acc[i] *= gp[i];
     store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
   }
 }

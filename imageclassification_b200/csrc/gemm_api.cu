@@ -27,10 +27,10 @@ using namespace cnx;
 extern "C" {
 
 int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64_t M, int64_t N, int64_t K,
-                           void* h_out, void* g_out, int dtype, int flags, void* stream) {
+                           void* gprime_out, void* g_out, int dtype, int flags, void* stream) {
   CNX_REQUIRE(A && W1 && b1 && g_out, CNX_E_BADARG, "gemm_bias_gelu_fwd: null pointer");
   CNX_GEMM_ARGS_OK("gemm_bias_gelu_fwd");
-  EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, h_out, g_out, N};
+  EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, gprime_out, g_out, N};
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CNX_F32) return gemm_tn_simt<float, float, EPI_BIAS_GELU>(A, W1, M, N, K, ep, s);
   if (flags & CNX_GEMM_FORCE_SIMT) return gemm_tn_simt<bf16, bf16, EPI_BIAS_GELU>(A, W1, M, N, K, ep, s);
@@ -58,11 +58,11 @@ int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float*
   return gemm_tn_tc<EPI_SCALE_RES, bf16>(A, W2, M, N, K, ep, s);
 }
 
-int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* h, void* dh, int64_t M, int64_t N,
+int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,
                             int64_t K, int dtype, int flags, void* stream) {
-  CNX_REQUIRE(dz && Bt && h && dh, CNX_E_BADARG, "gemm_dgrad_gelu_bwd: null pointer");
+  CNX_REQUIRE(dz && Bt && gprime && dh, CNX_E_BADARG, "gemm_dgrad_gelu_bwd: null pointer");
   CNX_GEMM_ARGS_OK("gemm_dgrad_gelu_bwd");
-  EpiParams ep = {nullptr, nullptr, nullptr, 1, h, dh, nullptr, N};
+  EpiParams ep = {nullptr, nullptr, nullptr, 1, gprime, dh, nullptr, N};
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == CNX_F32) return gemm_tn_simt<float, float, EPI_DGELU>(dz, Bt, M, N, K, ep, s);
   if (flags & CNX_GEMM_FORCE_SIMT) return gemm_tn_simt<bf16, bf16, EPI_DGELU>(dz, Bt, M, N, K, ep, s);

@@ -19,6 +19,7 @@
 #include "epilogue.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace cnx {
 namespace tc {
@@ -98,6 +99,59 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: one MMA spans two SMs (M = 256), each CTA feeds its own 128 rows of A and half of
+// the B tile, and holds 128 rows of the accumulator in its own TMEM ---------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(rank)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -142,38 +196,127 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN> struct TnCfg {
+// BN = columns of one output tile; NCTA = 1: one CTA owns a 128 x BN tile.  NCTA = 2: a CTA PAIR (cluster of 2, one
+// tcgen05.mma.cta_group::2 spans both SMs) owns a 256 x BN tile — each CTA stages its own 128 rows of A and HALF of the
+// B tile, so per flop a CTA moves half the bytes through L2 and shared memory that the single-CTA tile does.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Phi(x) - 0.5 = xc * P(xc^2) on |x| <= 4.5 (clamped beyond: |Phi - {0,1}| < 3.4e-6 there), degree-9 minimax fit of the
+// normal CDF, max abs error 1.4e-5 (profiles/fit_phi.py) — far below the bf16 resolution of the stored results.  No MUFU, no
+// division; evaluated two elements at a time with the packed fp32x2 FMA so the epilogue costs half the issue slots.
+__device__ __forceinline__ float2 phi_minus_half2(float2 x) {
+  const float R = 4.5f;
+  float2 xc = make_float2(fminf(fmaxf(x.x, -R), R), fminf(fmaxf(x.y, -R), R));
+  const float2 t = __fmul2_rn(xc, xc);
+  float2 p = make_float2(-1.726107430e-12f, -1.726107430e-12f);
+  p = __ffma2_rn(p, t, make_float2(2.022235545e-10f, 2.022235545e-10f));
+  p = __ffma2_rn(p, t, make_float2(-1.056632382e-08f, -1.056632382e-08f));
+  p = __ffma2_rn(p, t, make_float2(3.278768088e-07f, 3.278768088e-07f));
+  p = __ffma2_rn(p, t, make_float2(-6.813567067e-06f, -6.813567067e-06f));
+  p = __ffma2_rn(p, t, make_float2(1.017335529e-04f, 1.017335529e-04f));
+  p = __ffma2_rn(p, t, make_float2(-1.142722919e-03f, -1.142722919e-03f));
+  p = __ffma2_rn(p, t, make_float2(9.891897850e-03f, 9.891897850e-03f));
+  p = __ffma2_rn(p, t, make_float2(-6.642163740e-02f, -6.642163740e-02f));
+  p = __ffma2_rn(p, t, make_float2(3.989305611e-01f, 3.989305611e-01f));
+  float2 s = __fmul2_rn(p, xc);
+  s.x = fminf(fmaxf(s.x, -0.5f), 0.5f);
+  s.y = fminf(fmaxf(s.y, -0.5f), 0.5f);
+  return s;
+}
+// g = GELU(x) = x * Phi(x); if WITH_GRAD also gp = GELU'(x) = Phi(x) + x * pdf(x)
+template <bool WITH_GRAD>
+__device__ __forceinline__ void gelu_pair(float2 x, float2& g, float2& gp) {
+  const float2 s = phi_minus_half2(x);
+  const float2 phi = __fadd2_rn(s, make_float2(0.5f, 0.5f));
+  g = __fmul2_rn(x, phi);
+  if (WITH_GRAD) {
+    // pdf(x) = exp2(-x^2 * log2(e)/2) / sqrt(2 pi)
+    const float2 t = __fmul2_rn(x, x);
+    const float kc = -0.72134752044448170368f;
+    float2 e;
+    e.x = exp2f_fast(t.x * kc);
+    e.y = exp2f_fast(t.y * kc);
+    const float2 xk = __fmul2_rn(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f));
+    gp = __ffma2_rn(xk, e, phi);
+  }
+}
+
+constexpr int kSlabBytes = 4096;                 // one epilogue slab: [32 rows][32 columns] of <= 4-byte elements
+template <int BN, int NCTA, bool SLAB> struct TnCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  static constexpr int B_ROWS = BN / NCTA;                             // B rows staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SLAB_BYTES = SLAB ? kEpiWarps * 2 * kSlabBytes : 0;   // two slabs per epilogue warp
+  static constexpr int RING_BUDGET = 224 * 1024 - SLAB_BYTES;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int NCHUNK = BN / 32;                               // 32-column epilogue chunks per tile
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int EPI_COLS = BN / 2;                              // columns per epilogue warp
   static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
-  static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for the 128B swizzle");
+  static_assert(2 * STAGES + 5 + 2 * kEpiWarps <= 64, "barrier block");
+  static_assert(!SLAB || BN % 32 == 0, "slab epilogue works on 32-column chunks");
 };
 
 // ================================================================================================
-template <int BN, int KIND, typename TOUT>
+template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int64_t N,
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmIn, int64_t M, int64_t N,
                   int64_t K, EpiParams ep) {
-  typedef TnCfg<BN> Cfg;
+  typedef TnCfg<BN, NCTA, SLAB> Cfg;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TM = BM * NCTA;                      // rows of one output tile (per CTA pair when NCTA = 2)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * Cfg::A_BYTES;
-  const uint32_t bars = sB + STAGES * Cfg::B_BYTES;
+  const uint32_t sSlab = sB + STAGES * Cfg::B_BYTES;
+  const uint32_t bars = sSlab + Cfg::SLAB_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto in_bar = [&](int w, int b) { return bars + 8u * (2 * STAGES + 5 + 2 * w + b); };   // slab-input barriers, per warp
+  constexpr bool HAS_IN = SLAB && (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;       // 0 = the pair's leader (issues the MMAs)
+  const int64_t m_tiles = (M + TM - 1) / TM, n_tiles = (N + BN - 1) / BN;
   const int64_t num_tiles = m_tiles * n_tiles;
+  const int64_t first_tile = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;
   const int nkb = (int)((K + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
@@ -182,40 +325,54 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps * NCTA); }
+    if (SLAB)
+      for (int w = 0; w < kEpiWarps; ++w) { mbar_init(in_bar(w, 0), 1); mbar_init(in_bar(w, 1), 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (NCTA == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();                 // the peer's barriers must exist before anything lands on them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer (both CTAs of a pair: own A rows, own half of the B tile; bytes are counted on the leader's barrier) =====
       int s = 0; uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int32_t arow = (int32_t)(mt * TM + rank * BM);
+        const int32_t brow = (int32_t)(nt * BN + rank * Cfg::B_ROWS);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
-          tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), kb * BK, (int32_t)(mt * BM));
-          tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, (int32_t)(nt * BN));
+          if (NCTA == 2) {
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+            tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), kb * BK, arow);
+            tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+          } else {
+            mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+            tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), kb * BK, arow);
+            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (the leader CTA's elected thread issues for the pair) =====
+      constexpr uint32_t idesc = make_idesc(TM, BN, 0, 0);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator buffer
+      for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
+        mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue(s) have drained this accumulator buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -225,24 +382,28 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t bdesc = make_smem_desc(sB + s * Cfg::B_BYTES, 16, 1024);
           int64_t krem = K - (int64_t)kb * BK;
           const int kmma = krem >= BK ? BK / 16 : (int)((krem + 15) / 16);
-          for (int k = 0; k < kmma; ++k)
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          umma_commit(empty_bar(s));                 // smem slot free once these MMAs retire
+          for (int k = 0; k < kmma; ++k) {
+            if (NCTA == 2) umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          if (NCTA == 2) umma_commit_pair(empty_bar(s));   // slot s is free in BOTH CTAs once these MMAs retire
+          else umma_commit(empty_bar(s));
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar(as));                  // accumulator complete -> epilogue
+        if (NCTA == 2) umma_commit_pair(tfull_bar(as));    // accumulator complete -> both epilogues
+        else umma_commit(tfull_bar(as));
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp >= kFirstEpiWarp) {
-    // ===== epilogue: TMEM -> registers -> fused math -> global =====
+  } else if (warp >= kFirstEpiWarp && !SLAB) {
+    // ===== epilogue: TMEM -> registers -> fused math -> global (each CTA drains its own 128 accumulator rows) =====
     const int quarter = warp & 3;                    // TMEM lanes [32*quarter, +32) are this warp's
     const int half = (warp - kFirstEpiWarp) >> 2;    // which half of the tile's columns
     int as = 0; uint32_t aph = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
       const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int64_t m = mt * BM + quarter * 32 + lane;
+      const int64_t m = mt * TM + rank * BM + quarter * 32 + lane;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
@@ -262,15 +423,181 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(tempty_bar(as), 0);     // the leader's MMA issuer waits for both CTAs
+        else mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+  } else if (warp >= kFirstEpiWarp && SLAB) {
+    // ===== slab epilogue: every epilogue warp is autonomous.  It owns TMEM lanes [32q, 32q+32) and every other 32-column
+    // chunk of the tile; per chunk: (residual / GELU' slab prefetched by ITS OWN TMA load) -> tcgen05.ld -> fused math in
+    // registers -> swizzled shared-memory slab -> ITS OWN TMA store.  Global traffic is whole 128-byte rows moved by the TMA
+    // unit (ragged M / N edges clipped by the tensor maps); no CTA-wide barrier, no per-thread global addressing. =====
+    const int ew = warp - kFirstEpiWarp;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t slab0 = sSlab + (uint32_t)ew * 2u * kSlabBytes;
+    constexpr uint32_t ROWB = 32 * sizeof(TOUT);                       // slab row: 128 B (fp32) or 64 B (bf16)
+    const uint32_t row_off = (uint32_t)lane * ROWB;
+    const uint32_t swz = (sizeof(TOUT) == 4) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+    constexpr int NV = (int)ROWB / 16;                                 // 16-byte vectors per slab row
+    int as = 0; uint32_t aph = 0;
+    int buf = 0; uint32_t inph[2] = {0u, 0u};
+    int64_t t_cur = first_tile; int c_cur = half;
+    auto chunk_coords = [&](int64_t tile, int c, int32_t& x, int32_t& y) {
+      const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      x = (int32_t)(nt * BN + c * 32);
+      y = (int32_t)(mt * TM + rank * BM + quarter * 32);
+    };
+    if (HAS_IN && lane == 0 && t_cur < num_tiles) {
+      int32_t x, y;
+      chunk_coords(t_cur, c_cur, x, y);
+      mbar_expect_tx(in_bar(ew, 0), 32 * ROWB);
+      tma_load_2d(slab0, &tmIn, in_bar(ew, 0), x, y);
+    }
+    while (t_cur < num_tiles) {
+      int64_t t_nxt = t_cur; int c_nxt = c_cur + 2;
+      if (c_nxt >= Cfg::NCHUNK) { c_nxt = half; t_nxt += tile_step; }
+      const uint32_t slab = slab0 + (uint32_t)buf * kSlabBytes;
+      if (lane == 0) {
+        if (HAS_IN) {
+          bulk_wait_read0();                         // the store that last read the other slab is done with it
+          if (t_nxt < num_tiles) {
+            int32_t x, y;
+            chunk_coords(t_nxt, c_nxt, x, y);
+            mbar_expect_tx(in_bar(ew, buf ^ 1), 32 * ROWB);
+            tma_load_2d(slab0 + (uint32_t)(buf ^ 1) * kSlabBytes, &tmIn, in_bar(ew, buf ^ 1), x, y);
+          }
+        } else {
+          bulk_wait_read1();                         // the store issued two chunks ago has finished reading this slab
+        }
+      }
+      if (c_cur == half) {                           // first chunk of a tile for this warp
+        mbar_wait(tfull_bar(as), aph);
+        tc_fence_after();
+      }
+      float v[32];
+      tmem_ld32(tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + c_cur * 32, v);
+      tmem_ld_wait();
+      if (t_nxt != t_cur) {         // last chunk of this tile for this warp: hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(tempty_bar(as), 0);
+          else mbar_arrive(tempty_bar(as));
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      const int64_t n0 = (t_cur % n_tiles) * BN + c_cur * 32;
+      const int64_t m = (t_cur / n_tiles) * TM + rank * BM + quarter * 32 + lane;
+      // ---- fused math on this lane's row: 32 columns ----
+      if (KIND == EPI_PLAIN) {
+        if (ep.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+      } else if (KIND == EPI_SCALE_RES) {
+        float sc = 1.0f;
+        if (ep.dp) sc = __ldg(ep.dp + (m < M ? m : M - 1) / ep.rows_per_sample);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+          if (ep.gamma) g4 = __ldg(reinterpret_cast<const float4*>(ep.gamma + n0 + i));
+          v[i] = sc * (g4.x * (v[i] + b4.x));
+          v[i + 1] = sc * (g4.y * (v[i + 1] + b4.y));
+          v[i + 2] = sc * (g4.z * (v[i + 2] + b4.z));
+          v[i + 3] = sc * (g4.w * (v[i + 3] + b4.w));
+        }
+      }
+      uint32_t pg[16], pd[16];
+      const bool want_gp = (KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr);
+      if (KIND == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+          const float2 ha = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+          const float2 hb = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+          const uint32_t ua = pack_bf16(ha.x, ha.y);        // h rounded to bf16, as autocast's Linear output
+          const uint32_t ub = pack_bf16(hb.x, hb.y);
+          float2 ga, gb, da, db;
+          if (want_gp) {
+            gelu_pair<true>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+            gelu_pair<true>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+            pd[i / 2] = pack_bf16(da.x, da.y);              // GELU'(h): all that backward needs of h
+            pd[i / 2 + 1] = pack_bf16(db.x, db.y);
+          } else {
+            gelu_pair<false>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+            gelu_pair<false>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+          }
+          pg[i / 2] = pack_bf16(ga.x, ga.y);
+          pg[i / 2 + 1] = pack_bf16(gb.x, gb.y);
+        }
+      }
+      if (HAS_IN) {
+        mbar_wait(in_bar(ew, buf), inph[buf]);
+        inph[buf] ^= 1;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          uint32_t a0, a1, a2, a3;
+          lds128(slab + row_off + (((uint32_t)j ^ swz) << 4), a0, a1, a2, a3);
+          if (sizeof(TOUT) == 4) {
+            if (KIND == EPI_SCALE_RES) {
+              v[4 * j] += __uint_as_float(a0); v[4 * j + 1] += __uint_as_float(a1);
+              v[4 * j + 2] += __uint_as_float(a2); v[4 * j + 3] += __uint_as_float(a3);
+            } else {
+              v[4 * j] *= __uint_as_float(a0); v[4 * j + 1] *= __uint_as_float(a1);
+              v[4 * j + 2] *= __uint_as_float(a2); v[4 * j + 3] *= __uint_as_float(a3);
+            }
+          } else {
+            const uint32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (KIND == EPI_SCALE_RES) { v[8 * j + 2 * q] += bf16_lo(a[q]); v[8 * j + 2 * q + 1] += bf16_hi(a[q]); }
+              else { v[8 * j + 2 * q] *= bf16_lo(a[q]); v[8 * j + 2 * q + 1] *= bf16_hi(a[q]); }
+            }
+          }
+        }
+      }
+      __syncwarp();                                  // lane 0's wait on the slab's previous store covers the whole warp
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const uint32_t addr = slab + row_off + (((uint32_t)j ^ swz) << 4);
+        if (KIND == EPI_BIAS_GELU) {               // two bf16 outputs share the slab: g in the first 2 KB, GELU' in the second
+          sts128(addr, pg[4 * j], pg[4 * j + 1], pg[4 * j + 2], pg[4 * j + 3]);
+          if (want_gp) sts128(addr + 2048u, pd[4 * j], pd[4 * j + 1], pd[4 * j + 2], pd[4 * j + 3]);
+        } else if (sizeof(TOUT) == 4)
+          sts128(addr, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                 __float_as_uint(v[4 * j + 3]));
+        else
+          sts128(addr, pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        int32_t x, y;
+        chunk_coords(t_cur, c_cur, x, y);
+        tma_store_2d(&tmOut, slab, x, y);
+        if (want_gp) tma_store_2d(&tmIn, slab + 2048u, x, y);
+        bulk_commit();
+      }
+      buf ^= 1;
+      t_cur = t_nxt; c_cur = c_nxt;
+    }
+    if (lane == 0) bulk_wait0();
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();                 // no CTA may exit (or free TMEM) while its peer still uses it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (NCTA == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -296,42 +623,6 @@ constexpr int kStABytes = BM * BK * 2, kStBBytes = kStBN * BK * 2;
 constexpr int kStBoxBytes = BM * 128;                            // [128 rows][64 bf16] = 16 KB
 constexpr int kStSmem = kStStages * (kStABytes + kStBBytes) + 4 * kStBoxBytes + 1024 + 256;
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-
-// erf(x/sqrt2) pieces shared by GELU and GELU': returns Phi(x) and sets pdf_e = exp(-x^2/2)
-__device__ __forceinline__ float phi_fast(float x, float& pdf_e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  pdf_e = __expf(-z * z);
-  const float half_erfc = 0.5f * poly * pdf_e;             // 0.5 * erfc(|z|)
-  return x >= 0.f ? 1.0f - half_erfc : half_erfc;          // Phi(x)
-}
 
 template <int KIND>
 __global__ void __launch_bounds__(kStThreads, 1)
@@ -460,16 +751,24 @@ gemm_tn_tc_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-          const uint32_t ha = pack_bf16(v[i] + b4.x, v[i + 1] + b4.y);     // h rounded to bf16, as autocast's Linear output
-          const uint32_t hb = pack_bf16(v[i + 2] + b4.z, v[i + 3] + b4.w);
-          p0[i / 2] = ha;
-          p0[i / 2 + 1] = hb;
-          float e;
-          const float x0 = bf16_lo(ha), x1 = bf16_hi(ha), x2 = bf16_lo(hb), x3 = bf16_hi(hb);
-          p1[i / 2] = pack_bf16(x0 * phi_fast(x0, e), x1 * phi_fast(x1, e));
-          p1[i / 2 + 1] = pack_bf16(x2 * phi_fast(x2, e), x3 * phi_fast(x3, e));
+          const float2 ha = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+          const float2 hb = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+          const uint32_t ua = pack_bf16(ha.x, ha.y);        // h rounded to bf16, as autocast's Linear output
+          const uint32_t ub = pack_bf16(hb.x, hb.y);
+          float2 ga, gb, da, db;
+          if (write_o0) {
+            gelu_pair<true>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+            gelu_pair<true>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+            p0[i / 2] = pack_bf16(da.x, da.y);              // GELU'(h): all that backward needs of h
+            p0[i / 2 + 1] = pack_bf16(db.x, db.y);
+          } else {
+            gelu_pair<false>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+            gelu_pair<false>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+          }
+          p1[i / 2] = pack_bf16(ga.x, ga.y);
+          p1[i / 2 + 1] = pack_bf16(gb.x, gb.y);
         }
-      } else {   // EPI_DGELU: out0 = acc * GELU'(h), h tile in shared memory (TMA, same 128B swizzle)
+      } else {   // EPI_DGELU: out0 = acc * gp, gp = GELU'(h) tile in shared memory (TMA, same 128B swizzle)
         mbar_wait(aux_full, xph);
         xph ^= 1;
 #pragma unroll
@@ -481,12 +780,8 @@ gemm_tn_tc_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) mbar_arrive(aux_empty);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float h0 = bf16_lo(p1[i]), h1 = bf16_hi(p1[i]);
-          float e0, e1;
-          const float c0 = phi_fast(h0, e0), c1 = phi_fast(h1, e1);
-          const float g0 = fmaf(h0 * 0.39894228040143267794f, e0, c0);     // Phi(x) + x * pdf(x)
-          const float g1 = fmaf(h1 * 0.39894228040143267794f, e1, c1);
-          p0[i] = pack_bf16(v[2 * i] * g0, v[2 * i + 1] * g1);
+          const float2 r = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(bf16_lo(p1[i]), bf16_hi(p1[i])));
+          p0[i] = pack_bf16(r.x, r.y);
         }
       }
 
@@ -719,6 +1014,24 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
+// 2-D row-major tensor [rows, cols] of elem_bytes elements; box = [box_rows][32 cols] for the epilogue slabs
+static int make_slab_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int elem_bytes) {
+  EncodeTiledFn enc = get_encode();
+  CNX_REQUIRE(enc != nullptr, CNX_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  CNX_REQUIRE((((uintptr_t)ptr) & 15) == 0, CNX_E_SHAPE, "GEMM output must be 16-byte aligned");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * (cuuint64_t)elem_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elem_bytes == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CNX_REQUIRE(r == CUDA_SUCCESS, CNX_E_DRIVER, "cuTensorMapEncodeTiled (slab) failed (%d) rows=%lld cols=%lld", (int)r,
+              (long long)rows, (long long)cols);
+  return 0;
+}
+
 template <typename K>
 static int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -729,18 +1042,88 @@ static int set_smem(K kernel, int bytes) {
   return 0;
 }
 
-template <int BN, int KIND, typename TOUT>
-static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  CUtensorMap tmA, tmB;
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_GEMM_NCTA");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// CNX_GEMM_STAGED (experiments): unset -> the measured default; bit 0 / bit 1 force fc1+GELU / dGELU through the 16-warp
+// staged kernel, value 4 forces the slab kernel for both
+static bool staged_enabled(int kind, bool dflt) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_GEMM_STAGED");
+    v = e ? atoi(e) : 8;
+  }
+  if (v == 8) return dflt;
+  return kind == EPI_BIAS_GELU ? (v & 1) != 0 : (v & 2) != 0;
+}
+static bool slab_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_GEMM_SLAB");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB>
+static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  typedef TnCfg<BN, NCTA, SLAB> Cfg;
+  CUtensorMap tmA, tmB, tmOut, tmIn;
   if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
-  if (int rc = make_map(&tmB, B, N, K, BN)) return rc;
-  auto k = gemm_tn_tc_kernel<BN, KIND, TOUT>;
-  if (int rc = set_smem(k, TnCfg<BN>::SMEM)) return rc;
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  int64_t grid = sm_count();
+  if (int rc = make_map(&tmB, B, N, K, Cfg::B_ROWS)) return rc;
+  if (SLAB) {
+    void* o = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.out0;
+    const void* in = (KIND == EPI_BIAS_GELU) ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
+    if (int rc = make_slab_map(&tmOut, o, M, N, (int)sizeof(TOUT))) return rc;
+    if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
+  } else {
+    tmOut = tmA;
+    tmIn = tmA;
+  }
+  auto k = gemm_tn_tc_kernel<BN, KIND, TOUT, NCTA, SLAB>;
+  if (int rc = set_smem(k, Cfg::SMEM)) return rc;
+  const int64_t tiles = ((M + BM * NCTA - 1) / (BM * NCTA)) * ((N + BN - 1) / BN);
+  int64_t grid = sm_count() / NCTA;
   if (grid > tiles) grid = tiles;
-  k<<<(unsigned)grid, kThreads, TnCfg<BN>::SMEM, s>>>(tmA, tmB, M, N, K, ep);
+  grid *= NCTA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, M, N, K, ep);
+  if (e != cudaSuccess) {
+    set_error("gemm_tn_tc launch: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return (int)e;
+  }
   return check_launch("gemm_tn_tc");
+}
+
+template <int BN, int KIND, typename TOUT, int NCTA>
+static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  // slab epilogue: whole 32-column chunks, an input slab only where the epilogue has one
+  constexpr bool kSlabKind = (BN % 32 == 0) && (KIND != EPI_BIAS_GELU || sizeof(TOUT) == 2);
+  if constexpr (kSlabKind) {
+    const bool need_in = (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
+    const void* o = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.out0;
+    if (slab_enabled() && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr)
+      return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
+  }
+  return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
 }
 
 
@@ -770,12 +1153,20 @@ int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, co
   CNX_REQUIRE(N % 8 == 0 && K % 8 == 0, CNX_E_SHAPE, "gemm_tc: N=%lld and K=%lld must be multiples of 8", (long long)N,
               (long long)K);
   if constexpr ((KIND == EPI_BIAS_GELU || KIND == EPI_DGELU) && sizeof(TOUT) == 2) {
-    if (N % 128 == 0) return tc::launch_tn_staged<KIND>(A, B, M, N, K, ep, s);
+    // measured (profiles/r01c_*): the 16-warp staged kernel wins while the epilogue math dominates (fc1+GELU, K < 768) and on
+    // the shortest K of the dGELU GEMM; the CTA-pair slab kernel wins everywhere else
+    const bool prefer_staged = (KIND == EPI_BIAS_GELU) ? (K < 768) : (K <= 96);
+    if (N % 128 == 0 && tc::staged_enabled(KIND, prefer_staged)) return tc::launch_tn_staged<KIND>(A, B, M, N, K, ep, s);
   }
-  if (N % 128 == 0) return tc::launch_tn<128, KIND, TOUT>(A, B, M, N, K, ep, s);
-  if (N % 96 == 0) return tc::launch_tn<96, KIND, TOUT>(A, B, M, N, K, ep, s);
-  if (N % 64 == 0) return tc::launch_tn<64, KIND, TOUT>(A, B, M, N, K, ep, s);
-  return tc::launch_tn<128, KIND, TOUT>(A, B, M, N, K, ep, s);   // ragged N: TMA zero-fills, epilogue guards
+  // CTA-pair tiles (256 x BN) wherever a whole tile fits; CNX_GEMM_NCTA=1 in the environment selects the single-CTA kernel
+  if (tc::pair_enabled() && M >= 256) {
+    if (N % 256 == 0) return tc::launch_tn<256, KIND, TOUT, 2>(A, B, M, N, K, ep, s);
+    if (N % 192 == 0) return tc::launch_tn<192, KIND, TOUT, 2>(A, B, M, N, K, ep, s);
+  }
+  if (N % 128 == 0) return tc::launch_tn<128, KIND, TOUT, 1>(A, B, M, N, K, ep, s);
+  if (N % 96 == 0) return tc::launch_tn<96, KIND, TOUT, 1>(A, B, M, N, K, ep, s);
+  if (N % 64 == 0) return tc::launch_tn<64, KIND, TOUT, 1>(A, B, M, N, K, ep, s);
+  return tc::launch_tn<128, KIND, TOUT, 1>(A, B, M, N, K, ep, s);   // ragged N: TMA zero-fills, epilogue guards
 }
 
 #define CNX_INST(KIND, TOUT) \
@@ -790,7 +1181,7 @@ CNX_INST(EPI_DGELU, bf16)
 
 static int wgrad_splits_tc(int64_t M, int64_t N1, int64_t N2, int bn) {
   int64_t tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + bn - 1) / bn);
-  int64_t want = ((int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t want = (int64_t)sm_count() / tiles;   // one wave: tiles * splits <= SM count (a 1.2-wave grid costs two waves)
   int64_t kb_total = (M + tc::BK - 1) / tc::BK;
   int64_t maxs = (kb_total + 7) / 8;            // at least 8 k-blocks (512 rows) per split
   if (want > maxs) want = maxs;

@@ -147,9 +147,10 @@ CNX_API int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, i
  * ---------------------------------------------------------------------------------------------- */
 #define CNX_GEMM_FORCE_SIMT 1
 
-/* fc1: h = A.W1^T + b1 ; g = GELU_erf(h).  h_out may be NULL (inference). */
+/* fc1: h = round_dtype(A.W1^T + b1) ; g_out = GELU_erf(h) ; gprime_out = GELU_erf'(h) (what backward needs of h:
+ * saved instead of h so the dgrad epilogue is one multiply).  gprime_out may be NULL (no-grad forward). */
 CNX_API int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64_t M, int64_t N, int64_t K,
-                           void* h_out, void* g_out, int dtype, int flags, void* stream);
+                           void* gprime_out, void* g_out, int dtype, int flags, void* stream);
 
 /* fc2: out[m,n] = shortcut[m,n] + dp[m / rows_per_sample] * gamma[n] * (acc[m,n] + b2[n]).
  * dp NULL -> 1 (eval / no drop-path); gamma NULL -> 1; shortcut NULL -> 0.  out/shortcut stream dtype. */
@@ -158,8 +159,9 @@ CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, cons
                                      int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,
                                      void* stream);
 
-/* dgrad of fc2 with GELU': dh[m,n] = acc[m,n] * GELU'(h[m,n]),  acc = dz.W2s (B given as [N=4C, K=C]). */
-CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* h, void* dh, int64_t M, int64_t N,
+/* dgrad of fc2 with GELU': dh[m,n] = acc[m,n] * gprime[m,n],  acc = dz.W2s (B given as [N=4C, K=C]),
+ * gprime = GELU'(h) as saved by cnx_gemm_bias_gelu_fwd. */
+CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,
                             int64_t K, int dtype, int flags, void* stream);
 
 /* plain GEMM with cast epilogue: out = A.B^T (dgrad of fc1; also patchify convs).  bias may be NULL. */

@@ -35,11 +35,13 @@ def test_mlp_forward_gemms(M, C, mode):
     dt = torch.float32 if mode == "f32" else torch.bfloat16
     flags = SIMT if mode == "bf16_simt" else 0
     A, W1, b1, W2, b2, gamma = _mk(M, C, dt, M + C)
-    h, gl = gemm_bias_gelu(A, W1, b1, flags)
-    href = (A.float() @ W1.float().t() + b1)
+    gp, gl = gemm_bias_gelu(A, W1, b1, flags)
+    href = (A.float() @ W1.float().t() + b1).to(dt).float()   # h rounded to the activation dtype, as autocast's Linear output
     tol = 1e-4 if dt == torch.float32 else 1e-2
-    assert max_rel(h.float(), href) <= tol
-    assert max_rel(gl.float(), F.gelu(h.float())) <= tol      # GELU of the rounded h, as autocast computes it
+    assert max_rel(gl.float(), F.gelu(href)) <= tol
+    hr = href.clone().requires_grad_(True)
+    F.gelu(hr).sum().backward()
+    assert max_rel(gp.float(), hr.grad) <= tol                # saved for backward: GELU'(h), not h
     rps = 7
     n_s = (M + rps - 1) // rps
     dp = (torch.rand(n_s, device=DEV) > 0.3).float() / 0.7
@@ -63,12 +65,13 @@ def test_mlp_backward_gemms(M, C, mode):
     dz = torch.randn(M, C, generator=g).to(dt).to(DEV)
     h = torch.randn(M, 4 * C, generator=g).to(dt).to(DEV)
     tol = 1e-4 if dt == torch.float32 else 2e-2
-    # dgrad fc2 with GELU':  Bt = W2^T [4C, C]
+    # dgrad fc2 with GELU':  Bt = W2^T [4C, C]; the kernel takes gp = GELU'(h) as saved by the forward
     Bt = W2.t().contiguous()
-    dh = gemm_dgelu(dz, Bt, h, flags)
     hf = h.float().requires_grad_(True)
-    F.gelu(hf).backward(dz.float() @ W2.float())
-    assert max_rel(dh.float(), hf.grad) <= tol
+    F.gelu(hf).sum().backward()
+    gp = hf.grad.to(dt)
+    dh = gemm_dgelu(dz, Bt, gp, flags)
+    assert max_rel(dh.float(), (dz.float() @ W2.float()) * gp.float()) <= tol
     # dgrad fc1: dxn = dh . W1  (B = W1^T [C, 4C])
     dxn = gemm_plain(dh, W1.t().contiguous(), None, dt, flags)
     assert max_rel(dxn.float(), dh.float() @ W1.float()) <= tol
@@ -90,8 +93,8 @@ def test_tc_matches_simt_on_same_operands(M, C):
     A, W1, b1, W2, b2, gamma = _mk(M, C, torch.bfloat16, 3 * M + C)
     h0, g0 = gemm_bias_gelu(A, W1, b1, SIMT)
     h1, g1 = gemm_bias_gelu(A, W1, b1, 0)
-    assert max_rel(h1.float(), h0.float()) <= 4e-3        # <= 1 bf16 ulp on the rare rounding flip
-    assert (h1 != h0).float().mean().item() < 0.02
+    assert max_rel(h1.float(), h0.float()) <= 8e-3        # GELU'(h): <= 1 bf16 ulp on rounding flips (polynomial vs erff)
+    assert max_rel(g1.float(), g0.float()) <= 8e-3
     o0 = gemm_scale_res(g0, W2, b2, gamma, None, 1, None, torch.float32, SIMT)
     o1 = gemm_scale_res(g0, W2, b2, gamma, None, 1, None, torch.float32, 0)
     assert max_rel(o1, o0) <= 1e-5
