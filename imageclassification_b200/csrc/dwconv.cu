@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace cnx {
 namespace dw {
@@ -607,6 +608,25 @@ static int launch_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype
 }  // namespace dw
 }  // namespace cnx
 
+namespace cnx {
+// second-generation kernels (dwconv2.cu); CNX_DW_V1=1 in the environment selects the first-generation ones below
+int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
+                      float eps, int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn, int act_dtype, float* mean,
+                      float* rstd, cudaStream_t s);
+int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
+                     int64_t H, int64_t W, int64_t C, cudaStream_t s);
+int dwconv7_wgrad_v2(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W, int64_t C,
+                     float* partial, int P, cudaStream_t s);
+static bool dw_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_DW_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+}  // namespace cnx
+
 using namespace cnx;
 using namespace cnx::dw;
 
@@ -626,6 +646,7 @@ int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* wt, const float*
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_ln_fwd: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_ln_fwd: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!dw_v1()) return dwconv7_ln_fwd_v2(x, x_dtype, wt, bias, ln_w, ln_b, eps, N, H, W, C, y, xn, act_dtype, mean, rstd, s);
   if (x_dtype == CNX_F32 && act_dtype == CNX_F32)
     return pick_conv<MODE_FWD, float, float>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
   if (x_dtype == CNX_F32 && act_dtype == CNX_BF16)
@@ -643,6 +664,7 @@ int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void*
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_dgrad: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_dgrad: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!dw_v1()) return dwconv7_dgrad_v2(dy, dy_dtype, wt, dres, dx, stream_dtype, N, H, W, C, s);
   if (dy_dtype == CNX_F32 && stream_dtype == CNX_F32)
     return pick_conv<MODE_DGRAD, float, float>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
   if (dy_dtype == CNX_BF16 && stream_dtype == CNX_F32)
@@ -660,6 +682,7 @@ int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, 
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_wgrad: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_wgrad: C=%lld must be a multiple of 32", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!dw_v1()) return dwconv7_wgrad_v2(dy, dy_dtype, x, x_dtype, N, H, W, C, partial, P, s);
 #define CNX_WG(TD, TX)                                                                                  \
   do {                                                                                                  \
     if (W <= 8 && H <= 8) return launch_wgrad<GeoI, TD, TX>(dy, dy_dtype, x, x_dtype, N, H, W, C, partial, P, s); \

@@ -19,7 +19,7 @@
 #include <mutex>
 
 namespace cnx {
-namespace dw {
+namespace dw2 {
 
 constexpr int CH = 32;                        // channels per chunk (16 pairs per half-warp)
 constexpr int W_BYTES = 49 * CH * 4;          // one chunk of tap-major weights
@@ -72,13 +72,13 @@ inline int pick_geo(int64_t N, int64_t H, int64_t W) {
 
 #define CNX_GEO_SWITCH(gid, ...)                                                 \
   switch (gid) {                                                                 \
-    case cnx::dw::GEO_W32: { typedef cnx::dw::GeoW32 G; __VA_ARGS__; } break;    \
-    case cnx::dw::GEO_W28: { typedef cnx::dw::GeoW28 G; __VA_ARGS__; } break;    \
-    case cnx::dw::GEO_S28: { typedef cnx::dw::GeoS28 G; __VA_ARGS__; } break;    \
-    case cnx::dw::GEO_W16: { typedef cnx::dw::GeoW16 G; __VA_ARGS__; } break;    \
-    case cnx::dw::GEO_S14: { typedef cnx::dw::GeoS14 G; __VA_ARGS__; } break;    \
-    case cnx::dw::GEO_W8: { typedef cnx::dw::GeoW8 G; __VA_ARGS__; } break;      \
-    default: { typedef cnx::dw::GeoS7 G; __VA_ARGS__; } break;                   \
+    case cnx::dw2::GEO_W32: { typedef cnx::dw2::GeoW32 G; __VA_ARGS__; } break;    \
+    case cnx::dw2::GEO_W28: { typedef cnx::dw2::GeoW28 G; __VA_ARGS__; } break;    \
+    case cnx::dw2::GEO_S28: { typedef cnx::dw2::GeoS28 G; __VA_ARGS__; } break;    \
+    case cnx::dw2::GEO_W16: { typedef cnx::dw2::GeoW16 G; __VA_ARGS__; } break;    \
+    case cnx::dw2::GEO_S14: { typedef cnx::dw2::GeoS14 G; __VA_ARGS__; } break;    \
+    case cnx::dw2::GEO_W8: { typedef cnx::dw2::GeoW8 G; __VA_ARGS__; } break;      \
+    default: { typedef cnx::dw2::GeoS7 G; __VA_ARGS__; } break;                   \
   }
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -277,5 +277,5 @@ inline int64_t num_tiles(int64_t N, int64_t H, int64_t W, int* tiles_x, int* til
   return (int64_t)(*tiles_x) * (*tiles_y) * ((N + G::NB - 1) / G::NB);
 }
 
-}  // namespace dw
+}  // namespace dw2
 }  // namespace cnx

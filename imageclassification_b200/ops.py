@@ -188,7 +188,8 @@ class _BlockFn(torch.autograd.Function):
         dln = torch.empty((2 * C,), dtype=torch.float32, device=dev)
         L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dln), st), "reduce_partials")
         # 7. dwconv wgrad (+bias)
-        Pw = max(1, min(P, (N * ((H + 7) // 8) * ((W + 7) // 8))))
+        # one persistent CTA per SM: (C/32 channel chunks) x Pw partial rows ~= SM count, every CTA sweeps many tiles
+        Pw = max(1, min(L.load().cnx_sm_count() // max(C // 32, 1), (N * ((H + 7) // 8) * ((W + 31) // 32))))
         wpart = torch.empty((Pw, 50, C), dtype=torch.float32, device=dev)
         L.check(lib.cnx_dwconv7_wgrad(L.ptr(dy), ad, L.ptr(xl), sd, N, H, W, C, L.ptr(wpart), Pw, st), "dwconv7_wgrad")
         dconv_w = torch.empty_like(conv_w)

@@ -78,7 +78,7 @@ for si in [int(s) for s in args.stages.split(",")]:
         timeit(f"dwconv7_ln_fwd {tag}", lambda: cabi.dwconv7_ln_fwd(x, w, b, lw, lb, 1e-6, bf))
         dy = torch.randn(M, C, device=dev, generator=g).to(bf)
         timeit(f"dwconv7_dgrad {tag}", lambda: cabi.dwconv7_dgrad(dy, w, x, (N, H, H, C), f32))
-        timeit(f"dwconv7_wgrad {tag}", lambda: cabi.dwconv7_wgrad(dy, x, P=L.load().cnx_sm_count() * 2))
+        timeit(f"dwconv7_wgrad {tag}", lambda: cabi.dwconv7_wgrad(dy, x, P=max(1, L.load().cnx_sm_count() // (C // 32))))
         del dy
     if only is None or "ln" in only:
         y = torch.randn(M, C, device=dev, generator=g).to(bf)
