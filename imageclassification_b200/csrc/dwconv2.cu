@@ -176,7 +176,12 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int wy = tt % G::WY, img = tt / G::WY;
     const int row0 = wy * G::TH, col0 = wx * G::CPW;
     const int hbase = ((img * G::HH + row0) * G::HW + col0) * CH + 2 * cp;
-    const int64_t rowstride = (int64_t)W * C;
+    // byte offsets of this thread's NPIX pixels relative to its strip origin: tile-independent, computed once
+    uint32_t poff[NPIX];
+#pragma unroll
+    for (int q = 0; q < G::CPW; ++q)
+#pragma unroll
+      for (int r = 0; r < G::TH; ++r) poff[q * G::TH + r] = (uint32_t)((r * W + q) * C) * (uint32_t)sizeof(TOUT);
     int s = 0; uint32_t ph = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
@@ -191,43 +196,43 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int c = k * CH + 2 * cp;
         float2 b2 = make_float2(0.f, 0.f);
         if (MODE == MODE_FWD) b2 = __ldg(reinterpret_cast<const float2*>(bias + c));
+        uint8_t* op = reinterpret_cast<uint8_t*>(out + pix0 * C + c);
         // dgrad: the residual-gradient values are fetched BEFORE the FMAs so their latency hides under them
         float2 dr[G::CPW][G::TH];
         if (MODE == MODE_DGRAD) {
+          const uint8_t* dp = reinterpret_cast<const uint8_t*>(dres + pix0 * C + c);
 #pragma unroll
           for (int q = 0; q < G::CPW; ++q)
 #pragma unroll
             for (int r = 0; r < G::TH; ++r) {
               dr[q][r] = make_float2(0.f, 0.f);
-              if (dres != nullptr) {
-                int gx = gx0 + q, gy = gy0 + r;
-                if (!EXACT) { gx = gx < W ? gx : W - 1; gy = gy < H ? gy : H - 1; }
-                dr[q][r] = ldg_pair(dres + ((((int64_t)(n_ok ? n : 0) * H + gy) * W + gx) * C + c));
-              }
+              if (dres != nullptr && (EXACT || (n_ok && gx0 + q < W && gy0 + r < H)))
+                dr[q][r] = ldg_pair(reinterpret_cast<const TOUT*>(dp + poff[q * G::TH + r]));
             }
         }
         mbar_wait(full_bar(s), ph);
         const TIN* halo = reinterpret_cast<const TIN*>(base_p + s * Cfg::STAGE_BYTES);
         const float* wsm = reinterpret_cast<const float*>(base_p + s * Cfg::STAGE_BYTES + Cfg::HALO_PAD);
         float2 acc[G::CPW][G::TH];
-        conv_chunk<G, TIN, MODE == MODE_DGRAD>(halo, wsm, hbase, cp, acc);
+        conv_chunk<G, TIN, MODE == MODE_DGRAD>(halo, wsm, hbase, cp, acc, b2);     // accumulators start at the bias
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));          // this warp is done with the slot
         if (++s == STAGES) { s = 0; ph ^= 1; }
-        TOUT* op = out + pix0 * C + c;
 #pragma unroll
         for (int q = 0; q < G::CPW; ++q) {
 #pragma unroll
           for (int r = 0; r < G::TH; ++r) {
             float2 v = acc[q][r];
             if (MODE == MODE_FWD) {
-              v = round_pair(__fadd2_rn(v, b2), (TOUT*)nullptr);
-              st[q * G::TH + r].x += v.x + v.y;
-              st[q * G::TH + r].y = fmaf(v.x, v.x, fmaf(v.y, v.y, st[q * G::TH + r].y));
+              v = round_pair(v, (TOUT*)nullptr);
+              // (sum, sum of squares) of the rounded pair in two packed FMAs
+              float2& sp = st[q * G::TH + r];
+              sp = __ffma2_rn(make_float2(v.x, v.x), make_float2(1.0f, v.x), sp);
+              sp = __ffma2_rn(make_float2(v.y, v.y), make_float2(1.0f, v.y), sp);
             } else {
               v = __fadd2_rn(v, dr[q][r]);
             }
-            if (EXACT || (n_ok && gx0 + q < W && gy0 + r < H)) st_pair(op + (r * rowstride + (int64_t)q * C), v);
+            if (EXACT || (n_ok && gx0 + q < W && gy0 + r < H)) st_pair(reinterpret_cast<TOUT*>(op + poff[q * G::TH + r]), v);
           }
         }
       }

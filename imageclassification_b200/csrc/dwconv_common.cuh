@@ -179,14 +179,14 @@ struct Worker {
 // The register-tiled 7x7 correlation for one 32-channel chunk: acc[q][r] for output column q, row r of the strip.
 template <class G, typename TS, bool FLIP>
 __device__ __forceinline__ void conv_chunk(const TS* __restrict__ halo, const float* __restrict__ wsm, int hbase, int cp,
-                                           float2 (&acc)[G::CPW][G::TH]) {
+                                           float2 (&acc)[G::CPW][G::TH], float2 init = make_float2(0.f, 0.f)) {
   float2 wr[49];
 #pragma unroll
   for (int t = 0; t < 49; ++t) wr[t] = *reinterpret_cast<const float2*>(wsm + (FLIP ? 48 - t : t) * CH + 2 * cp);
 #pragma unroll
   for (int q = 0; q < G::CPW; ++q)
 #pragma unroll
-    for (int r = 0; r < G::TH; ++r) acc[q][r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < G::TH; ++r) acc[q][r] = init;
 #pragma unroll
   for (int j = 0; j < 6 + G::CPW; ++j) {
 #pragma unroll
