@@ -5,6 +5,7 @@
 // (d ln_w, d ln_b) in warp-private shared-memory columns across all the rows a persistent CTA visits and
 // writes one partial row per CTA (deterministic; reduced by cnx_reduce_partials).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace cnx {
 
@@ -137,6 +138,138 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
   }
 }
 
+
+// ---- LayerNorm backward, second generation -------------------------------------------------------
+// LPP lanes per row (32/LPP rows per warp pass), 8-channel (16-byte bf16 / 2x16-byte fp32) vectors, U passes in flight so one
+// DRAM round trip covers U rows per lane; a lane always owns the same channels, so d ln_w / d ln_b accumulate in REGISTERS
+// over all the rows the warp visits (the first generation did a shared-memory read-modify-write per vector per row) and
+// meet in shared memory once at the end.  Output format unchanged: one partial row [2][C] per CTA.
+template <typename TG, typename TY, typename TD, int NJ, int LPP, int U>
+#ifndef CNX_LNB_MINB
+#define CNX_LNB_MINB 3
+#endif
+#ifndef CNX_LNB_U1
+#define CNX_LNB_U1 2
+#endif
+#ifndef CNX_LNB_U2
+#define CNX_LNB_U2 2
+#endif
+__global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(const TG* __restrict__ dxn, const TY* __restrict__ y,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ ln_w, int64_t M, int C,
+                                                                  TD* __restrict__ dy, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
+  constexpr int PPW = 32 / LPP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPP, l = lane % LPP;
+  const int VPR = C >> 3;
+  const float invC = 1.0f / (float)C;
+  float lw[NJ][8], aw[NJ][8], ab[NJ][8];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int v = l + LPP * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lw[j][e] = v < VPR ? __ldg(ln_w + v * 8 + e) : 0.f; aw[j][e] = 0.f; ab[j][e] = 0.f; }
+  }
+  const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp, tw = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t base = gw * (PPW * U); base < M; base += tw * (PPW * U)) {
+    float d[U][NJ][8], yv[U][NJ][8], mu[U], rs[U];
+    int64_t row[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      row[u] = base + u * PPW + sub;
+      const bool ok = row[u] < M;
+      mu[u] = ok ? __ldg(mean + row[u]) : 0.f;
+      rs[u] = ok ? __ldg(rstd + row[u]) : 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int v = l + LPP * j;
+        if (ok && v < VPR) {
+          load8(dxn + row[u] * C + v * 8, d[u][j]);
+          load8(y + row[u] * C + v * 8, yv[u][j]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { d[u][j][e] = 0.f; yv[u][j][e] = mu[u]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (yv[u][j][e] - mu[u]) * rs[u];
+          const float g = d[u][j][e] * lw[j][e];
+          aw[j][e] = fmaf(d[u][j][e], xh, aw[j][e]);
+          ab[j][e] += d[u][j][e];
+          yv[u][j][e] = xh;
+          d[u][j][e] = g;
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= invC;
+      s2 *= invC;
+      if (row[u] < M) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int v = l + LPP * j;
+          if (v < VPR) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = rs[u] * (d[u][j][e] - s1 - yv[u][j][e] * s2);
+            store8(dy + row[u] * C + v * 8, o8);
+          }
+        }
+      }
+    }
+  }
+  // rows handled by the two halves of a warp (LPP = 16) meet first, then the warps through shared memory in a fixed order
+  if (LPP == 16) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        aw[j][e] += __shfl_xor_sync(0xffffffffu, aw[j][e], 16);
+        ab[j][e] += __shfl_xor_sync(0xffffffffu, ab[j][e], 16);
+      }
+  }
+  float* my = colacc + (size_t)warp * 2 * C;
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int v = l + LPP * j;
+      if (v < VPR) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { my[v * 8 + e] = aw[j][e]; my[C + v * 8 + e] = ab[j][e]; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += LN_WARPS * 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < LN_WARPS; ++wv) sum += colacc[(size_t)wv * 2 * C + i];
+    partial[(int64_t)blockIdx.x * 2 * C + i] = sum;
+  }
+}
+
+static bool ln_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_LN_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 static inline int nj_for(int64_t C) { return (int)((C / 4 + 31) / 32); }
 
 #define CNX_NJ_SWITCH(nj, ...)                                   \
@@ -167,6 +300,25 @@ template <typename TG, typename TY, typename TD>
 static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, const float* rstd, const float* ln_w,
                          int64_t M, int64_t C, void* dy, float* partial, int P, cudaStream_t s) {
   size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
+  // measured (profiles/r01d_*): the register-accumulating kernel wins for rows of up to 32 vectors (C <= 256) at 3 CTAs/SM;
+  // wider rows keep the first-generation kernel
+  if (C % 8 == 0 && C <= 256 && !ln_v1()) {
+#define CNX_LNB2(NJ, LPP, U)                                                                                         \
+  do {                                                                                                               \
+    auto k = ln_bwd_v2_kernel<TG, TY, TD, NJ, LPP, U>;                                                               \
+    if (smem > 48 * 1024) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }             \
+    }                                                                                                                \
+    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,   \
+                                               partial);                                                             \
+    return check_launch("ln_bwd");                                                                                   \
+  } while (0)
+    const int64_t vpr = C / 8;
+    if (vpr <= 16) CNX_LNB2(1, 16, CNX_LNB_U1);
+    if (vpr <= 32) CNX_LNB2(1, 32, CNX_LNB_U1);
+#undef CNX_LNB2
+  }
   CNX_NJ_SWITCH(nj_for(C), {
     auto k = ln_bwd_kernel<TG, TY, TD, NJ>;
     if (smem > 48 * 1024) {

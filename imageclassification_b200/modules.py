@@ -118,7 +118,14 @@ class ConvNeXtStage(nn.Module):
             ConvNeXtBlock(out_chs, ls_init_value=ls_init_value, drop_path=drop_path_rates[j]) for j in range(depth)])
 
     def forward(self, x):
-        return self.blocks(self.downsample(x))
+        ds = self.downsample
+        if isinstance(ds, nn.Sequential):
+            conv = ds[1]
+            if conv.kernel_size == (2, 2) and conv.stride == (2, 2) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+                x = ops.downsample_forward(x, ds[0].weight, ds[0].bias, conv.weight, conv.bias, ds[0].eps)
+            else:
+                x = ds(x)
+        return self.blocks(x)
 
 
 class NormMlpClassifierHead(nn.Module):
@@ -184,8 +191,11 @@ class ConvNeXt(nn.Module):
     def forward_features(self, x):
         # channels-last from the first kernel on: the patch-conv output is then already the [N,H,W,C]
         # row-major matrix the Block kernels consume (no permute copies anywhere in the network)
-        x = x.contiguous(memory_format=torch.channels_last)
-        x = self.stem(x)
+        conv, norm = self.stem[0], self.stem[1]
+        if conv.kernel_size == (4, 4) and conv.stride == (4, 4) and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
+            x = ops.stem_forward(x, conv.weight, conv.bias, norm.weight, norm.bias, norm.eps)
+        else:
+            x = self.stem(x.contiguous(memory_format=torch.channels_last))
         x = self.stages(x)
         return self.norm_pre(x)
 

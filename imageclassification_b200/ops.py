@@ -38,8 +38,9 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
     return xl if xl.is_contiguous() else xl.contiguous()
 
 
-def _num_partials() -> int:
-    return L.load().cnx_sm_count() * 2
+def _num_partials(C: int = 1024) -> int:
+    """CTAs (= partial rows) of the LayerNorm-backward kernels: 3 per SM for narrow rows, 2 per SM otherwise."""
+    return L.load().cnx_sm_count() * (3 if C <= 256 else 2)
 
 
 # Kernel-side layouts of the canonical fp32 parameters (bf16 copies, transposes, tap-major conv weights) are derived
@@ -180,7 +181,7 @@ class _BlockFn(torch.autograd.Function):
         # 5. fc1 wgrad + bias grad
         dW1, db1 = _wgrad(dh, xn, M, C4, C, True)
         # 6. LayerNorm backward
-        P = _num_partials()
+        P = _num_partials(C)
         dy = torch.empty((M, C), dtype=act_dtype, device=dev)
         part = torch.empty((P, 2 * C), dtype=torch.float32, device=dev)
         L.check(lib.cnx_ln_bwd(L.ptr(dxn), ad, L.ptr(y), ad, L.ptr(mean), L.ptr(rstd), L.ptr(ln_w), M, C, L.ptr(dy), ad,
@@ -243,7 +244,7 @@ class _LayerNormCLFn(torch.autograd.Function):
         d2 = dout.reshape(M, C)
         if not d2.is_contiguous():
             d2 = d2.contiguous()
-        P = max(1, min(_num_partials(), (M + 7) // 8))
+        P = max(1, min(_num_partials(C), (M + 7) // 8))
         dx = torch.empty((M, C), dtype=x2.dtype, device=x2.device)
         part = torch.empty((P, 2 * C), dtype=torch.float32, device=x2.device)
         L.check(lib.cnx_ln_bwd(L.ptr(d2), L.dt(d2), L.ptr(x2), L.dt(x2), L.ptr(mean), L.ptr(rstd), L.ptr(w), M, C,
@@ -257,6 +258,140 @@ def layer_norm_cl(x, w, b, eps: float):
     """F.layer_norm(x, (C,), w, b, eps) for channels-last x; output fp32 under autocast (ATen autocast policy)."""
     out_dtype = torch.float32 if (torch.is_autocast_enabled("cuda") or x.dtype == torch.float32) else x.dtype
     return _LayerNormCLFn.apply(x, w, b, float(eps), out_dtype)
+
+
+def _gemm_plain(A, B, bias, out_dtype):
+    """out[M,N] = A[M,K] . B[N,K]^T (+ bias[N]); A, B in the activation dtype, fp32 accumulate."""
+    lib = L.load()
+    M, K = A.shape
+    Nn = B.shape[0]
+    out = torch.empty((M, Nn), dtype=out_dtype, device=A.device)
+    L.check(lib.cnx_gemm_plain(L.ptr(A), L.ptr(B), L.ptr(bias), L.ptr(out), L.dt(out_dtype), M, Nn, K, L.dt(A), GEMM_FLAGS,
+                               L.stream()), "gemm_plain")
+    return out
+
+
+def _ln_fwd(x2, w, b, eps, out_dtype):
+    lib = L.load()
+    M, C = x2.shape
+    out = torch.empty((M, C), dtype=out_dtype, device=x2.device)
+    mean = torch.empty((M,), dtype=torch.float32, device=x2.device)
+    rstd = torch.empty((M,), dtype=torch.float32, device=x2.device)
+    L.check(lib.cnx_ln_fwd(L.ptr(x2), L.dt(x2), L.ptr(w), L.ptr(b), eps, M, C, L.ptr(out), L.dt(out_dtype), L.ptr(mean),
+                           L.ptr(rstd), L.stream()), "ln_fwd")
+    return out, mean, rstd
+
+
+def _ln_bwd(dxn, y, mean, rstd, w, dy_dtype):
+    """-> dy [M,C], d ln_w [C], d ln_b [C]"""
+    lib = L.load()
+    M, C = y.shape
+    P = max(1, min(_num_partials(C), (M + 7) // 8))
+    dy = torch.empty((M, C), dtype=dy_dtype, device=y.device)
+    part = torch.empty((P, 2 * C), dtype=torch.float32, device=y.device)
+    L.check(lib.cnx_ln_bwd(L.ptr(dxn), L.dt(dxn), L.ptr(y), L.dt(y), L.ptr(mean), L.ptr(rstd), L.ptr(w), M, C, L.ptr(dy),
+                           L.dt(dy_dtype), L.ptr(part), P, L.stream()), "ln_bwd")
+    dwb = torch.empty((2 * C,), dtype=torch.float32, device=y.device)
+    L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
+    return dy, dwb[:C], dwb[C:]
+
+
+def _patch_weight(conv_w: torch.Tensor, act_dtype, channels_last_taps: bool) -> torch.Tensor:
+    """[Cout,Cin,k,k] conv weight -> the GEMM's B operand [Cout, k*k*Cin] in the activation dtype.  The stem operand
+    keeps the canonical (ci,ky,kx) flattening; the downsample operand is (ky,kx,ci) to match channels-last patches."""
+    def build():
+        Cout = conv_w.shape[0]
+        w2 = conv_w.detach().permute(0, 2, 3, 1) if channels_last_taps else conv_w.detach()
+        return w2.reshape(Cout, -1).to(act_dtype).contiguous()
+    return _derived((conv_w,), ("patchw", channels_last_taps, act_dtype), build)
+
+
+class _StemFn(torch.autograd.Function):
+    """stem: Conv2d(3, C, 4, stride 4) -> LayerNorm2d (convnext.py:79-82) as patchify + tcgen05 GEMM + LayerNorm kernels.
+    Under bf16 autocast the conv output is rounded to bf16 and the LayerNorm output is fp32, as ATen's policies give."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, eps, act_dtype):
+        lib = L.load()
+        L.require_cuda(x, conv_w, ln_w)
+        N, Cin, H, W = x.shape
+        Cout = conv_w.shape[0]
+        xc = x.detach().to(torch.float32).contiguous()
+        M = N * (H // 4) * (W // 4)
+        A = torch.empty((M, Cin * 16), dtype=act_dtype, device=x.device)
+        L.check(lib.cnx_patchify4_nchw(L.ptr(xc), N, Cin, H, W, L.ptr(A), L.dt(act_dtype), L.stream()), "patchify4")
+        y = _gemm_plain(A, _patch_weight(conv_w, act_dtype, False), conv_b, act_dtype)
+        out, mean, rstd = _ln_fwd(y, ln_w, ln_b, eps, torch.float32)
+        if any(ctx.needs_input_grad[1:5]):
+            ctx.save_for_backward(A, y, mean, rstd, conv_w, ln_w)
+            ctx.act_dtype = act_dtype
+        return out.view(N, H // 4, W // 4, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        A, y, mean, rstd, conv_w, ln_w = ctx.saved_tensors
+        M, Cout = y.shape
+        d2 = _nhwc(dout).reshape(M, Cout)
+        dy, dlw, dlb = _ln_bwd(d2, y, mean, rstd, ln_w, ctx.act_dtype)
+        dW, db = _wgrad(dy, A, M, Cout, A.shape[1], True)
+        return None, dW.view_as(conv_w), db, dlw, dlb, None, None
+
+
+class _DownsampleFn(torch.autograd.Function):
+    """downsample: LayerNorm2d -> Conv2d(C, C2, 2, stride 2) (convnext.py:84-89) as LayerNorm + 2x2 patch gather + GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, conv_w, conv_b, eps, act_dtype):
+        lib = L.load()
+        L.require_cuda(x, conv_w, ln_w)
+        N, C, H, W = x.shape
+        C2 = conv_w.shape[0]
+        xl = _nhwc(x.detach())
+        M = N * H * W
+        xn, mean, rstd = _ln_fwd(xl.reshape(M, C), ln_w, ln_b, eps, act_dtype)
+        A = torch.empty((M // 4, 4 * C), dtype=act_dtype, device=x.device)
+        L.check(lib.cnx_patch2(L.ptr(xn), L.dt(act_dtype), N, H, W, C, L.ptr(A), 1, L.stream()), "patch2")
+        out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
+        if ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5]):
+            ctx.save_for_backward(xl, mean, rstd, A, conv_w, ln_w)
+            ctx.shape = (N, C, H, W)
+            ctx.act_dtype = act_dtype
+        return out.view(N, H // 2, W // 2, C2).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        xl, mean, rstd, A, conv_w, ln_w = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        act_dtype = ctx.act_dtype
+        C2 = conv_w.shape[0]
+        M = N * H * W
+        d2 = _nhwc(dout).reshape(M // 4, C2)
+        if d2.dtype != act_dtype:
+            d2 = d2.to(act_dtype)
+        # weight / bias gradient: dWp[C2, 4C] = d2^T . A  (taps-last layout) -> canonical [C2, C, 2, 2]
+        dWp, db = _wgrad(d2, A, M // 4, C2, 4 * C, True)
+        dW = dWp.view(C2, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+        dx = dlw = dlb = None
+        # data gradient: dA = d2 . Wp  (B operand = Wp^T [4C, C2]) -> scatter back to pixel order -> LayerNorm backward
+        wpt = _derived((conv_w,), ("patchwT", act_dtype),
+                       lambda: conv_w.detach().permute(2, 3, 1, 0).reshape(4 * C, C2).to(act_dtype).contiguous())
+        dA = _gemm_plain(d2, wpt, None, act_dtype)
+        dxn = torch.empty((M, C), dtype=act_dtype, device=dA.device)
+        L.check(lib.cnx_patch2(L.ptr(dA), L.dt(act_dtype), N, H, W, C, L.ptr(dxn), 0, L.stream()), "patch2")
+        dxl, dlw, dlb = _ln_bwd(dxn, xl.reshape(M, C), mean, rstd, ln_w, xl.dtype)
+        dx = dxl.view(N, H, W, C).permute(0, 3, 1, 2)
+        return dx, dlw, dlb, dW, db, None, None
+
+
+def stem_forward(x, conv_w, conv_b, ln_w, ln_b, eps: float):
+    """Conv2d(Cin, C, 4, 4) + LayerNorm2d on a [N,Cin,H,W] image batch -> logical [N,C,H/4,W/4] (channels-last memory)."""
+    return _StemFn.apply(x, conv_w, conv_b, ln_w, ln_b, float(eps), _act_dtype())
+
+
+def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float):
+    """LayerNorm2d + Conv2d(C, C2, 2, 2) on a logical [N,C,H,W] stream -> logical [N,C2,H/2,W/2]."""
+    return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype())
 
 
 class _SoftTargetCEFn(torch.autograd.Function):

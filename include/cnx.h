@@ -195,6 +195,19 @@ CNX_API int cnx_layerscale_finalize(const float* G2, const float* s, const float
                             int64_t C, int64_t K4, int accumulate, float* dW2, float* db2, float* dgamma,
                             void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Patchify convolutions (stem 4x4 stride 4, downsample 2x2 stride 2; convnext.py:79-89): a k x k
+ * stride-k conv is a GEMM over non-overlapping patches.  These entry points only re-order activations into / out
+ * of the [patches, k*k*C] operand; the arithmetic is cnx_gemm_plain / cnx_gemm_wgrad.
+ * ---------------------------------------------------------------------------------------------- */
+/* x [N,Cin,H,W] fp32 NCHW -> out [N*(H/4)*(W/4), Cin*16], column k = (ci*4 + ky)*4 + kx (the flattening of the
+ * canonical [Cout,Cin,4,4] weight). */
+CNX_API int cnx_patchify4_nchw(const float* x, int64_t N, int64_t Cin, int64_t H, int64_t W, void* out, int out_dtype,
+                               void* stream);
+/* gather != 0: in [N,H,W,C] -> out [N,H/2,W/2,(ky,kx,C)];  gather == 0: the inverse permutation. */
+CNX_API int cnx_patch2(const void* in, int dtype, int64_t N, int64_t H, int64_t W, int64_t C, void* out, int gather,
+                       void* stream);
+
 /* Elementwise fp32 -> bf16 cast of a flat buffer (parameter shadow copies). */
 CNX_API int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
 

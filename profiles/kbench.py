@@ -85,7 +85,7 @@ for si in [int(s) for s in args.stages.split(",")]:
         dxn = torch.randn(M, C, device=dev, generator=g).to(bf)
         mean = torch.zeros(M, device=dev)
         rstd = torch.ones(M, device=dev)
-        timeit(f"ln_bwd {tag}", lambda: cabi.ln_bwd(dxn, y, mean, rstd, lw, bf, P=296))
+        timeit(f"ln_bwd {tag}", lambda: cabi.ln_bwd(dxn, y, mean, rstd, lw, bf, P=int(os.environ.get("CNX_LN_P", "296"))))
         del y, dxn
     if only is None or "gemm" in only:
         A = torch.randn(M, C, device=dev, generator=g).to(bf)
