@@ -141,13 +141,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-// arrive on the barrier at this offset in CTA `rank` of the cluster
+// arrive on the barrier at this offset in CTA `rank` of the cluster.  RELAXED: the only thing the waiter (the MMA issuer)
+// consumes is the TMEM accumulator, ordered by tcgen05.fence::before_thread_sync; a release at cluster scope would drain
+// every outstanding global store of the warp first (measured: 22 % of all warp stalls in the dGELU kernel)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(bar), "r"(rank)
       : "memory");
 }
@@ -270,12 +272,13 @@ __device__ __forceinline__ void gelu_pair(float2 x, float2& g, float2& gp) {
 }
 
 constexpr int kSlabBytes = 4096;                 // one epilogue slab: [32 rows][32 columns] of <= 4-byte elements
-template <int BN, int NCTA, bool SLAB> struct TnCfg {
+template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
+  static constexpr int THREADS = (kFirstEpiWarp + NEPI) * 32;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = BN / NCTA;                             // B rows staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLAB_BYTES = SLAB ? kEpiWarps * 2 * kSlabBytes : 0;   // two slabs per epilogue warp
+  static constexpr int SLAB_BYTES = SLAB ? NEPI * 2 * kSlabBytes : 0;        // two slabs per epilogue warp
   static constexpr int RING_BUDGET = 224 * 1024 - SLAB_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int NCHUNK = BN / 32;                               // 32-column epilogue chunks per tile
@@ -285,19 +288,22 @@ template <int BN, int NCTA, bool SLAB> struct TnCfg {
   static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
   static constexpr int SMEM = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for the 128B swizzle");
-  static_assert(2 * STAGES + 5 + 2 * kEpiWarps <= 64, "barrier block");
+  static_assert(2 * STAGES + 5 + 2 * NEPI <= 64, "barrier block");
+  static_assert(STAGES >= 2, "ring too small");
   static_assert(!SLAB || BN % 32 == 0, "slab epilogue works on 32-column chunks");
 };
 
 // ================================================================================================
-template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB, int NEPI>
+__global__ void __launch_bounds__((kFirstEpiWarp + NEPI) * 32, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmIn, int64_t M, int64_t N,
                   int64_t K, EpiParams ep) {
-  typedef TnCfg<BN, NCTA, SLAB> Cfg;
+  typedef TnCfg<BN, NCTA, SLAB, NEPI> Cfg;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int TM = BM * NCTA;                      // rows of one output tile (per CTA pair when NCTA = 2)
+  constexpr int TM = BM * NCTA;
+  constexpr int NGRP = NEPI / 4;                     // epilogue warps per TMEM lane quarter = column groups
+  static_assert(SLAB || NEPI == kEpiWarps, "the direct-store epilogue is written for 8 warps");                      // rows of one output tile (per CTA pair when NCTA = 2)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base;
@@ -325,9 +331,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps * NCTA); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NEPI * NCTA); }
     if (SLAB)
-      for (int w = 0; w < kEpiWarps; ++w) { mbar_init(in_bar(w, 0), 1); mbar_init(in_bar(w, 1), 1); }
+      for (int w = 0; w < NEPI; ++w) { mbar_init(in_bar(w, 0), 1); mbar_init(in_bar(w, 1), 1); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -436,7 +442,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // unit (ragged M / N edges clipped by the tensor maps); no CTA-wide barrier, no per-thread global addressing. =====
     const int ew = warp - kFirstEpiWarp;
     const int quarter = warp & 3;
-    const int half = ew >> 2;
+    const int half = ew >> 2;                          // column group: chunks half, half + NGRP, ...
     const uint32_t slab0 = sSlab + (uint32_t)ew * 2u * kSlabBytes;
     constexpr uint32_t ROWB = 32 * sizeof(TOUT);                       // slab row: 128 B (fp32) or 64 B (bf16)
     const uint32_t row_off = (uint32_t)lane * ROWB;
@@ -457,7 +463,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tma_load_2d(slab0, &tmIn, in_bar(ew, 0), x, y);
     }
     while (t_cur < num_tiles) {
-      int64_t t_nxt = t_cur; int c_nxt = c_cur + 2;
+      int64_t t_nxt = t_cur; int c_nxt = c_cur + NGRP;
       if (c_nxt >= Cfg::NCHUNK) { c_nxt = half; t_nxt += tile_step; }
       const uint32_t slab = slab0 + (uint32_t)buf * kSlabBytes;
       if (lane == 0) {
@@ -1071,9 +1077,9 @@ static bool slab_enabled() {
   return v != 0;
 }
 
-template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB>
+template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB, int NEPI = kEpiWarps>
 static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  typedef TnCfg<BN, NCTA, SLAB> Cfg;
+  typedef TnCfg<BN, NCTA, SLAB, NEPI> Cfg;
   CUtensorMap tmA, tmB, tmOut, tmIn;
   if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
   if (int rc = make_map(&tmB, B, N, K, Cfg::B_ROWS)) return rc;
@@ -1086,7 +1092,7 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
     tmOut = tmA;
     tmIn = tmA;
   }
-  auto k = gemm_tn_tc_kernel<BN, KIND, TOUT, NCTA, SLAB>;
+  auto k = gemm_tn_tc_kernel<BN, KIND, TOUT, NCTA, SLAB, NEPI>;
   if (int rc = set_smem(k, Cfg::SMEM)) return rc;
   const int64_t tiles = ((M + BM * NCTA - 1) / (BM * NCTA)) * ((N + BN - 1) / BN);
   int64_t grid = sm_count() / NCTA;
@@ -1094,7 +1100,7 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   grid *= NCTA;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1120,8 +1126,11 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
   if constexpr (kSlabKind) {
     const bool need_in = (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
     const void* o = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.out0;
-    if (slab_enabled() && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr)
-      return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
+    if (slab_enabled() && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
+      // the GELU epilogue is issue-bound: 16 epilogue warps (4 per scheduler) where the tile has >= 4 column chunks
+      if constexpr (KIND == EPI_BIAS_GELU && BN >= 128) return launch_tn_impl<BN, KIND, TOUT, NCTA, true, 16>(A, B, M, N, K, ep, s);
+      else return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
+    }
   }
   return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
 }
@@ -1153,9 +1162,9 @@ int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, co
   CNX_REQUIRE(N % 8 == 0 && K % 8 == 0, CNX_E_SHAPE, "gemm_tc: N=%lld and K=%lld must be multiples of 8", (long long)N,
               (long long)K);
   if constexpr ((KIND == EPI_BIAS_GELU || KIND == EPI_DGELU) && sizeof(TOUT) == 2) {
-    // measured (profiles/r01c_*): the 16-warp staged kernel wins while the epilogue math dominates (fc1+GELU, K < 768) and on
-    // the shortest K of the dGELU GEMM; the CTA-pair slab kernel wins everywhere else
-    const bool prefer_staged = (KIND == EPI_BIAS_GELU) ? (K < 768) : (K <= 96);
+    // measured (profiles/r01e_*): the single-CTA 16-warp staged kernel still wins the fc1+GELU GEMM at K = 96 (pure
+    // HBM-write-bound); the CTA-pair slab kernel wins everywhere else
+    const bool prefer_staged = (KIND == EPI_BIAS_GELU) ? (K < 192) : false;
     if (N % 128 == 0 && tc::staged_enabled(KIND, prefer_staged)) return tc::launch_tn_staged<KIND>(A, B, M, N, K, ep, s);
   }
   // CTA-pair tiles (256 x BN) wherever a whole tile fits; CNX_GEMM_NCTA=1 in the environment selects the single-CTA kernel
