@@ -982,6 +982,164 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+// ================================================================================================
+// wgrad on CTA pairs: one tcgen05.mma.cta_group::2 spans a 256 x BN tile of out = X^T.Y (BN = 128 or 256).  Each CTA stages
+// its own 128 channels of X (two 64-channel MN-major boxes) and HALF of the BN channels of Y per 64-row k-block, so a CTA moves
+// 24 / 32 KB per k-block where the single-CTA 128 x 128 tile moves 32 KB for a quarter / half of the MACs.  Bias gradient,
+// split-K partials and the deterministic reduction are as in gemm_wgrad_tc_kernel.  grid = (2 * tiles, splits), cluster (2,1,1).
+// ================================================================================================
+template <int BN> struct WgPairCfg {
+  static constexpr int A_BYTES = 2 * 64 * BK * 2;                      // own 128 channels of X
+  static constexpr int B_BOXES = BN / 2 / 64;                          // 64-channel boxes of Y staged by one CTA
+  static constexpr int B_BYTES = B_BOXES * 64 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int CS_COL = BN;                                    // 16 column-sum columns after the accumulator
+  static constexpr int TMEM_COLS = (BN + 16 <= 256) ? 256 : 512;
+  static constexpr int EPI_COLS = BN / 2;
+  static constexpr int ONES_BYTES = 2048;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + ONES_BYTES + 1024 + 256;
+  static_assert(BN == 128 || BN == 256, "the pair's half of the Y tile must be whole 64-channel boxes");
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, int64_t Mtot,
+                       int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part) {
+  typedef WgPairCfg<BN> Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * Cfg::A_BYTES;
+  const uint32_t sOnes = sB + STAGES * Cfg::B_BYTES;
+  const uint32_t bars = sOnes + Cfg::ONES_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t j_tiles = (N2 + BN - 1) / BN;
+  const int64_t tile = blockIdx.x >> 1;
+  const int64_t it = tile / j_tiles, jt = tile - it * j_tiles;
+  const int split = blockIdx.y;
+  const int kb_total = (int)((Mtot + BK - 1) / BK);
+  const int kb0 = split * kb_per_split;
+  int kb1 = kb0 + kb_per_split;
+  if (kb1 > kb_total) kb1 = kb_total;
+  const int nkb = kb1 > kb0 ? kb1 - kb0 : 0;
+  const bool do_colsum = (cs_part != nullptr) && (jt == 0);
+
+  {
+    uint8_t* gen = smem_raw + (sOnes - smem_u32(smem_raw));
+    for (int i = threadIdx.x; i < Cfg::ONES_BYTES / 4; i += kThreads) reinterpret_cast<uint32_t*>(gen)[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      const int32_t a_ch = (int32_t)(it * 256 + rank * 128);
+      const int32_t b_ch = (int32_t)(jt * BN + rank * (BN / 2));
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int32_t mrow = (kb0 + kb) * BK;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+        tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), a_ch, mrow);
+        tma_load_2d_pair(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), a_ch + 64, mrow);
+#pragma unroll
+        for (int b = 0; b < Cfg::B_BOXES; ++b)
+          tma_load_2d_pair(sB + s * Cfg::B_BYTES + b * 8192, &tmY, full_bar(s), b_ch + 64 * b, mrow);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0 && nkb > 0) {
+      constexpr uint32_t idesc = make_idesc(256, BN, 1, 1);
+      constexpr uint32_t idesc_ones = make_idesc(256, 16, 1, 1);
+      const uint64_t odesc = make_smem_desc(sOnes, 8192, 1024);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(sA + s * Cfg::A_BYTES, 8192, 1024);
+        const uint64_t bdesc = make_smem_desc(sB + s * Cfg::B_BYTES, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16_pair(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+          if (do_colsum) umma_f16_pair(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
+        }
+        umma_commit_pair(empty_bar(s));
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit_pair(tfull_bar);
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    const int quarter = warp & 3;
+    const int half = (warp - kFirstEpiWarp) >> 2;
+    const int64_t i = it * 256 + rank * 128 + quarter * 32 + lane;
+    float* po = part + (int64_t)split * N1 * N2;
+    if (nkb > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < Cfg::EPI_COLS; c += 32) {
+      const int col = half * Cfg::EPI_COLS + c;
+      float v[32];
+      if (nkb > 0) {
+        tmem_ld32(t_row + col, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const int64_t jj = jt * BN + col;
+      if (i < N1) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          if (jj + j < N2) store8(po + i * N2 + jj + j, *reinterpret_cast<float(*)[8]>(&v[j]));
+      }
+    }
+    if (do_colsum && half == 0) {
+      float v[16];
+      if (nkb > 0) {
+        tmem_ld16(t_row + Cfg::CS_COL, v);
+        tmem_ld_wait();
+      } else {
+        v[0] = 0.f;
+      }
+      if (i < N1) cs_part[(int64_t)split * N1 + i] = v[0];
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1188,26 +1346,64 @@ CNX_INST(EPI_SCALE_RES, bf16)
 CNX_INST(EPI_DGELU, bf16)
 #undef CNX_INST
 
-static int wgrad_splits_tc(int64_t M, int64_t N1, int64_t N2, int bn) {
-  int64_t tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + bn - 1) / bn);
-  int64_t want = (int64_t)sm_count() / tiles;   // one wave: tiles * splits <= SM count (a 1.2-wave grid costs two waves)
-  int64_t kb_total = (M + tc::BK - 1) / tc::BK;
-  int64_t maxs = (kb_total + 7) / 8;            // at least 8 k-blocks (512 rows) per split
+// tile plan of the wgrad GEMM: CTA pairs (256 x BN) where both dimensions carry at least a tile, single CTAs otherwise
+struct WgPlan { int pair; int bn; int splits; int64_t tiles; };
+static WgPlan wgrad_plan_tc(int64_t M, int64_t N1, int64_t N2) {
+  WgPlan p;
+  p.pair = (tc::pair_enabled() && N1 >= 192 && N2 >= 128) ? 1 : 0;
+  if (p.pair) {
+    // 256-wide tiles even when the last one is ragged (TMA zero fill): measured faster than exact 128-wide tiles (384 -> 2 x 256)
+    p.bn = (N2 >= 192) ? 256 : 128;
+    p.tiles = ((N1 + 255) / 256) * ((N2 + p.bn - 1) / p.bn);
+  } else {
+    p.bn = (N2 % 128 == 0) ? 128 : ((N2 % 96 == 0) ? 96 : 128);
+    p.tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + p.bn - 1) / p.bn);
+  }
+  const int64_t slots = p.pair ? sm_count() / 2 : sm_count();   // one wave: tiles * splits <= CTAs (pairs) that fit
+  int64_t want = slots / p.tiles;
+  const int64_t kb_total = (M + tc::BK - 1) / tc::BK;
+  const int64_t maxs = (kb_total + 7) / 8;                      // at least 8 k-blocks (512 rows) per split
   if (want > maxs) want = maxs;
   if (want < 1) want = 1;
-  return (int)want;
+  p.splits = (int)want;
+  return p;
 }
-static int wgrad_bn(int64_t N2) { return (N2 % 128 == 0) ? 128 : ((N2 % 96 == 0) ? 96 : 128); }
 
 int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2) {
-  return (int64_t)wgrad_splits_tc(M, N1, N2, wgrad_bn(N2)) * (N1 * N2 + N1) * 4;
+  return (int64_t)wgrad_plan_tc(M, N1, N2).splits * (N1 * N2 + N1) * 4;
+}
+
+template <int BN>
+static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int64_t M, int64_t N1, int64_t N2, int kb_per_split,
+                             int64_t tiles, int splits, float* part, float* cs_part, cudaStream_t s) {
+  auto k = tc::gemm_wgrad_pair_kernel<BN>;
+  if (int rc = tc::set_smem(k, tc::WgPairCfg<BN>::SMEM)) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * tiles), (unsigned)splits);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = tc::WgPairCfg<BN>::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmX, tmY, M, N1, N2, kb_per_split, part, cs_part);
+  if (e != cudaSuccess) {
+    set_error("gemm_wgrad_pair launch: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return (int)e;
+  }
+  return check_launch("gemm_wgrad_pair");
 }
 
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                   float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
   CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_tc: N1, N2 must be multiples of 8");
-  const int bn = wgrad_bn(N2);
-  const int splits = wgrad_splits_tc(M, N1, N2, bn);
+  const WgPlan pl = wgrad_plan_tc(M, N1, N2);
+  const int splits = pl.splits;
   CNX_REQUIRE(workspace_bytes >= (int64_t)splits * (N1 * N2 + N1) * 4, CNX_E_WORKSPACE, "gemm_wgrad: workspace too small");
   CUtensorMap tmX, tmY;
   if (int rc = tc::make_map(&tmX, X, M, N1, tc::BK)) return rc;
@@ -1216,18 +1412,24 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
   const int kb_per_split = (int)((kb_total + splits - 1) / splits);
   float* part = (float*)workspace;
   float* cs_part = part + (int64_t)splits * N1 * N2;
-  const int64_t tiles = ((N1 + tc::BM - 1) / tc::BM) * ((N2 + bn - 1) / bn);
-  dim3 grid((unsigned)tiles, (unsigned)splits);
-  if (bn == 128) {
-    auto k = tc::gemm_wgrad_tc_kernel<128>;
-    if (int rc = tc::set_smem(k, tc::WgCfg<128>::SMEM)) return rc;
-    k<<<grid, tc::kThreads, tc::WgCfg<128>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+  if (pl.pair) {
+    int rc = (pl.bn == 256)
+                 ? launch_wgrad_pair<256>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s)
+                 : launch_wgrad_pair<128>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s);
+    if (rc) return rc;
   } else {
-    auto k = tc::gemm_wgrad_tc_kernel<96>;
-    if (int rc = tc::set_smem(k, tc::WgCfg<96>::SMEM)) return rc;
-    k<<<grid, tc::kThreads, tc::WgCfg<96>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+    dim3 grid((unsigned)pl.tiles, (unsigned)splits);
+    if (pl.bn == 128) {
+      auto k = tc::gemm_wgrad_tc_kernel<128>;
+      if (int rc = tc::set_smem(k, tc::WgCfg<128>::SMEM)) return rc;
+      k<<<grid, tc::kThreads, tc::WgCfg<128>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+    } else {
+      auto k = tc::gemm_wgrad_tc_kernel<96>;
+      if (int rc = tc::set_smem(k, tc::WgCfg<96>::SMEM)) return rc;
+      k<<<grid, tc::kThreads, tc::WgCfg<96>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+    }
+    if (int rc = check_launch("gemm_wgrad_tc")) return rc;
   }
-  if (int rc = check_launch("gemm_wgrad_tc")) return rc;
   if (int rc = cnx_reduce_partials(part, splits, N1 * N2, 1.0f, accumulate, out, s)) return rc;
   if (colsum_x) return cnx_reduce_partials(cs_part, splits, N1, 1.0f, accumulate, colsum_x, s);
   return 0;
