@@ -118,6 +118,17 @@ def kernel_work(name, a):
     if name == "cnx_ln_bwd":
         M, C = a[7:9]
         return M * C * (es(a[1]) + es(a[3]) + es(a[10])) + 8 * M + 16 * C, 0, f"ln_bwd C{C}"
+    if name == "cnx_ln_fwd_patch2":
+        N, H, W, C = a[5:9]
+        M = N * H * W
+        return M * C * (es(a[1]) + es(a[10])) + 8 * M + 8 * C, 0, f"ln_fwd_patch2 C{C}"
+    if name == "cnx_ln_bwd_patch2":
+        N, H, W, C = a[7:11]
+        M = N * H * W
+        return M * C * (es(a[1]) + es(a[3]) + es(a[12])) + 8 * M + 16 * C, 0, f"ln_bwd_patch2 C{C}"
+    if name == "cnx_patchify4_nchw":
+        N, Cin, H, W = a[1:5]
+        return N * Cin * H * W * (4 + es(a[6])), 0, "patchify4"
     if name == "cnx_ln_fwd":
         M, C = a[5:7]
         return M * C * (es(a[1]) + es(a[8])) + 8 * M + 8 * C, 0, f"ln_fwd C{C}"

@@ -272,6 +272,29 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   out[j] = accumulate ? out[j] + s : s;
 }
 
+// the same reduction for the two outputs of one split-K wgrad (weight gradient + bias gradient) in ONE launch
+__global__ void __launch_bounds__(256) reduce_partials2_kernel(const float* __restrict__ pa, int64_t La, float* __restrict__ oa,
+                                                               const float* __restrict__ pb, int64_t Lb, float* __restrict__ ob,
+                                                               int P, int accumulate) {
+  int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= La + Lb) return;
+  const float* partial = pa;
+  float* out = oa;
+  int64_t L = La;
+  if (j >= La) { partial = pb; out = ob; L = Lb; j -= La; }
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 4 <= P; p += 4) {
+    s0 += partial[(int64_t)(p + 0) * L + j];
+    s1 += partial[(int64_t)(p + 1) * L + j];
+    s2 += partial[(int64_t)(p + 2) * L + j];
+    s3 += partial[(int64_t)(p + 3) * L + j];
+  }
+  for (; p < P; ++p) s0 += partial[(int64_t)p * L + j];
+  float s = (s0 + s1) + (s2 + s3);
+  out[j] = accumulate ? out[j] + s : s;
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, int64_t n, bf16* __restrict__ out) {
   int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   int64_t stride = (int64_t)gridDim.x * 256 * 4;
@@ -365,6 +388,18 @@ int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int
                                                                                          accumulate, out);
   return check_launch("reduce_partials");
 }
+
+}  // extern "C"
+
+namespace cnx {
+int reduce_partials2(const float* pa, int64_t La, float* oa, const float* pb, int64_t Lb, float* ob, int P, int accumulate,
+                     cudaStream_t s) {
+  reduce_partials2_kernel<<<(unsigned)((La + Lb + 255) / 256), 256, 0, s>>>(pa, La, oa, pb, Lb, ob, P, accumulate);
+  return check_launch("reduce_partials2");
+}
+}  // namespace cnx
+
+extern "C" {
 
 int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
   CNX_REQUIRE(in && out && n > 0, CNX_E_BADARG, "cast_f32_to_bf16: bad argument");

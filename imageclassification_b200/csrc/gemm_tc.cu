@@ -22,6 +22,8 @@
 #include <stdlib.h>
 
 namespace cnx {
+int reduce_partials2(const float* pa, int64_t La, float* oa, const float* pb, int64_t Lb, float* ob, int P, int accumulate,
+                     cudaStream_t s);
 namespace tc {
 
 constexpr int BM = 128;
@@ -1430,9 +1432,8 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
     }
     if (int rc = check_launch("gemm_wgrad_tc")) return rc;
   }
-  if (int rc = cnx_reduce_partials(part, splits, N1 * N2, 1.0f, accumulate, out, s)) return rc;
-  if (colsum_x) return cnx_reduce_partials(cs_part, splits, N1, 1.0f, accumulate, colsum_x, s);
-  return 0;
+  if (colsum_x) return reduce_partials2(part, N1 * N2, out, cs_part, N1, colsum_x, splits, accumulate, s);
+  return cnx_reduce_partials(part, splits, N1 * N2, 1.0f, accumulate, out, s);
 }
 
 }  // namespace cnx

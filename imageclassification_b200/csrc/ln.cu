@@ -11,11 +11,22 @@ namespace cnx {
 
 constexpr int LN_WARPS = 8;
 
+// pixel row m of an [N,H,W] grid -> its row in the 2x2-patch-major order [N,H/2,W/2,(ky,kx)] (pH == 0: identity).  Lets the
+// downsample LayerNorm write the patchify-GEMM operand directly and its backward read the GEMM's data gradient in place.
+__device__ __forceinline__ int64_t patch2_row(int64_t m, int pH, int pW) {
+  if (pH == 0) return m;
+  const int xx = (int)(m % pW);
+  const int64_t t = m / pW;
+  const int yy = (int)(t % pH);
+  const int64_t n = t / pH;
+  return (((n * (pH >> 1) + (yy >> 1)) * (pW >> 1) + (xx >> 1)) << 2) + ((yy & 1) << 1) + (xx & 1);
+}
+
 template <typename TX, typename TO, int NJ>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ ln_w,
                                                                const float* __restrict__ ln_b, float eps, int64_t M,
                                                                int C, TO* __restrict__ out, float* __restrict__ mean_out,
-                                                               float* __restrict__ rstd_out) {
+                                                               float* __restrict__ rstd_out, int pH, int pW) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   float lw[NJ][4], lb[NJ][4];
@@ -53,7 +64,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restr
       if (mean_out) mean_out[row] = mu;
       if (rstd_out) rstd_out[row] = rs;
     }
-    TO* orow = out + row * C;
+    TO* orow = out + patch2_row(row, pH, pW) * C;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       int vi = lane + 32 * j;
@@ -73,7 +84,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd,
                                                                const float* __restrict__ ln_w, int64_t M, int C,
-                                                               TD* __restrict__ dy, float* __restrict__ partial) {
+                                                               TD* __restrict__ dy, float* __restrict__ partial, int pH,
+                                                               int pW) {
   extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
@@ -90,6 +102,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
   const float invC = 1.0f / (float)C;
   for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M; row += (int64_t)gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
+    const int64_t grow = patch2_row(row, pH, pW);
     float g[NJ][4], xh[NJ][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
       int vi = lane + 32 * j;
       if (vi < nvec) {
         float d[4], yv[4];
-        load4(dxn + row * C + vi * 4, d);
+        load4(dxn + grow * C + vi * 4, d);
         load4(y + row * C + vi * 4, yv);
         float4 aw = *reinterpret_cast<float4*>(my_dw + vi * 4);
         float4 ab = *reinterpret_cast<float4*>(my_db + vi * 4);
@@ -157,7 +170,8 @@ template <typename TG, typename TY, typename TD, int NJ, int LPP, int U>
 __global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(const TG* __restrict__ dxn, const TY* __restrict__ y,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ ln_w, int64_t M, int C,
-                                                                  TD* __restrict__ dy, float* __restrict__ partial) {
+                                                                  TD* __restrict__ dy, float* __restrict__ partial, int pH,
+                                                                  int pW) {
   extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
   constexpr int PPW = 32 / LPP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(
       for (int j = 0; j < NJ; ++j) {
         const int v = l + LPP * j;
         if (ok && v < VPR) {
-          load8(dxn + row[u] * C + v * 8, d[u][j]);
+          load8(dxn + patch2_row(row[u], pH, pW) * C + v * 8, d[u][j]);
           load8(y + row[u] * C + v * 8, yv[u][j]);
         } else {
 #pragma unroll
@@ -287,18 +301,18 @@ static inline int nj_for(int64_t C) { return (int)((C / 4 + 31) / 32); }
 
 template <typename TX, typename TO>
 static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C, void* out,
-                         float* mean, float* rstd, cudaStream_t s) {
+                         float* mean, float* rstd, cudaStream_t s, int pH = 0, int pW = 0) {
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   CNX_NJ_SWITCH(nj_for(C), (ln_fwd_kernel<TX, TO, NJ><<<(unsigned)blocks, LN_WARPS * 32, 0, s>>>(
-                               (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, mean, rstd)));
+                               (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, mean, rstd, pH, pW)));
   return check_launch("ln_fwd");
 }
 
 template <typename TG, typename TY, typename TD>
 static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, const float* rstd, const float* ln_w,
-                         int64_t M, int64_t C, void* dy, float* partial, int P, cudaStream_t s) {
+                         int64_t M, int64_t C, void* dy, float* partial, int P, cudaStream_t s, int pH = 0, int pW = 0) {
   size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
   // measured (profiles/r01d_*): the register-accumulating kernel wins for rows of up to 32 vectors (C <= 256) at 3 CTAs/SM;
   // wider rows keep the first-generation kernel
@@ -311,7 +325,7 @@ static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, cons
       if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }             \
     }                                                                                                                \
     k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,   \
-                                               partial);                                                             \
+                                               partial, pH, pW);                                                     \
     return check_launch("ln_bwd");                                                                                   \
   } while (0)
     const int64_t vpr = C / 8;
@@ -326,7 +340,7 @@ static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, cons
       if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     }
     k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,
-                                               partial);
+                                               partial, pH, pW);
   });
   return check_launch("ln_bwd");
 }
@@ -337,21 +351,33 @@ using namespace cnx;
 
 extern "C" {
 
-int cnx_ln_fwd(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
-               void* out, int out_dtype, float* mean, float* rstd, void* stream) {
+static int ln_fwd_impl(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
+                       void* out, int out_dtype, float* mean, float* rstd, void* stream, int pH, int pW) {
   CNX_REQUIRE(x && ln_w && ln_b && out, CNX_E_BADARG, "ln_fwd: null pointer");
   CNX_REQUIRE(dtype_ok(x_dtype) && dtype_ok(out_dtype) && M > 0 && C > 0, CNX_E_BADARG, "ln_fwd: bad shape/dtype");
   CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "ln_fwd: C=%lld must be a multiple of 4", (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == CNX_F32 && out_dtype == CNX_F32) return launch_ln_fwd<float, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
-  if (x_dtype == CNX_F32 && out_dtype == CNX_BF16) return launch_ln_fwd<float, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
-  if (x_dtype == CNX_BF16 && out_dtype == CNX_F32) return launch_ln_fwd<bf16, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
-  return launch_ln_fwd<bf16, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s);
+  if (x_dtype == CNX_F32 && out_dtype == CNX_F32) return launch_ln_fwd<float, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s, pH, pW);
+  if (x_dtype == CNX_F32 && out_dtype == CNX_BF16) return launch_ln_fwd<float, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s, pH, pW);
+  if (x_dtype == CNX_BF16 && out_dtype == CNX_F32) return launch_ln_fwd<bf16, float>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s, pH, pW);
+  return launch_ln_fwd<bf16, bf16>(x, ln_w, ln_b, eps, M, C, out, mean, rstd, s, pH, pW);
 }
 
-int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
-               const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
-               void* stream) {
+int cnx_ln_fwd(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t M, int64_t C,
+               void* out, int out_dtype, float* mean, float* rstd, void* stream) {
+  return ln_fwd_impl(x, x_dtype, ln_w, ln_b, eps, M, C, out, out_dtype, mean, rstd, stream, 0, 0);
+}
+
+int cnx_ln_fwd_patch2(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t N, int64_t H,
+                      int64_t W, int64_t C, void* out, int out_dtype, float* mean, float* rstd, void* stream) {
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, CNX_E_SHAPE, "ln_fwd_patch2: H=%lld, W=%lld must be even",
+              (long long)H, (long long)W);
+  return ln_fwd_impl(x, x_dtype, ln_w, ln_b, eps, N * H * W, C, out, out_dtype, mean, rstd, stream, (int)H, (int)W);
+}
+
+static int ln_bwd_impl(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+                       const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
+                       void* stream, int pH, int pW) {
   CNX_REQUIRE(dxn && y && mean && rstd && ln_w && dy && partial && P > 0, CNX_E_BADARG, "ln_bwd: bad argument");
   CNX_REQUIRE(dtype_ok(dxn_dtype) && dtype_ok(y_dtype) && dtype_ok(dy_dtype) && M > 0 && C > 0, CNX_E_BADARG,
               "ln_bwd: bad shape/dtype");
@@ -359,15 +385,30 @@ int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const
   cudaStream_t s = (cudaStream_t)stream;
   const int key = (dxn_dtype << 2) | (y_dtype << 1) | dy_dtype;
   switch (key) {
-    case 0: return launch_ln_bwd<float, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 7: return launch_ln_bwd<bf16, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 1: return launch_ln_bwd<float, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 2: return launch_ln_bwd<float, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 3: return launch_ln_bwd<float, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 4: return launch_ln_bwd<bf16, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    case 5: return launch_ln_bwd<bf16, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
-    default: return launch_ln_bwd<bf16, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s);
+    case 0: return launch_ln_bwd<float, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 7: return launch_ln_bwd<bf16, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 1: return launch_ln_bwd<float, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 2: return launch_ln_bwd<float, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 3: return launch_ln_bwd<float, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 4: return launch_ln_bwd<bf16, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 5: return launch_ln_bwd<bf16, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    default: return launch_ln_bwd<bf16, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
   }
+}
+
+int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+               const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
+               void* stream) {
+  return ln_bwd_impl(dxn, dxn_dtype, y, y_dtype, mean, rstd, ln_w, M, C, dy, dy_dtype, partial, P, stream, 0, 0);
+}
+
+int cnx_ln_bwd_patch2(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+                      const float* ln_w, int64_t N, int64_t H, int64_t W, int64_t C, void* dy, int dy_dtype, float* partial,
+                      int P, void* stream) {
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, CNX_E_SHAPE, "ln_bwd_patch2: H=%lld, W=%lld must be even",
+              (long long)H, (long long)W);
+  return ln_bwd_impl(dxn, dxn_dtype, y, y_dtype, mean, rstd, ln_w, N * H * W, C, dy, dy_dtype, partial, P, stream, (int)H,
+                     (int)W);
 }
 
 }  // extern "C"

@@ -348,9 +348,12 @@ class _DownsampleFn(torch.autograd.Function):
         C2 = conv_w.shape[0]
         xl = _nhwc(x.detach())
         M = N * H * W
-        xn, mean, rstd = _ln_fwd(xl.reshape(M, C), ln_w, ln_b, eps, act_dtype)
+        # LayerNorm writes the GEMM operand directly in 2x2-patch-major order (no gather pass)
         A = torch.empty((M // 4, 4 * C), dtype=act_dtype, device=x.device)
-        L.check(lib.cnx_patch2(L.ptr(xn), L.dt(act_dtype), N, H, W, C, L.ptr(A), 1, L.stream()), "patch2")
+        mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+        L.check(lib.cnx_ln_fwd_patch2(L.ptr(xl), L.dt(xl), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C, L.ptr(A), L.dt(act_dtype),
+                                      L.ptr(mean), L.ptr(rstd), L.stream()), "ln_fwd_patch2")
         out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
         if ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5]):
             ctx.save_for_backward(xl, mean, rstd, A, conv_w, ln_w)
@@ -376,10 +379,15 @@ class _DownsampleFn(torch.autograd.Function):
         # data gradient: dA = d2 . Wp  (B operand = Wp^T [4C, C2]) -> scatter back to pixel order -> LayerNorm backward
         wpt = _derived((conv_w,), ("patchwT", act_dtype),
                        lambda: conv_w.detach().permute(2, 3, 1, 0).reshape(4 * C, C2).to(act_dtype).contiguous())
-        dA = _gemm_plain(d2, wpt, None, act_dtype)
-        dxn = torch.empty((M, C), dtype=act_dtype, device=dA.device)
-        L.check(lib.cnx_patch2(L.ptr(dA), L.dt(act_dtype), N, H, W, C, L.ptr(dxn), 0, L.stream()), "patch2")
-        dxl, dlw, dlb = _ln_bwd(dxn, xl.reshape(M, C), mean, rstd, ln_w, xl.dtype)
+        dA = _gemm_plain(d2, wpt, None, act_dtype)            # patch-major; the LayerNorm backward reads it in place
+        P = max(1, min(_num_partials(C), (M + 7) // 8))
+        dxl = torch.empty((M, C), dtype=xl.dtype, device=dA.device)
+        part = torch.empty((P, 2 * C), dtype=torch.float32, device=dA.device)
+        L.check(lib.cnx_ln_bwd_patch2(L.ptr(dA), L.dt(dA), L.ptr(xl), L.dt(xl), L.ptr(mean), L.ptr(rstd), L.ptr(ln_w), N, H, W, C,
+                                      L.ptr(dxl), L.dt(xl.dtype), L.ptr(part), P, L.stream()), "ln_bwd_patch2")
+        dwb = torch.empty((2 * C,), dtype=torch.float32, device=dA.device)
+        L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
+        dlw, dlb = dwb[:C], dwb[C:]
         dx = dxl.view(N, H, W, C).permute(0, 3, 1, 2)
         return dx, dlw, dlb, dW, db, None, None
 

@@ -122,6 +122,15 @@ CNX_API int cnx_ln_bwd(const void* dxn, int dxn_dtype, const void* y, int y_dtyp
                const float* ln_w, int64_t M, int64_t C, void* dy, int dy_dtype, float* partial, int P,
                void* stream);
 
+/* Downsample LayerNorm (convnext.py:84-89) fused with the 2x2 stride-2 patch gather: x [N,H,W,C] is normalised per pixel and
+ * written in patch-major order out [N,H/2,W/2,(ky,kx,C)] = the A operand of the patchify GEMM; the backward reads the GEMM's
+ * data gradient dxn in that same order.  mean/rstd/y/dy stay in pixel order. */
+CNX_API int cnx_ln_fwd_patch2(const void* x, int x_dtype, const float* ln_w, const float* ln_b, float eps, int64_t N, int64_t H,
+                      int64_t W, int64_t C, void* out, int out_dtype, float* mean, float* rstd, void* stream);
+CNX_API int cnx_ln_bwd_patch2(const void* dxn, int dxn_dtype, const void* y, int y_dtype, const float* mean, const float* rstd,
+                      const float* ln_w, int64_t N, int64_t H, int64_t W, int64_t C, void* dy, int dy_dtype, float* partial,
+                      int P, void* stream);
+
 /* out[j] = (accumulate ? out[j] : 0) + scale * sum_p partial[p, j], fixed order (deterministic). */
 CNX_API int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream);
