@@ -26,6 +26,11 @@ class EmaEntry(ctypes.Structure):
     _fields_ = [("ema", c_void_p), ("param", c_void_p), ("numel", c_int64), ("chunk_start", c_int64)]
 
 
+class WeightPrepEntry(ctypes.Structure):
+    _fields_ = [("W", c_void_p), ("row_scale", c_void_p), ("out", c_void_p), ("R", c_int64), ("Cc", c_int64),
+                ("mode", ctypes.c_int32), ("out_dtype", ctypes.c_int32), ("tile_start", c_int64), ("tiles_x", c_int64)]
+
+
 class AdamWEntry(ctypes.Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("ema", c_void_p), ("numel", c_int64), ("chunk_start", c_int64)]
@@ -58,6 +63,7 @@ SIGNATURES = {
     "cnx_gemm_wgrad": (c_int, [_P, _P, _L, _L, _L, _I, _P, _P, _P, _L, _I, _I, _P]),
     "cnx_grad_prep": (c_int, [_P, _I, _P, _L, _L, _L, _P, _I, _P]),
     "cnx_weight_prep": (c_int, [_P, _L, _L, _P, _I, _P, _I, _P]),
+    "cnx_weight_prep_multi": (c_int, [_P, _I, _L, _P]),
     "cnx_layerscale_finalize": (c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
     "cnx_cast_f32_to_bf16": (c_int, [_P, _L, _P, _P]),
     "cnx_patchify4_nchw": (c_int, [_P, _L, _L, _L, _L, _P, _I, _P]),
@@ -74,7 +80,7 @@ KERNELS_PER_CALL = {
     "cnx_mixup_target": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1,
     "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_dwconv7_weight_prep": 1, "cnx_gemm_bias_gelu_fwd": 1,
     "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2,
-    "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,
+    "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_weight_prep_multi": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,
     "cnx_patchify4_nchw": 1, "cnx_patch2": 1, "cnx_ln_fwd_patch2": 1, "cnx_ln_bwd_patch2": 1,
 }
 CALL_COUNTS = {k: 0 for k in KERNELS_PER_CALL}

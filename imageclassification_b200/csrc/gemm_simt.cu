@@ -232,6 +232,52 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
   }
 }
 
+// All derived weight layouts of a model in ONE launch: a device table of (source, scale, destination, shape, mode) entries,
+// one 32x32 tile per CTA found by binary search over the entries' first-tile prefix.  Replaces 4 launches per Block per step.
+struct WeightPrepEntry {
+  const float* W;
+  const float* row_scale;
+  void* out;
+  int64_t R, Cc;
+  int32_t mode, out_dtype;
+  int64_t tile_start;      // first CTA of this entry
+  int64_t tiles_x;         // ceil(Cc / 32)
+};
+
+__global__ void __launch_bounds__(256) weight_prep_multi_kernel(const WeightPrepEntry* __restrict__ table, int n) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.x;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].tile_start <= b) lo = mid; else hi = mid - 1;
+  }
+  const WeightPrepEntry e = table[lo];
+  const int64_t t = b - e.tile_start;
+  const int64_t r0 = (t / e.tiles_x) * 32, c0 = (t % e.tiles_x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < e.R && c < e.Cc) {
+      v = e.W[r * e.Cc + c];
+      if (e.mode == 2 && e.row_scale) v *= e.row_scale[r];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int64_t r, c, o;
+    float v;
+    if (e.mode == 0) { r = r0 + i; c = c0 + tx; o = r * e.Cc + c; v = tile[i][tx]; }
+    else { c = c0 + i; r = r0 + tx; o = c * e.R + r; v = tile[tx][i]; }
+    if (r < e.R && c < e.Cc) {
+      if (e.out_dtype == CNX_F32) reinterpret_cast<float*>(e.out)[o] = v;
+      else reinterpret_cast<bf16*>(e.out)[o] = from_f32<bf16>(v);
+    }
+  }
+}
+
 // one CTA per channel c: dgamma[c] = sum_k W2[c,k]*G2[c,k] + b2[c]*s[c]; dW2[c,:] = gamma[c]*G2[c,:]
 __global__ void __launch_bounds__(256) layerscale_finalize_kernel(const float* __restrict__ G2, const float* __restrict__ s,
                                                                   const float* __restrict__ W2, const float* __restrict__ b2,
@@ -297,6 +343,13 @@ int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_s
   if (out_dtype == CNX_F32) weight_prep_kernel<float><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (float*)out);
   else weight_prep_kernel<bf16><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (bf16*)out);
   return check_launch("weight_prep");
+}
+
+int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_tiles, void* stream) {
+  CNX_REQUIRE(table_dev && n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), CNX_E_BADARG,
+              "weight_prep_multi: bad argument");
+  weight_prep_multi_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const WeightPrepEntry*)table_dev, n_entries);
+  return check_launch("weight_prep_multi");
 }
 
 int cnx_layerscale_finalize(const float* G2, const float* s, const float* W2, const float* b2, const float* gamma,

@@ -11,6 +11,16 @@ namespace cnx {
 
 constexpr int LN_WARPS = 8;
 
+static bool ln_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_LN_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+
 // pixel row m of an [N,H,W] grid -> its row in the 2x2-patch-major order [N,H/2,W/2,(ky,kx)] (pH == 0: identity).  Lets the
 // downsample LayerNorm write the patchify-GEMM operand directly and its backward read the GEMM's data gradient in place.
 __device__ __forceinline__ int64_t patch2_row(int64_t m, int pH, int pW) {
@@ -73,6 +83,84 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = fmaf((v[j][k] - mu) * rs, lw[j][k], lb[j][k]);
         store4(orow + vi * 4, o);
+      }
+    }
+  }
+}
+
+
+// ---- LayerNorm forward, second generation: LPP lanes per row, 8-element vectors, U rows in flight per warp pass ----
+template <typename TX, typename TO, int NJ, int LPP, int U>
+__global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_fwd_v2_kernel(const TX* __restrict__ x, const float* __restrict__ ln_w,
+                                                                     const float* __restrict__ ln_b, float eps, int64_t M, int C,
+                                                                     TO* __restrict__ out, float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out, int pH, int pW) {
+  constexpr int PPW = 32 / LPP;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPP, l = lane % LPP;
+  const int VPR = C >> 3;
+  const float invC = 1.0f / (float)C;
+  float lw[NJ][8], lb[NJ][8];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int v = l + LPP * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lw[j][e] = v < VPR ? __ldg(ln_w + v * 8 + e) : 0.f; lb[j][e] = v < VPR ? __ldg(ln_b + v * 8 + e) : 0.f; }
+  }
+  const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp, tw = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t base = gw * (PPW * U); base < M; base += tw * (PPW * U)) {
+    float v[U][NJ][8];
+    int64_t row[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      row[u] = base + u * PPW + sub;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int vi = l + LPP * j;
+        if (row[u] < M && vi < VPR) load8(x + row[u] * C + vi * 8, v[u][j]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[u][j][e] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[u][j][e];
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mu = s * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (l + LPP * j < VPR) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { const float d = v[u][j][e] - mu; q = fmaf(d, d, q); }
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rs = rsqrtf(q * invC + eps);
+      if (row[u] < M) {
+        if (l == 0) {
+          if (mean_out) mean_out[row[u]] = mu;
+          if (rstd_out) rstd_out[row[u]] = rs;
+        }
+        TO* orow = out + patch2_row(row[u], pH, pW) * C;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int vi = l + LPP * j;
+          if (vi < VPR) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = fmaf((v[u][j][e] - mu) * rs, lw[j][e], lb[j][e]);
+            store8(orow + vi * 8, o8);
+          }
+        }
       }
     }
   }
@@ -275,15 +363,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(
   }
 }
 
-static bool ln_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CNX_LN_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
 static inline int nj_for(int64_t C) { return (int)((C / 4 + 31) / 32); }
 
 #define CNX_NJ_SWITCH(nj, ...)                                   \
@@ -305,6 +384,16 @@ static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, fl
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  if (C % 8 == 0 && C <= 256 && M >= 4096 && !ln_v1()) {
+    int64_t b2 = (int64_t)sm_count() * 3;
+    if (C <= 128)
+      ln_fwd_v2_kernel<TX, TO, 1, 16, 4><<<(unsigned)b2, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
+                                                                                mean, rstd, pH, pW);
+    else
+      ln_fwd_v2_kernel<TX, TO, 1, 32, 4><<<(unsigned)b2, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
+                                                                                mean, rstd, pH, pW);
+    return check_launch("ln_fwd");
+  }
   CNX_NJ_SWITCH(nj_for(C), (ln_fwd_kernel<TX, TO, NJ><<<(unsigned)blocks, LN_WARPS * 32, 0, s>>>(
                                (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, mean, rstd, pH, pW)));
   return check_launch("ln_fwd");

@@ -66,15 +66,79 @@ def _derived(params, tag, build):
     return val
 
 
-def _weight_prep(w: torch.Tensor, mode: int, row_scale, out_dtype) -> torch.Tensor:
-    def build():
+class _PrepRegistry:
+    """Every derived GEMM weight layout (bf16 copy, transpose, gamma-scaled transpose) of the live models on one device.
+    When any of them is found stale (the optimizer or load_state_dict wrote the parameters), ALL stale entries are rebuilt
+    by ONE cnx_weight_prep_multi launch over a cached device table instead of one launch per weight."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = {}          # (id(w), mode, dtype) -> dict(w=weakref, scale=weakref|None, out, key)
+        self.table = None          # (device table tensor, n, total_tiles, [entry keys in table order])
+        self._keepalive = None
+
+    def _drop(self, k):
+        self.entries.pop(k, None)
+        self.table = None
+
+    @staticmethod
+    def _key(w, scale):
+        return (w.data_ptr(), w._version) + ((scale.data_ptr(), scale._version) if scale is not None else ())
+
+    def get(self, w, mode, scale, out_dtype):
+        k = (id(w), mode, out_dtype)
+        e = self.entries.get(k)
+        if e is None or e["w"]() is not w:
+            R, Cc = w.shape
+            out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
+            e = {"w": weakref.ref(w), "scale": weakref.ref(scale) if scale is not None else None, "out": out, "key": None,
+                 "mode": mode, "dtype": out_dtype}
+            self.entries[k] = e
+            self.table = None
+            weakref.finalize(w, self._drop, k)
+        if e["key"] != self._key(w, scale):
+            self.refresh()
+        return e["out"]
+
+    def refresh(self):
         lib = L.load()
-        R, Cc = w.shape
-        out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
-        L.check(lib.cnx_weight_prep(L.ptr(w), R, Cc, L.ptr(row_scale), mode, L.ptr(out), L.dt(out_dtype), L.stream()),
-                "weight_prep")
-        return out
-    return _derived((w, row_scale), ("wprep", mode, out_dtype), build)
+        live = []
+        for k, e in list(self.entries.items()):
+            w = e["w"]()
+            sc = e["scale"]() if e["scale"] is not None else None
+            if w is None or (e["scale"] is not None and sc is None):
+                self._drop(k)
+                continue
+            live.append((k, e, w, sc))
+        if self.table is None or self.table[3] != [(k, w.data_ptr(), sc.data_ptr() if sc is not None else 0) for k, e, w, sc in live]:
+            rows, start = [], 0
+            for k, e, w, sc in live:
+                R, Cc = w.shape
+                tx, ty = (Cc + 31) // 32, (R + 31) // 32
+                rows.append(L.WeightPrepEntry(w.data_ptr(), sc.data_ptr() if sc is not None else None, e["out"].data_ptr(), R, Cc,
+                                              e["mode"], L.dt(e["dtype"]), start, tx))
+                start += tx * ty
+            arr = (L.WeightPrepEntry * len(rows))(*rows)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            dev = host.to(self.device)
+            self.table = (dev, len(rows), start, [(k, w.data_ptr(), sc.data_ptr() if sc is not None else 0) for k, e, w, sc in live])
+        dev, n, total, _ = self.table
+        if n:
+            L.check(lib.cnx_weight_prep_multi(L.ptr(dev), n, total, L.stream()), "weight_prep_multi")
+        for k, e, w, sc in live:
+            e["key"] = self._key(w, sc)
+
+
+_PREP: dict = {}
+
+
+def _weight_prep(w: torch.Tensor, mode: int, row_scale, out_dtype) -> torch.Tensor:
+    if w.dtype != torch.float32 or not w.is_contiguous() or (row_scale is not None and row_scale.dtype != torch.float32):
+        raise TypeError("libcnx keeps canonical parameters as contiguous fp32 tensors")
+    reg = _PREP.get(w.device)
+    if reg is None:
+        reg = _PREP[w.device] = _PrepRegistry(w.device)
+    return reg.get(w, mode, row_scale, out_dtype)
 
 
 def _conv_weight_tap_major(conv_w: torch.Tensor) -> torch.Tensor:

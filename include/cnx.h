@@ -197,6 +197,12 @@ CNX_API int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, i
 CNX_API int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_scale, int mode, void* out,
                     int out_dtype, void* stream);
 
+/* The same for MANY weights in one launch.  table_dev: device array of n_entries
+ *   struct { const float* W; const float* row_scale; void* out; int64_t R, Cc; int32_t mode, out_dtype;
+ *            int64_t tile_start, tiles_x; }          (tile_start = prefix sum of ceil(R/32)*ceil(Cc/32), tiles_x = ceil(Cc/32))
+ * total_tiles = sum of the entries' tile counts. */
+CNX_API int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_tiles, void* stream);
+
 /* Layer-scale gradient from the UNSCALED fc2 wgrad G2[c,k] = sum_m dz[m,c] g[m,k], s[c] = sum_m dz[m,c]:
  *   dgamma[c] (+)= sum_k W2[c,k]*G2[c,k] + b2[c]*s[c];  dW2[c,k] (+)= gamma[c]*G2[c,k];  db2[c] (+)= gamma[c]*s[c]
  * (identity used instead of saving z = fc2 output).  gamma NULL -> 1 and dgamma skipped. */
