@@ -255,21 +255,31 @@ __global__ void __launch_bounds__(256) mixup_target_kernel(const int64_t* __rest
 // ================================================================================================
 // deterministic reduction of per-CTA partial sums: out[j] = scale * sum_p partial[p, j]
 // ================================================================================================
+// 32 columns per CTA; the 8 warps split the P rows (fixed assignment), then meet in shared memory in a fixed order:
+// deterministic, and a tall narrow partial buffer (P = several hundred CTAs x 2C columns) no longer runs on one warp's latency
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int P, int64_t L,
                                                               float scale, int accumulate, float* __restrict__ out) {
-  int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (j >= L) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int p = 0;
-  for (; p + 4 <= P; p += 4) {
-    s0 += partial[(int64_t)(p + 0) * L + j];
-    s1 += partial[(int64_t)(p + 1) * L + j];
-    s2 += partial[(int64_t)(p + 2) * L + j];
-    s3 += partial[(int64_t)(p + 3) * L + j];
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f;
+  if (j < L) {
+    int p = ty;
+    for (; p + 8 < P; p += 16) {
+      s0 += partial[(int64_t)p * L + j];
+      s1 += partial[(int64_t)(p + 8) * L + j];
+    }
+    if (p < P) s0 += partial[(int64_t)p * L + j];
   }
-  for (; p < P; ++p) s0 += partial[(int64_t)p * L + j];
-  float s = ((s0 + s1) + (s2 + s3)) * scale;
-  out[j] = accumulate ? out[j] + s : s;
+  red[ty][tx] = s0 + s1;
+  __syncthreads();
+  if (ty == 0 && j < L) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][tx];
+    s *= scale;
+    out[j] = accumulate ? out[j] + s : s;
+  }
 }
 
 // the same reduction for the two outputs of one split-K wgrad (weight gradient + bias gradient) in ONE launch
@@ -384,8 +394,8 @@ int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, do
 int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream) {
   CNX_REQUIRE(partial && out && P > 0 && L > 0, CNX_E_BADARG, "reduce_partials: bad argument");
-  reduce_partials_kernel<<<(unsigned)((L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, P, L, scale,
-                                                                                         accumulate, out);
+  reduce_partials_kernel<<<(unsigned)((L + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, P, L, scale,
+                                                                                       accumulate, out);
   return check_launch("reduce_partials");
 }
 

@@ -36,7 +36,7 @@ class _TableUploader:
             self.events[s] = None
         if self.events[s] is not None:
             self.events[s].synchronize()
-        self.slots[s][:n].copy_(torch.from_numpy(np.frombuffer(raw, dtype=np.uint8)))
+        self.slots[s][:n].copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
         dev = torch.empty(n, dtype=torch.uint8, device=device)
         dev.copy_(self.slots[s][:n], non_blocking=True)
         ev = torch.cuda.Event()

@@ -1,0 +1,123 @@
+"""stem (Conv2d 4x4 s4 + LayerNorm2d) and downsample (LayerNorm2d + Conv2d 2x2 s2) as patchify + GEMM +
+LayerNorm kernels, against stock torch ops (fp32 reference; fp32 bar <= 1e-4 relative, bf16 bar <= 2e-2), plus the raw
+re-ordering kernels (bit-exact: pure data movement)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cabi import max_rel
+from imageclassification_b200 import _lib as L, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _st():
+    return L.stream()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 48), (1, 3, 224, 224), (3, 4, 8, 8)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_patchify4_is_unfold(shape, dt):
+    N, C, H, W = shape
+    x = torch.randn(shape, device=DEV)
+    out = torch.empty((N * (H // 4) * (W // 4), C * 16), dtype=dt, device=DEV)
+    L.check(L.load().cnx_patchify4_nchw(L.ptr(x), N, C, H, W, L.ptr(out), L.dt(dt), _st()), "patchify4")
+    ref = F.unfold(x, kernel_size=4, stride=4).transpose(1, 2).reshape(-1, C * 16).to(dt)     # (ci, ky, kx) flattening
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 6, 8), (1, 56, 56, 96), (3, 2, 2, 32)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_patch2_roundtrip(shape, dt):
+    N, H, W, C = shape
+    x = torch.randn(shape, device=DEV).to(dt)
+    g = torch.empty((N, H // 2, W // 2, 4 * C), dtype=dt, device=DEV)
+    L.check(L.load().cnx_patch2(L.ptr(x), L.dt(dt), N, H, W, C, L.ptr(g), 1, _st()), "patch2")
+    ref = x.view(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * C)
+    assert torch.equal(g, ref)
+    back = torch.empty_like(x)
+    L.check(L.load().cnx_patch2(L.ptr(g), L.dt(dt), N, H, W, C, L.ptr(back), 0, _st()), "patch2")
+    assert torch.equal(back, x)
+
+
+def _run(fn, params, x, dout, autocast):
+    for p in params:
+        p.grad = None
+    xr = x.clone().requires_grad_(x.is_floating_point() and fn.__name__ != "stem")
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out = fn(xr)
+    out.float().backward(dout)
+    return out.float(), [p.grad.clone() for p in params], (xr.grad.clone() if xr.grad is not None else None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,H,C", [(2, 32, 96), (1, 64, 64), (3, 16, 32)])
+def test_stem_fwd_bwd(mode, N, H, C):
+    torch.manual_seed(N * H + C)
+    conv = torch.nn.Conv2d(3, C, 4, 4).to(DEV)
+    lw = (1 + 0.1 * torch.randn(C)).to(DEV).requires_grad_(True)
+    lb = (0.1 * torch.randn(C)).to(DEV).requires_grad_(True)
+    x = torch.randn(N, 3, H, H, device=DEV)
+    dout = torch.randn(N, C, H // 4, H // 4, device=DEV)
+    params = [conv.weight, conv.bias, lw, lb]
+
+    def ref(xx):
+        y = conv(xx)
+        return F.layer_norm(y.permute(0, 2, 3, 1), (C,), lw, lb, 1e-6).permute(0, 3, 1, 2)
+
+    def stem(xx):
+        return ops.stem_forward(xx, conv.weight, conv.bias, lw, lb, 1e-6)
+
+    ro, rg, _ = _run(ref, params, x, dout, mode == "bf16")
+    oo, og, _ = _run(stem, params, x, dout, mode == "bf16")
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert max_rel(oo, ro) <= tol
+    for a, b in zip(og, rg):
+        assert max_rel(a, b) <= (2e-4 if mode == "fp32" else 2e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,H,C", [(2, 28, 96), (1, 14, 192), (3, 8, 32), (2, 14, 384)])
+def test_downsample_fwd_bwd(mode, N, H, C):
+    torch.manual_seed(N * H + C + 1)
+    conv = torch.nn.Conv2d(C, 2 * C, 2, 2).to(DEV)
+    lw = (1 + 0.1 * torch.randn(C)).to(DEV).requires_grad_(True)
+    lb = (0.1 * torch.randn(C)).to(DEV).requires_grad_(True)
+    x = torch.randn(N, C, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    dout = torch.randn(N, 2 * C, H // 2, H // 2, device=DEV)
+    params = [conv.weight, conv.bias, lw, lb]
+
+    def ref(xx):
+        y = F.layer_norm(xx.permute(0, 2, 3, 1), (C,), lw, lb, 1e-6).permute(0, 3, 1, 2)
+        return conv(y)
+
+    def down(xx):
+        return ops.downsample_forward(xx, lw, lb, conv.weight, conv.bias, 1e-6)
+
+    ro, rg, rx = _run(ref, params, x, dout, mode == "bf16")
+    oo, og, ox = _run(down, params, x, dout, mode == "bf16")
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert max_rel(oo, ro) <= tol
+    assert max_rel(ox.float(), rx.float()) <= (2e-4 if mode == "fp32" else 3e-2)
+    for a, b in zip(og, rg):
+        assert max_rel(a, b) <= (2e-4 if mode == "fp32" else 3e-2)
+
+
+def test_weight_prep_registry_refreshes_all_in_one_launch():
+    """The derived-weight registry rebuilds every stale layout with ONE cnx_weight_prep_multi call."""
+    ws = [torch.randn(64 + 32 * i, 96, device=DEV) for i in range(3)]
+    sc = torch.rand(64, device=DEV) + 0.5
+    outs = [ops._weight_prep(w, 1, None, torch.bfloat16) for w in ws] + [ops._weight_prep(ws[0], 2, sc, torch.bfloat16)]
+    for w, o in zip(ws, outs):
+        assert torch.equal(o, w.t().to(torch.bfloat16))
+    assert torch.equal(outs[3], (ws[0] * sc[:, None]).t().to(torch.bfloat16))
+    with torch.no_grad():
+        for w in ws:
+            w.mul_(2.0)                        # bumps the versions: everything is stale
+    c0 = L.CALL_COUNTS["cnx_weight_prep_multi"]
+    again = [ops._weight_prep(w, 1, None, torch.bfloat16) for w in ws] + [ops._weight_prep(ws[0], 2, sc, torch.bfloat16)]
+    assert L.CALL_COUNTS["cnx_weight_prep_multi"] - c0 == 1
+    for w, o in zip(ws, again):
+        assert torch.equal(o, w.t().to(torch.bfloat16))
+    assert torch.equal(again[3], (ws[0] * sc[:, None]).t().to(torch.bfloat16))
