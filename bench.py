@@ -140,6 +140,9 @@ def kernel_work(name, a):
         M, N, K = a[9:12]
         e, s = es(a[12]), es(a[8])
         return (M * K + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
+    if name == "cnx_mlp_fused_fwd":
+        M, C = a[10:12]
+        return M * C * (2 + 4 + 4) + 8 * C * C * 2, 16 * M * C * C, f"mlp_fused_fwd C{C}"
     if name == "cnx_gemm_dgrad_gelu_bwd":
         M, N, K = a[4:7]
         e = es(a[7])

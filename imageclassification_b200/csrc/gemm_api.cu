@@ -13,6 +13,9 @@ int gemm_wgrad_simt(const void* X, const void* Y, int64_t M, int64_t N1, int64_t
                     float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                   float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                     const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
+                     cudaStream_t s);
 int64_t wgrad_workspace_bytes_simt(int64_t M, int64_t N1, int64_t N2);
 int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2);
 }  // namespace cnx
@@ -56,6 +59,14 @@ int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float*
   }
   if (stream_dtype == CNX_F32) return gemm_tn_tc<EPI_SCALE_RES, float>(A, W2, M, N, K, ep, s);
   return gemm_tn_tc<EPI_SCALE_RES, bf16>(A, W2, M, N, K, ep, s);
+}
+
+int cnx_mlp_fused_fwd(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
+                      void* stream) {
+  CNX_REQUIRE(xn && W1 && b1 && W2 && b2 && shortcut && out, CNX_E_BADARG, "mlp_fused_fwd: null pointer");
+  CNX_REQUIRE(M > 0 && rows_per_sample > 0, CNX_E_BADARG, "mlp_fused_fwd: bad shape");
+  return mlp_fused_fwd_tc(xn, W1, b1, W2, b2, gamma, dp, rows_per_sample, shortcut, out, M, C, (cudaStream_t)stream);
 }
 
 int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,

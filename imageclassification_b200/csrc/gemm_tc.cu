@@ -985,6 +985,272 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 }
 
 // ================================================================================================
+// Fused MLP forward for the HBM-bound stages (C <= 192), no-grad pass:
+//     out = x + dp * gamma * ( GELU(xn . W1^T + b1) . W2^T + b2 )
+// in ONE kernel: the [M, 4C] hidden activation never leaves the SM.  Per 128-row tile, the hidden dimension is walked in
+// 64-column chunks: GEMM1 (tcgen05, K = C) -> TMEM acc1 (double-buffered) -> 16 epilogue warps (bias + GELU, bf16) write the
+// chunk into shared memory in the K-major 128B-swizzled layout of an MMA A operand -> GEMM2 (K = 64) accumulates the [128, C]
+// output tile in TMEM acc2.  The final epilogue adds bias / layer-scale / drop-path / residual through per-warp TMA slabs.
+// HBM traffic per token: C*2 (xn) + C*4 (x) + C*4 (out) bytes instead of that plus 2 * 4C*2 for the hidden round trip.
+// ================================================================================================
+constexpr int kFuHCH = 64;                         // hidden columns per chunk
+constexpr int kFuEpiWarps = 16;
+constexpr int kFuThreads = (kFirstEpiWarp + kFuEpiWarps) * 32;
+
+template <int C> struct FuCfg {
+  static constexpr int KBX = (C + 63) / 64;                 // 64-wide K boxes of the xn / W1 tiles
+  static constexpr int XN_BYTES = KBX * BM * 128;           // [128 rows][64 k] boxes
+  static constexpr int W1_BYTES = KBX * kFuHCH * 128;       // [64 hidden rows][64 k] boxes
+  static constexpr int W2_BYTES = C * 128;                  // [C out rows][64 hidden k]
+  static constexpr int WST_BYTES = W1_BYTES + W2_BYTES;
+  static constexpr int G_BYTES = BM * 128;                  // [128 rows][64 hidden] bf16
+  static constexpr int NXBUF = (C <= 96) ? 2 : 1;
+  static constexpr int NCH32 = C / 32;                      // 32-column chunks of the output tile
+  static constexpr int NSLABW = (NCH32 * 4 <= kFuEpiWarps) ? NCH32 * 4 : 8;   // warps that run the final epilogue
+  static constexpr int ITEMS = NCH32 * 4 / NSLABW;          // (quarter, chunk) items per such warp
+  static constexpr int NBARS = 2 * NXBUF + 4 + 4 + 4 + 2 + NSLABW + 1;
+  static constexpr int SMEM = NXBUF * XN_BYTES + 2 * WST_BYTES + 2 * G_BYTES + NSLABW * kSlabBytes + 1024 + 8 * NBARS + 64;
+  static constexpr int ACC2_COL = 128;
+  static_assert(C % 32 == 0 && C <= 256 && (NCH32 * 4) % NSLABW == 0, "fused MLP tile shape");
+  static_assert(SMEM <= 227 * 1024, "fused MLP does not fit in shared memory");
+};
+
+template <int C>
+__global__ void __launch_bounds__(kFuThreads, 1)
+mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
+                     const __grid_constant__ CUtensorMap tmOut, int64_t M, const float* __restrict__ b1,
+                     const float* __restrict__ b2, const float* __restrict__ gamma, const float* __restrict__ dp,
+                     int64_t rows_per_sample) {
+  typedef FuCfg<C> Cfg;
+  constexpr int NJ = 4 * C / kFuHCH;                 // hidden chunks per tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sXn = base;
+  const uint32_t sW = sXn + Cfg::NXBUF * Cfg::XN_BYTES;
+  const uint32_t sG = sW + 2 * Cfg::WST_BYTES;
+  const uint32_t sSlab = sG + 2 * Cfg::G_BYTES;
+  const uint32_t bars = sSlab + Cfg::NSLABW * kSlabBytes;
+  int bi = 0;
+  auto nb = [&](int n) { const uint32_t a = bars + 8u * bi; bi += n; return a; };
+  const uint32_t xn_full = nb(Cfg::NXBUF), xn_empty = nb(Cfg::NXBUF);
+  const uint32_t w_full = nb(2), w_empty = nb(2);
+  const uint32_t a1_full = nb(2), a1_empty = nb(2);
+  const uint32_t g_full = nb(2), g_empty = nb(2);
+  const uint32_t a2_full = nb(1), a2_empty = nb(1);
+  const uint32_t res_full = nb(Cfg::NSLABW);
+  const uint32_t tmem_slot = nb(1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmXn); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmRes); tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::NXBUF; ++i) { mbar_init(xn_full + 8 * i, 1); mbar_init(xn_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1);
+      mbar_init(a1_full + 8 * i, 1); mbar_init(a1_empty + 8 * i, kFuEpiWarps);
+      mbar_init(g_full + 8 * i, kFuEpiWarps); mbar_init(g_empty + 8 * i, 1);
+    }
+    mbar_init(a2_full, 1); mbar_init(a2_empty, Cfg::NSLABW);
+    for (int i = 0; i < Cfg::NSLABW; ++i) mbar_init(res_full + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: the xn tile once per tile, one (W1 chunk, W2 chunk) weight stage per hidden chunk =====
+      uint32_t xc = 0, wc = 0;
+      for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+        const uint32_t xb = xc % Cfg::NXBUF, xu = xc / Cfg::NXBUF;
+        mbar_wait(xn_empty + 8 * xb, (xu & 1) ^ 1);
+        mbar_expect_tx(xn_full + 8 * xb, Cfg::XN_BYTES);
+        for (int kb = 0; kb < Cfg::KBX; ++kb)
+          tma_load_2d(sXn + xb * Cfg::XN_BYTES + kb * (BM * 128), &tmXn, xn_full + 8 * xb, kb * 64, (int32_t)(tile * BM));
+        ++xc;
+        for (int j = 0; j < NJ; ++j, ++wc) {
+          const uint32_t ws = wc & 1, wu = wc >> 1;
+          mbar_wait(w_empty + 8 * ws, (wu & 1) ^ 1);
+          mbar_expect_tx(w_full + 8 * ws, Cfg::WST_BYTES);
+          for (int kb = 0; kb < Cfg::KBX; ++kb)
+            tma_load_2d(sW + ws * Cfg::WST_BYTES + kb * (kFuHCH * 128), &tmW1, w_full + 8 * ws, kb * 64, j * kFuHCH);
+          tma_load_2d(sW + ws * Cfg::WST_BYTES + Cfg::W1_BYTES, &tmW2, w_full + 8 * ws, j * kFuHCH, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: GEMM1(j) runs one chunk ahead of GEMM2(j-1) so the GELU epilogue of chunk j-1 overlaps it =====
+      constexpr uint32_t idesc1 = make_idesc(BM, kFuHCH, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc(BM, C, 0, 0);
+      uint32_t xc = 0, cc = 0, tc_ = 0;             // tile / chunk counters (chunk counter is shared by acc1, G and weight rings)
+      for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++xc, ++tc_) {
+        const uint32_t xb = xc % Cfg::NXBUF, xu = xc / Cfg::NXBUF;
+        mbar_wait(xn_full + 8 * xb, xu & 1);
+        for (int j = 0; j <= NJ; ++j) {
+          if (j < NJ) {
+            const uint32_t c = cc + j, b = c & 1, u = c >> 1;
+            mbar_wait(w_full + 8 * b, u & 1);
+            mbar_wait(a1_empty + 8 * b, (u & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d1 = tmem_base + b * kFuHCH;
+#pragma unroll
+            for (int kb = 0; kb < Cfg::KBX; ++kb) {
+              const uint64_t adesc = make_smem_desc(sXn + xb * Cfg::XN_BYTES + kb * (BM * 128), 16, 1024);
+              const uint64_t bdesc = make_smem_desc(sW + b * Cfg::WST_BYTES + kb * (kFuHCH * 128), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (kb * 64 + k * 16 < C) umma_f16(d1, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+            }
+            umma_commit(a1_full + 8 * b);
+            if (j == NJ - 1) umma_commit(xn_empty + 8 * xb);
+          }
+          if (j > 0) {
+            const uint32_t c = cc + j - 1, b = c & 1, u = c >> 1;
+            mbar_wait(g_full + 8 * b, u & 1);
+            if (j == 1) mbar_wait(a2_empty, (tc_ & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(sG + b * Cfg::G_BYTES, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(sW + b * Cfg::WST_BYTES + Cfg::W1_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + Cfg::ACC2_COL, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc2, ((j - 1) | k) != 0);
+            umma_commit(g_empty + 8 * b);
+            umma_commit(w_empty + 8 * b);
+            if (j == NJ) umma_commit(a2_full);
+          }
+        }
+        cc += NJ;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    const int ew = warp - kFirstEpiWarp;
+    const int quarter = warp & 3;
+    const int cg = ew >> 2;                           // 16 of the chunk's 64 hidden columns
+    const int r = quarter * 32 + lane;                // row within the tile
+    const uint32_t lane_t = (uint32_t)(quarter * 32) << 16;
+    const uint32_t g_row = (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t slab = sSlab + (uint32_t)ew * kSlabBytes;
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t rswz = (uint32_t)(lane & 7);
+    const bool fin = ew < Cfg::NSLABW;
+    uint32_t cc = 0, tc_ = 0, rc = 0;                 // chunk counter, tile counter, residual-slab load counter
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++tc_) {
+      const int32_t y0 = (int32_t)(tile * BM + quarter * 32);
+      if (fin && lane == 0) {
+        // the residual slab of this warp's first output item: in flight during the whole chunk loop
+        bulk_wait_read0();
+        mbar_expect_tx(res_full + 8 * ew, kSlabBytes);
+        tma_load_2d(slab, &tmRes, res_full + 8 * ew, (int32_t)((ew >> 2) * 32), y0);
+      }
+      for (int j = 0; j < NJ; ++j, ++cc) {
+        const uint32_t b = cc & 1, u = cc >> 1;
+        mbar_wait(a1_full + 8 * b, u & 1);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(tmem_base + b * kFuHCH + lane_t + cg * 16, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a1_empty + 8 * b);
+        uint32_t pg[8];
+        const float* bp = b1 + j * kFuHCH + cg * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+          const float2 ha = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
+          const float2 hb = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
+          const uint32_t ua = pack_bf16(ha.x, ha.y), ub = pack_bf16(hb.x, hb.y);   // h rounded to bf16 (autocast's Linear output)
+          float2 ga, gb, da, db;
+          gelu_pair<false>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+          gelu_pair<false>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+          pg[i / 2] = pack_bf16(ga.x, ga.y);
+          pg[i / 2 + 1] = pack_bf16(gb.x, gb.y);
+        }
+        mbar_wait(g_empty + 8 * b, (u & 1) ^ 1);      // GEMM2 of two chunks ago has consumed this buffer
+        const uint32_t gb_ = sG + b * Cfg::G_BYTES + g_row;
+        sts128(gb_ + (((uint32_t)(cg * 2) ^ swz) << 4), pg[0], pg[1], pg[2], pg[3]);
+        sts128(gb_ + (((uint32_t)(cg * 2 + 1) ^ swz) << 4), pg[4], pg[5], pg[6], pg[7]);
+        fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_full + 8 * b);
+      }
+      if (fin) {
+        // ===== final epilogue: this warp's (quarter, 32-column chunk) items of the [128, C] output tile =====
+        mbar_wait(a2_full, tc_ & 1);
+        tc_fence_after();
+        const int64_t m = tile * BM + r;
+        float sc = 1.0f;
+        if (dp) sc = __ldg(dp + (m < M ? m : M - 1) / rows_per_sample);
+#pragma unroll 1
+        for (int it = 0; it < Cfg::ITEMS; ++it) {
+          const int ch = (ew >> 2) + (Cfg::NSLABW / 4) * it;
+          float v[32];
+          tmem_ld32(tmem_base + Cfg::ACC2_COL + lane_t + ch * 32, v);
+          tmem_ld_wait();
+          if (it == Cfg::ITEMS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a2_empty);
+          }
+          const int n0 = ch * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n0 + i));
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + n0 + i));
+            v[i] = sc * (g4.x * (v[i] + b4.x));
+            v[i + 1] = sc * (g4.y * (v[i + 1] + b4.y));
+            v[i + 2] = sc * (g4.z * (v[i + 2] + b4.z));
+            v[i + 3] = sc * (g4.w * (v[i + 3] + b4.w));
+          }
+          mbar_wait(res_full + 8 * ew, rc & 1);
+          ++rc;
+#pragma unroll
+          for (int jv = 0; jv < 8; ++jv) {
+            uint32_t a0, a1, a2, a3;
+            const uint32_t addr = slab + row_off + (((uint32_t)jv ^ rswz) << 4);
+            lds128(addr, a0, a1, a2, a3);
+            sts128(addr, __float_as_uint(v[4 * jv] + __uint_as_float(a0)), __float_as_uint(v[4 * jv + 1] + __uint_as_float(a1)),
+                   __float_as_uint(v[4 * jv + 2] + __uint_as_float(a2)), __float_as_uint(v[4 * jv + 3] + __uint_as_float(a3)));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, slab, (int32_t)n0, y0);
+            bulk_commit();
+            if (it + 1 < Cfg::ITEMS) {
+              bulk_wait_read0();
+              mbar_expect_tx(res_full + 8 * ew, kSlabBytes);
+              tma_load_2d(slab, &tmRes, res_full + 8 * ew, (int32_t)(((ew >> 2) + (Cfg::NSLABW / 4) * (it + 1)) * 32), y0);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (fin && lane == 0) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ================================================================================================
 // wgrad on CTA pairs: one tcgen05.mma.cta_group::2 spans a 256 x BN tile of out = X^T.Y (BN = 128 or 256).  Each CTA stages
 // its own 128 channels of X (two 64-channel MN-major boxes) and HALF of the BN channels of Y per 64-row k-block, so a CTA moves
 // 24 / 32 KB per k-block where the single-CTA 128 x 128 tile moves 32 KB for a quarter / half of the MACs.  Bias gradient,
@@ -1315,7 +1581,41 @@ static int launch_tn_staged(const void* A, const void* B, int64_t M, int64_t N, 
   return check_launch("gemm_tn_tc_staged");
 }
 
+
+// 2-D bf16 row-major tensor [rows, cols]; box = [box_rows][64 cols], 128-byte swizzle (make_map), used by the fused MLP
+template <int C>
+static int launch_mlp_fused(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                            const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, cudaStream_t s) {
+  typedef FuCfg<C> Cfg;
+  CUtensorMap tmXn, tmW1, tmW2, tmRes, tmOut;
+  if (int rc = make_map(&tmXn, xn, M, C, BM)) return rc;
+  if (int rc = make_map(&tmW1, W1, 4 * C, C, kFuHCH)) return rc;
+  if (int rc = make_map(&tmW2, W2, C, 4 * C, C)) return rc;
+  if (int rc = make_slab_map(&tmRes, shortcut, M, C, 4)) return rc;
+  if (int rc = make_slab_map(&tmOut, out, M, C, 4)) return rc;
+  auto k = mlp_fused_fwd_kernel<C>;
+  if (int rc = set_smem(k, Cfg::SMEM)) return rc;
+  int64_t grid = sm_count();
+  const int64_t tiles = (M + BM - 1) / BM;
+  if (grid > tiles) grid = tiles;
+  k<<<(unsigned)grid, kFuThreads, Cfg::SMEM, s>>>(tmXn, tmW1, tmW2, tmRes, tmOut, M, b1, b2, gamma, dp, rows_per_sample);
+  return check_launch("mlp_fused_fwd");
+}
+
 }  // namespace tc
+
+int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                     const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
+                     cudaStream_t s) {
+  if (C == 96) return tc::launch_mlp_fused<96>(xn, W1, b1, W2, b2, gamma, dp, rows_per_sample, shortcut, out, M, s);
+  if (C == 128) return tc::launch_mlp_fused<128>(xn, W1, b1, W2, b2, gamma, dp, rows_per_sample, shortcut, out, M, s);
+  if (C == 192) return tc::launch_mlp_fused<192>(xn, W1, b1, W2, b2, gamma, dp, rows_per_sample, shortcut, out, M, s);
+  set_error("mlp_fused_fwd: C=%lld is not a fused shape (96, 128, 192)", (long long)C);
+  return CNX_E_SHAPE;
+}
+
+namespace tc_unused {
+}  // namespace tc_unused
 
 template <int KIND, typename TOUT>
 int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {

@@ -10,6 +10,7 @@ Reference ops replaced:
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -18,6 +19,8 @@ from . import _lib as L
 
 # Test-only switch: route the bf16 GEMMs through the CUDA-core kernel to cross-check the tcgen05 path.
 GEMM_FLAGS = 0
+# The fused no-grad MLP kernel (C <= 192); CNX_FUSED_MLP=0 in the environment selects the two-GEMM path for comparison.
+FUSED_MLP = os.environ.get("CNX_FUSED_MLP", "1") != "0"
 
 
 def _act_dtype() -> torch.dtype:
@@ -168,7 +171,7 @@ class _BlockFn(torch.autograd.Function):
     """dwconv7 -> LN -> fc1 -> GELU -> fc2 -> gamma -> drop_path -> + shortcut, forward and backward."""
 
     @staticmethod
-    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps, act_dtype):
+    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps, act_dtype, track):
         lib = L.load()
         L.require_cuda(x, conv_w, w1, w2)
         if x.dtype not in (torch.float32, torch.bfloat16):
@@ -192,7 +195,17 @@ class _BlockFn(torch.autograd.Function):
             w1a = _weight_prep(w1, 0, None, act_dtype)
             w2a = _weight_prep(w2, 0, None, act_dtype)
         C4 = w1.shape[0]
-        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:10])
+        # `track` = grad mode of the CALLER (inside Function.forward grad mode is always off; needs_input_grad alone is True
+        # for parameters even under torch.no_grad())
+        need_grad = track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:10]))
+        if (not need_grad and FUSED_MLP and act_dtype == torch.bfloat16 and xl.dtype == torch.float32 and C in (96, 128, 192)
+                and C4 == 4 * C and M >= 128):
+            # no-grad pass (engine.py:89-97 accuracy forward, evaluate()): fc1 -> GELU -> fc2 -> gamma / drop-path / residual
+            # in one kernel, the hidden activation never reaches HBM
+            out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+            L.check(lib.cnx_mlp_fused_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), L.ptr(w2a), L.ptr(b2), L.ptr(gamma), L.ptr(dp), H * W,
+                                          L.ptr(xl), L.ptr(out), M, C, st), "mlp_fused_fwd")
+            return out.permute(0, 3, 1, 2)
         h = torch.empty((M, C4), dtype=act_dtype, device=dev) if need_grad else None
         g = torch.empty((M, C4), dtype=act_dtype, device=dev)
         L.check(lib.cnx_gemm_bias_gelu_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), M, C4, C, L.ptr(h), L.ptr(g), ad,
@@ -268,7 +281,7 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
                     "dwconv7_dgrad")
             dx = dxl.permute(0, 3, 1, 2)
-        return (dx, dconv_w, dconv_b, dln[:C], dln[C:], dW1, db1, dW2, db2, dgamma, None, None, None)
+        return (dx, dconv_w, dconv_b, dln[:C], dln[C:], dW1, db1, dW2, db2, dgamma, None, None, None, None)
 
 
 def block_forward(x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps: float):
@@ -276,7 +289,8 @@ def block_forward(x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps:
     act_dtype = _act_dtype()
     if act_dtype == torch.float32 and x.dtype != torch.float32:
         raise TypeError("fp32 mode (no autocast) needs an fp32 residual stream")
-    return _BlockFn.apply(x, conv_w.contiguous(), conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, float(eps), act_dtype)
+    return _BlockFn.apply(x, conv_w.contiguous(), conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, float(eps), act_dtype,
+                          torch.is_grad_enabled())
 
 
 class _LayerNormCLFn(torch.autograd.Function):
@@ -375,7 +389,7 @@ class _StemFn(torch.autograd.Function):
     Under bf16 autocast the conv output is rounded to bf16 and the LayerNorm output is fp32, as ATen's policies give."""
 
     @staticmethod
-    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, eps, act_dtype):
+    def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, eps, act_dtype, track):
         lib = L.load()
         L.require_cuda(x, conv_w, ln_w)
         N, Cin, H, W = x.shape
@@ -386,7 +400,7 @@ class _StemFn(torch.autograd.Function):
         L.check(lib.cnx_patchify4_nchw(L.ptr(xc), N, Cin, H, W, L.ptr(A), L.dt(act_dtype), L.stream()), "patchify4")
         y = _gemm_plain(A, _patch_weight(conv_w, act_dtype, False), conv_b, act_dtype)
         out, mean, rstd = _ln_fwd(y, ln_w, ln_b, eps, torch.float32)
-        if any(ctx.needs_input_grad[1:5]):
+        if track and any(ctx.needs_input_grad[1:5]):
             ctx.save_for_backward(A, y, mean, rstd, conv_w, ln_w)
             ctx.act_dtype = act_dtype
         return out.view(N, H // 4, W // 4, Cout).permute(0, 3, 1, 2)
@@ -398,14 +412,14 @@ class _StemFn(torch.autograd.Function):
         d2 = _nhwc(dout).reshape(M, Cout)
         dy, dlw, dlb = _ln_bwd(d2, y, mean, rstd, ln_w, ctx.act_dtype)
         dW, db = _wgrad(dy, A, M, Cout, A.shape[1], True)
-        return None, dW.view_as(conv_w), db, dlw, dlb, None, None
+        return None, dW.view_as(conv_w), db, dlw, dlb, None, None, None
 
 
 class _DownsampleFn(torch.autograd.Function):
     """downsample: LayerNorm2d -> Conv2d(C, C2, 2, stride 2) (convnext.py:84-89) as LayerNorm + 2x2 patch gather + GEMM."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, conv_w, conv_b, eps, act_dtype):
+    def forward(ctx, x, ln_w, ln_b, conv_w, conv_b, eps, act_dtype, track):
         lib = L.load()
         L.require_cuda(x, conv_w, ln_w)
         N, C, H, W = x.shape
@@ -419,7 +433,7 @@ class _DownsampleFn(torch.autograd.Function):
         L.check(lib.cnx_ln_fwd_patch2(L.ptr(xl), L.dt(xl), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C, L.ptr(A), L.dt(act_dtype),
                                       L.ptr(mean), L.ptr(rstd), L.stream()), "ln_fwd_patch2")
         out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
-        if ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5]):
+        if track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5])):
             ctx.save_for_backward(xl, mean, rstd, A, conv_w, ln_w)
             ctx.shape = (N, C, H, W)
             ctx.act_dtype = act_dtype
@@ -453,17 +467,17 @@ class _DownsampleFn(torch.autograd.Function):
         L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
         dlw, dlb = dwb[:C], dwb[C:]
         dx = dxl.view(N, H, W, C).permute(0, 3, 1, 2)
-        return dx, dlw, dlb, dW, db, None, None
+        return dx, dlw, dlb, dW, db, None, None, None
 
 
 def stem_forward(x, conv_w, conv_b, ln_w, ln_b, eps: float):
     """Conv2d(Cin, C, 4, 4) + LayerNorm2d on a [N,Cin,H,W] image batch -> logical [N,C,H/4,W/4] (channels-last memory)."""
-    return _StemFn.apply(x, conv_w, conv_b, ln_w, ln_b, float(eps), _act_dtype())
+    return _StemFn.apply(x, conv_w, conv_b, ln_w, ln_b, float(eps), _act_dtype(), torch.is_grad_enabled())
 
 
 def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float):
     """LayerNorm2d + Conv2d(C, C2, 2, 2) on a logical [N,C,H,W] stream -> logical [N,C2,H/2,W/2]."""
-    return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype())
+    return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype(), torch.is_grad_enabled())
 
 
 class _SoftTargetCEFn(torch.autograd.Function):

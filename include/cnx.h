@@ -168,6 +168,14 @@ CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, cons
                                      int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,
                                      void* stream);
 
+/* Fused no-grad MLP forward for the HBM-bound stages (C in {96, 128, 192}; bf16 operands, fp32 residual stream):
+ *   out[m,:] = shortcut[m,:] + dp[m / rows_per_sample] * gamma * (GELU_erf(xn[m,:].W1^T + b1).W2^T + b2)
+ * in one kernel — the [M,4C] hidden activation stays in shared / tensor memory (convnext.py:48-55 in one pass).
+ * xn [M,C] bf16, W1 [4C,C] bf16, W2 [C,4C] bf16, shortcut/out [M,C] fp32; dp, gamma may be NULL. */
+CNX_API int cnx_mlp_fused_fwd(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2,
+                      const float* gamma, const float* dp, int64_t rows_per_sample, const void* shortcut, void* out,
+                      int64_t M, int64_t C, void* stream);
+
 /* dgrad of fc2 with GELU': dh[m,n] = acc[m,n] * gprime[m,n],  acc = dz.W2s (B given as [N=4C, K=C]),
  * gprime = GELU'(h) as saved by cnx_gemm_bias_gelu_fwd. */
 CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,

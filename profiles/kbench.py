@@ -97,6 +97,8 @@ for si in [int(s) for s in args.stages.split(",")]:
         hh, gg = cabi.gemm_bias_gelu(A, W1, b1)
         timeit(f"fc1_bias_gelu {tag}", lambda: cabi.gemm_bias_gelu(A, W1, b1))
         xs = x.view(M, C)
+        if C <= 192:
+            timeit(f"mlp_fused_fwd {tag}", lambda: cabi.mlp_fused_fwd(A, W1, b1, W2, b2, gam, None, H * H, xs))
         timeit(f"fc2_scale_res {tag}", lambda: cabi.gemm_scale_res(gg, W2, b2, gam, None, H * H, xs, f32))
         W2t = W2.t().contiguous()
         timeit(f"dgrad_fc2_gelu {tag}", lambda: cabi.gemm_dgelu(A, W2t, hh))

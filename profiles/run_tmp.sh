@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_patchify_gpu.py -x -q 2>&1 | tail -n 15
+timeout 300 python profiles/kbench.py --only gemm --stages 0,1 --iters 3 2>&1 | grep -E "fc1|fc2_|fused"

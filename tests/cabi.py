@@ -140,3 +140,12 @@ def max_rel(a, b):
     """max |a-b| / max |b| — the 'relative on logits and gradients' measure of BASELINE.json north_star."""
     a, b = a.double(), b.double()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def mlp_fused_fwd(xn, W1, b1, W2, b2, gamma, dp, rps, shortcut):
+    lib = L.load()
+    M, C = xn.shape
+    out = torch.empty((M, C), dtype=torch.float32, device=xn.device)
+    L.check(lib.cnx_mlp_fused_fwd(L.ptr(xn), L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), L.ptr(gamma), L.ptr(dp), rps,
+                                  L.ptr(shortcut), L.ptr(out), M, C, _st()), "mlp_fused_fwd")
+    return out

@@ -110,3 +110,25 @@ def test_gemm_argument_errors():
     assert rc == -2 and b"multiple of 8" in lib.cnx_last_error_string()
     rc = lib.cnx_gemm_plain(None, L.ptr(a), None, L.ptr(a), 0, 8, 8, 12, 0, 0, L.stream())
     assert rc == -1
+
+
+@pytest.mark.parametrize("M,C", [(3136, 96), (128, 96), (1000, 192), (777, 128), (50176, 96), (4 * 784 + 5, 192)])
+@pytest.mark.parametrize("with_dp", [False, True])
+def test_fused_mlp_forward_matches_two_gemm_path(M, C, with_dp):
+    """The fused no-grad MLP kernel (hidden activation kept on chip) vs the fc1+GELU and fc2+residual GEMM kernels on the same
+    bf16 operands: same roundings (h and g to bf16), fp32 accumulation — differences are summation order only."""
+    from cabi import mlp_fused_fwd
+    A, W1, b1, W2, b2, gamma = _mk(M, C, torch.bfloat16, 5 * M + C)
+    rps = 49
+    n_s = (M + rps - 1) // rps
+    dp = ((torch.rand(n_s, device=DEV) > 0.3).float() / 0.7) if with_dp else None
+    sc = torch.randn(M, C, device=DEV)
+    _, g = gemm_bias_gelu(A, W1, b1, 0)
+    ref = gemm_scale_res(g, W2, b2, gamma, dp, rps, sc, torch.float32, 0)
+    out = mlp_fused_fwd(A, W1, b1, W2, b2, gamma, dp, rps, sc)
+    assert max_rel(out, ref) <= 2e-5
+    # and against fp32 torch on the bf16-rounded operands (the bf16 bar)
+    h = (A.float() @ W1.float().t() + b1).to(torch.bfloat16).float()
+    z = F.gelu(h).to(torch.bfloat16).float() @ W2.float().t() + b2
+    s = dp.repeat_interleave(rps)[:M, None] if with_dp else 1.0
+    assert max_rel(out, sc + s * (gamma * z)) <= 2e-2
