@@ -1,1 +1,3 @@
-timeout 300 python profiles/kbench.py --only gemm --stages 0,1 --iters 3 2>&1 | grep -E "fc1|fc2_|fused"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -n 25
+TAG=r01g bash profiles/run_evidence.sh

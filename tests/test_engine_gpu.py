@@ -1,0 +1,102 @@
+"""engine.train_one_epoch end to end (BASELINE configs 1 and 3): this package's objects and step
+loop on the B200 vs
+  * the golden numbers the REFERENCE'S OWN engine.py produced in the build container (tests/golden/engine_step.npz,
+    case "b": no drop-path, so no device-RNG dependence), and
+  * the oracle objects + oracle step loop run on the same device with the same seeds (drop-path, cutmix, gradient
+    accumulation, bf16 autocast, fused AdamW+EMA optimizer).
+Bars: fp32 <= 1e-4 relative on loss / parameter norms, bf16 <= 2e-2 (BASELINE.json north_star); EMA follows parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import imageclassification_b200 as P
+from imageclassification_b200 import engine as PE
+from imageclassification_b200 import optim as PO
+from oracle import convnext as OC, ema as OE, engine as OEng, loss as OL, mixup as OM
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _adamw(model, lr=1e-3, wd=5e-4):
+    return torch.optim.AdamW([{"params": list(model.parameters()), "weight_decay": wd}], lr=lr, weight_decay=0.0)
+
+
+def _norms(params):
+    return np.array([p.detach().double().norm().item() for p in params])
+
+
+def test_engine_matches_reference_golden_config1():
+    """BASELINE config 1 (ConvNeXt-T fp32, batch 8, 2 classes, mixup 0.8, smoothing 0.1, AdamW, EMA 0.9995), two iterations:
+    same seeds as tests/golden/make_golden.py case "b" => the loss, accuracy, parameters and EMA the reference's engine gave."""
+    z = np.load(os.path.join(GOLD, "engine_step.npz"))
+    torch.manual_seed(88)
+    np.random.seed(88)
+    o = OC.create_model("convnext_tiny", num_classes=2, drop_path_rate=0.0, ls_init_value=1.0)      # CPU init = golden's init
+    data = [(torch.randn(8, 3, 64, 64), torch.randint(0, 2, (8,))) for _ in range(2)]
+    model = P.create_model("convnext_tiny", num_classes=2, drop_path_rate=0.0, ls_init_value=1.0)
+    model.load_state_dict(o.state_dict())
+    model.to(DEV)
+    ema = P.ModelEmaV3(model, decay=0.9995, device=DEV)
+    mix = P.Mixup(mixup_alpha=0.8, cutmix_alpha=0.0, label_smoothing=0.1, num_classes=2)
+    stats = PE.train_one_epoch(model, P.SoftTargetCrossEntropy(), data, _adamw(model), DEV, 0, None, None, ema, mix,
+                               num_training_steps_per_epoch=2, update_freq=1, use_amp=False, num_classes=2, verbose=False)
+    assert abs(stats["loss"] - float(z["b.loss"])) <= 1e-4 * abs(float(z["b.loss"]))
+    assert stats["class_acc"] == float(z["b.class_acc"])
+    np.testing.assert_allclose(_norms(model.parameters()), z["b.param_norms"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(_norms(ema.module.parameters()), z["b.ema_norms"], rtol=1e-5, atol=1e-8)
+    ps = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    np.testing.assert_allclose(ps, z["b.param_sums"], rtol=0, atol=2e-3 * np.abs(z["b.param_norms"]).max())
+
+
+CASES = [
+    # tag, amp, img, batch, classes, dpr, gamma, cutmix, update_freq, fused optimizer
+    ("fp32_dp", False, 64, 8, 2, 0.05, 1.0, 0.0, 1, False),
+    ("fp32_cutmix_accum", False, 64, 8, 5, 0.0, 1.0, 1.0, 2, False),
+    ("fp32_fused_opt", False, 64, 8, 2, 0.0, 1.0, 0.0, 1, True),
+    ("bf16", True, 96, 16, 10, 0.05, 1.0, 1.0, 1, True),
+    ("bf16_tiny_gamma", True, 64, 8, 2, 0.0, 1e-6, 0.0, 2, False),
+]
+
+
+@pytest.mark.parametrize("tag,amp,img,batch,K,dpr,gamma,cutmix,uf,fused", CASES, ids=[c[0] for c in CASES])
+def test_engine_matches_oracle_engine(tag, amp, img, batch, K, dpr, gamma, cutmix, uf, fused):
+    torch.manual_seed(11)
+    o = OC.create_model("convnext_tiny", num_classes=K, drop_path_rate=dpr, ls_init_value=gamma).to(DEV)
+    p = P.create_model("convnext_tiny", num_classes=K, drop_path_rate=dpr, ls_init_value=gamma).to(DEV)
+    p.load_state_dict(o.state_dict())
+    g = torch.Generator().manual_seed(5)
+    n_it = 2 * uf
+    data = [(torch.randn(batch, 3, img, img, generator=g), torch.randint(0, K, (batch,), generator=g)) for _ in range(n_it)]
+    out = []
+    for eng, model, crit, mixc, emac in ((OEng, o, OL.SoftTargetCrossEntropy(), OM.Mixup, OE.ModelEmaV3),
+                                         (PE, p, P.SoftTargetCrossEntropy(), P.Mixup, P.ModelEmaV3)):
+        torch.manual_seed(3)                   # drop-path masks
+        np.random.seed(3)                      # mixup lambda / cutmix box
+        ema = emac(model, decay=0.9995, device=DEV)
+        mix = mixc(mixup_alpha=0.8, cutmix_alpha=cutmix, label_smoothing=0.1, num_classes=K)
+        if fused and eng is PE:
+            opt = PO.AdamW([{"params": list(model.parameters()), "weight_decay": 5e-4}], lr=1e-3, weight_decay=0.0)
+            opt.fuse_ema(ema, model)
+        else:
+            opt = _adamw(model)
+        kw = {"verbose": False} if eng is PE else {}
+        stats = eng.train_one_epoch(model, crit, [(a.clone(), b.clone()) for a, b in data], opt, DEV, 0, None, None, ema, mix,
+                                    num_training_steps_per_epoch=2, update_freq=uf, use_amp=amp, num_classes=K, **kw)
+        out.append((stats, _norms(model.parameters()), _norms(ema.module.parameters()),
+                    torch.cat([q.detach().flatten() for q in model.parameters()]).double()))
+    (so, no, eo, fo), (sp, npar, ep, fp) = out
+    tol = 2e-2 if amp else 1e-4
+    assert abs(sp["loss"] - so["loss"]) <= tol * abs(so["loss"]), (sp, so)
+    np.testing.assert_allclose(npar, no, rtol=tol, atol=1e-6)
+    np.testing.assert_allclose(ep, eo, rtol=tol * 1e-2 + 1e-6, atol=1e-8)
+    if not amp:
+        # Adam's first steps move every weight by ~lr*sign(g): compare the parameter vectors themselves (gradient-sign flips on
+        # near-zero gradients are the only admissible differences; they are bounded by 2*lr per element)
+        d = (fp - fo).abs()
+        assert d.max().item() <= 2 * 2e-3 + 1e-6
+        assert (d > 1e-5).double().mean().item() <= 1e-2
+        assert sp["class_acc"] == so["class_acc"]
