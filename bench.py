@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW instead of the fused AdamW+EMA")
+    ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: in-line H2D copies on the compute stream")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
     return ap.parse_args()
 
@@ -54,23 +55,61 @@ def workload_name(a):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed regions.  In-process NVML (nvidia_ml_py) every 50 ms: a
+    query costs microseconds.  (Spawning `nvidia-smi` instead re-initialises NVML over every GPU of the box each time and was
+    measured to stall this process's CUDA calls for ~100 ms — 10 ms per step over a 10-step region; kept only as a fallback.)"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         self.rows, self.stop, self.index = [], threading.Event(), index
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = 0.0
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.rows.append([str(sm), str(self.max_sm), str(pw)] + ["Active" if mask & m else "Not Active" for _, m in self.MASKS])
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(float(os.environ.get("CNX_CLOCK_PERIOD", "0.05")) if self.nvml is not None else 1.0)
 
     def __enter__(self):
         self.t.start()
@@ -82,12 +121,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = [n for n, _ in self.MASKS]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ roofline
@@ -208,7 +248,7 @@ def run_ours(a):
         if a.no_acc_forward:
             return _fast_epoch(batches)
         return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=True,
-                                       num_classes=a.classes, verbose=False)
+                                       num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch)
 
     def _fast_epoch(batches):
         net.train(True)
@@ -301,10 +341,12 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "params": n_params, "optimizer": "torch.optim.AdamW" if a.torch_adamw else "libcnx fused AdamW+EMA",
                    "l2": "activation footprint per step >> 126 MB L2 (inputs larger than L2, no explicit flush)",
-                   "final_loss": stats.get("loss")},
+                   "final_loss": stats.get("loss"),
+                   "residual_stream": "bf16 in stages 1-3 (CNX_BF16_STREAM=1, not the reference's promotion)"
+                   if os.environ.get("CNX_BF16_STREAM", "0") == "1" else "fp32 (reference's autocast type promotion)"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / a.steps, 3), "api": "imageclassification_b200.engine.train_one_epoch, pinned host batches"},
+                "ms_per_step": round(ms_e2e / a.steps, 3), "api": "imageclassification_b200.engine.train_one_epoch on pinned host batches (H2D of batch i+1 on a side stream during step i)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
     }
     if rank == 0:

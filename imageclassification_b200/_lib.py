@@ -47,6 +47,7 @@ SIGNATURES = {
     "cnx_soft_target_ce_fwd": (c_int, [_P, _I, _P, _L, _L, _P, _P, _P, _P, _P]),
     "cnx_soft_target_ce_bwd": (c_int, [_P, _I, _P, _P, _P, _L, _L, _P, _I, _P]),
     "cnx_mixup_target": (c_int, [_P, _L, _L, _D, _D, _P, _P]),
+    "cnx_mixup_batch": (c_int, [_P, _P, _L, _L, _L, _L, _D, _I, _I, _I, _I, _I, _P]),
     "cnx_dwconv7_weight_prep": (c_int, [_P, _L, _P, _P]),
     "cnx_dwconv7_ln_fwd": (c_int, [_P, _I, _P, _P, _P, _P, _F, _L, _L, _L, _L, _P, _P, _I, _P, _P, _P]),
     "cnx_ln_fwd": (c_int, [_P, _I, _P, _P, _F, _L, _L, _P, _I, _P, _P, _P]),
@@ -78,7 +79,7 @@ SIGNATURES = {
 # cnx_gemm_wgrad launches the GEMM + one partial reduction, + one more when the bias gradient is requested).
 KERNELS_PER_CALL = {
     "cnx_ema_lerp_multi": 1, "cnx_adamw_ema_multi": 1, "cnx_soft_target_ce_fwd": 1, "cnx_soft_target_ce_bwd": 1,
-    "cnx_mixup_target": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1,
+    "cnx_mixup_target": 1, "cnx_mixup_batch": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1,
     "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_dwconv7_weight_prep": 1, "cnx_gemm_bias_gelu_fwd": 1,
     "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2,
     "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_weight_prep_multi": 1, "cnx_mlp_fused_fwd": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,

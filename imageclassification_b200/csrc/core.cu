@@ -253,6 +253,66 @@ __global__ void __launch_bounds__(256) mixup_target_kernel(const int64_t* __rest
 }
 
 // ================================================================================================
+// a11 (image half): timm Mixup._mix_batch on a contiguous fp32 [B, L] batch, in place, sample pairs (i, B-1-i).
+//   mixup : x_i <- fl(fl(lam * x_i) + fl((1-lam) * x_j)), both members of the pair from the OLD values — what
+//           `x_flipped = x.flip(0).mul_(1-lam); x.mul_(lam).add_(x_flipped)` computes in five ATen passes.
+//   cutmix: x[i, :, yl:yh, xl:xh] <-> x[B-1-i, :, yl:yh, xl:xh]  (`x[..box] = x.flip(0)[..box]`).
+// One pass: 16-byte loads of both members, both results stored; `orig` (optional) receives the un-mixed pair in the same
+// pass (engine.py:40 keeps a second device copy of the batch for the accuracy forward).
+// ================================================================================================
+__global__ void __launch_bounds__(256) mixup_batch_kernel(float* __restrict__ x, float* __restrict__ orig, int64_t half_b,
+                                                          int64_t B, int64_t L4, float lam, float oml) {
+  const int64_t total = half_b * L4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t b = i / L4, e = i - b * L4;
+    float4* pa = reinterpret_cast<float4*>(x) + b * L4 + e;
+    float4* pb = reinterpret_cast<float4*>(x) + (B - 1 - b) * L4 + e;
+    const float4 a = *pa, c = *pb;
+    if (orig) {
+      reinterpret_cast<float4*>(orig)[b * L4 + e] = a;
+      reinterpret_cast<float4*>(orig)[(B - 1 - b) * L4 + e] = c;
+    }
+    float4 ra, rc;
+    ra.x = __fadd_rn(__fmul_rn(a.x, lam), __fmul_rn(c.x, oml)); rc.x = __fadd_rn(__fmul_rn(c.x, lam), __fmul_rn(a.x, oml));
+    ra.y = __fadd_rn(__fmul_rn(a.y, lam), __fmul_rn(c.y, oml)); rc.y = __fadd_rn(__fmul_rn(c.y, lam), __fmul_rn(a.y, oml));
+    ra.z = __fadd_rn(__fmul_rn(a.z, lam), __fmul_rn(c.z, oml)); rc.z = __fadd_rn(__fmul_rn(c.z, lam), __fmul_rn(a.z, oml));
+    ra.w = __fadd_rn(__fmul_rn(a.w, lam), __fmul_rn(c.w, oml)); rc.w = __fadd_rn(__fmul_rn(c.w, lam), __fmul_rn(a.w, oml));
+    *pa = ra;
+    *pb = rc;
+  }
+}
+// odd batch middle sample (timm requires an even batch in Mixup.__call__, but _mix_batch itself is defined for any B):
+// x_m <- fl(fl(lam*x_m) + fl((1-lam)*x_m)); also the scalar path when L is not a multiple of 4
+__global__ void __launch_bounds__(256) mixup_batch_scalar_kernel(float* __restrict__ x, float* __restrict__ orig, int64_t B,
+                                                                 int64_t L, float lam, float oml) {
+  const int64_t hb = (B + 1) / 2, total = hb * L;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t b = i / L, e = i - b * L, j = B - 1 - b;
+    const float a = x[b * L + e], c = x[j * L + e];
+    if (orig) { orig[b * L + e] = a; orig[j * L + e] = c; }
+    x[b * L + e] = __fadd_rn(__fmul_rn(a, lam), __fmul_rn(c, oml));
+    if (j != b) x[j * L + e] = __fadd_rn(__fmul_rn(c, lam), __fmul_rn(a, oml));
+  }
+}
+__global__ void __launch_bounds__(256) cutmix_swap_kernel(float* __restrict__ x, int64_t B, int64_t C, int64_t H, int64_t W,
+                                                          int yl, int yh, int xl, int xh) {
+  const int64_t bw = xh - xl, bh = yh - yl;
+  const int64_t total = (B / 2) * C * bh * bw;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    int64_t r = i;
+    const int64_t xx = r % bw; r /= bw;
+    const int64_t yy = r % bh; r /= bh;
+    const int64_t c = r % C; const int64_t b = r / C;
+    const int64_t off = (c * H + yl + yy) * W + xl + xx;
+    float* pa = x + b * C * H * W + off;
+    float* pb = x + (B - 1 - b) * C * H * W + off;
+    const float a = *pa;
+    *pa = *pb;
+    *pb = a;
+  }
+}
+
+// ================================================================================================
 // deterministic reduction of per-CTA partial sums: out[j] = scale * sum_p partial[p, j]
 // ================================================================================================
 // 32 columns per CTA; the 8 warps split the P rows (fixed assignment), then meet in shared memory in a fixed order:
@@ -389,6 +449,40 @@ int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, do
   mixup_target_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(target, B, K, (float)on, (float)off, (float)lam,
                                                                (float)oml, out);
   return check_launch("mixup_target");
+}
+
+int cnx_mixup_batch(float* x, float* orig, int64_t B, int64_t C, int64_t H, int64_t W, double lam, int use_cutmix, int yl,
+                    int yh, int xl, int xh, void* stream) {
+  CNX_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0, CNX_E_BADARG, "mixup_batch: bad argument");
+  CNX_REQUIRE(((uintptr_t)x & 15) == 0 && (!orig || ((uintptr_t)orig & 15) == 0), CNX_E_BADARG,
+              "mixup_batch: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t L = C * H * W;
+  const unsigned cap = 148u * 16u;
+  if (use_cutmix) {
+    CNX_REQUIRE(0 <= yl && yl <= yh && yh <= H && 0 <= xl && xl <= xh && xh <= W, CNX_E_BADARG, "mixup_batch: bad cutmix box");
+    if (orig) {
+      cudaError_t e = cudaMemcpyAsync(orig, x, (size_t)(B * L) * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) { set_error("mixup_batch: copy failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const int64_t total = (B / 2) * C * (int64_t)(yh - yl) * (int64_t)(xh - xl);
+    if (total == 0) return 0;
+    unsigned grid = (unsigned)((total + 255) / 256 > cap ? cap : (total + 255) / 256);
+    cutmix_swap_kernel<<<grid, 256, 0, s>>>(x, B, C, H, W, yl, yh, xl, xh);
+    return check_launch("mixup_batch(cutmix)");
+  }
+  // timm: python doubles lam and (1. - lam) meet the fp32 tensor as fp32 scalars
+  const float flam = (float)lam, foml = (float)(1.0 - lam);
+  if ((L & 3) == 0 && (B & 1) == 0) {
+    const int64_t total = (B / 2) * (L / 4);
+    unsigned grid = (unsigned)((total + 255) / 256 > cap ? cap : (total + 255) / 256);
+    mixup_batch_kernel<<<grid, 256, 0, s>>>(x, orig, B / 2, B, L / 4, flam, foml);
+  } else {
+    const int64_t total = ((B + 1) / 2) * L;
+    unsigned grid = (unsigned)((total + 255) / 256 > cap ? cap : (total + 255) / 256);
+    mixup_batch_scalar_kernel<<<grid, 256, 0, s>>>(x, orig, B, L, flam, foml);
+  }
+  return check_launch("mixup_batch");
 }
 
 int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,

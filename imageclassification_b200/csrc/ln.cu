@@ -363,6 +363,216 @@ __global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(
   }
 }
 
+// ---- LayerNorm backward, third generation (the all-bf16 hot path) ----------------------------------
+// LPP in {4, 8, 16, 32} lanes per row, each lane NJ <= 4 eight-channel vectors, chosen so that NO lane idles at the ConvNeXt
+// widths (C = 96: 4 x 3, 192: 8 x 3, 384: 16 x 3, 768: 32 x 3, 128/256/512/1024: x 4) — the second generation left a quarter of
+// the lanes idle at C = 96 / 192 and did not cover C > 256 at all.  Inputs stay PACKED (raw 16-byte vectors) in registers
+// between the two passes over a row, so a lane keeps ~NJ*U*8 registers of data in flight instead of NJ*U*16 floats, and the
+// output is three FMAs per element:  dy = (rs*w_c)*d + (-rs^2*s2)*y + (rs^2*s2*mu - rs*s1).
+// d ln_w / d ln_b accumulate in registers over all rows a lane visits; one partial row [2][C] per CTA, as before.
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+  v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <int NJ, int LPP, int U>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_v3_kernel(const bf16* __restrict__ dxn, const bf16* __restrict__ y,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     const float* __restrict__ ln_w, int64_t M, int C,
+                                                                     bf16* __restrict__ dy, float* __restrict__ partial, int pH,
+                                                                     int pW) {
+  extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C], then ln_w [C] when it does not fit in registers
+  constexpr int PPW = 32 / LPP;
+  constexpr bool LW_SMEM = NJ >= 3;                      // 16 accumulators per vector already: keep ln_w in shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPP, l = lane % LPP;
+  const int VPR = C >> 3;
+  const float invC = 1.0f / (float)C;
+  float lwr[LW_SMEM ? 1 : NJ][8], aw[NJ][8], ab[NJ][8];
+  float* slw = colacc + (size_t)LN_WARPS * 2 * C;
+  if (LW_SMEM) {
+    for (int i = threadIdx.x; i < C; i += LN_WARPS * 32) slw[i] = __ldg(ln_w + i);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int v = l + LPP * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (!LW_SMEM) lwr[j][e] = v < VPR ? __ldg(ln_w + v * 8 + e) : 0.f;
+      aw[j][e] = 0.f; ab[j][e] = 0.f;
+    }
+  }
+  auto get_lw = [&](int j, float (&w8)[8]) {
+    if (LW_SMEM) {
+      const int v = l + LPP * j;
+      const float4* p4 = reinterpret_cast<const float4*>(slw + (v < VPR ? v : 0) * 8);
+      const float4 a4 = p4[0], b4 = p4[1];
+      w8[0] = a4.x; w8[1] = a4.y; w8[2] = a4.z; w8[3] = a4.w; w8[4] = b4.x; w8[5] = b4.y; w8[6] = b4.z; w8[7] = b4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w8[e] = lwr[j][e];
+    }
+  };
+  const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp, tw = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t base = gw * (PPW * U); base < M; base += tw * (PPW * U)) {
+    uint4 rd[U][NJ], ry[U][NJ];
+    float mu[U], rs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * PPW + sub;
+      const bool ok = row < M;
+      mu[u] = ok ? __ldg(mean + row) : 0.f;
+      rs[u] = ok ? __ldg(rstd + row) : 0.f;
+      const uint4* pd = reinterpret_cast<const uint4*>(dxn + patch2_row(ok ? row : 0, pH, pW) * C);
+      const uint4* py = reinterpret_cast<const uint4*>(y + (ok ? row : 0) * C);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int v = l + LPP * j;
+        if (ok && v < VPR) {
+          rd[u][j] = pd[v];
+          ry[u][j] = py[v];
+        } else {
+          rd[u][j] = make_uint4(0u, 0u, 0u, 0u);
+          ry[u][j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = base + u * PPW + sub;
+      const float nmr = -mu[u] * rs[u];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float d[8], yv[8], w8[8];
+        unpack8(rd[u][j], d);
+        unpack8(ry[u][j], yv);
+        get_lw(j, w8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = fmaf(yv[e], rs[u], nmr);
+          const float g = d[e] * w8[e];
+          aw[j][e] = fmaf(d[e], xh, aw[j][e]);       // padded lanes / rows: d = 0 -> no contribution
+          ab[j][e] += d[e];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+        }
+      }
+#pragma unroll
+      for (int o = LPP / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= invC;
+      s2 *= invC;
+      // dy = rs*(g - s1 - xh*s2) with xh = rs*y - rs*mu   ->   (rs*w)*d + cy*y + c0
+      const float cy = -rs[u] * rs[u] * s2;
+      const float c0 = -fmaf(cy, mu[u], rs[u] * s1);
+      if (row < M) {
+        uint4* po = reinterpret_cast<uint4*>(dy + row * C);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int v = l + LPP * j;
+          if (v < VPR) {
+            float d[8], yv[8], o8[8], w8[8];
+            unpack8(rd[u][j], d);
+            unpack8(ry[u][j], yv);
+            get_lw(j, w8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = fmaf(rs[u] * w8[e], d[e], fmaf(cy, yv[e], c0));
+            po[v] = make_uint4(pack2_bf16(o8[0], o8[1]), pack2_bf16(o8[2], o8[3]), pack2_bf16(o8[4], o8[5]),
+                               pack2_bf16(o8[6], o8[7]));
+          }
+        }
+      }
+    }
+  }
+  // the PPW row groups of a warp meet by shuffles (fixed order), then the warps through shared memory (fixed order)
+#pragma unroll
+  for (int o = LPP; o < 32; o <<= 1) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        aw[j][e] += __shfl_xor_sync(0xffffffffu, aw[j][e], o);
+        ab[j][e] += __shfl_xor_sync(0xffffffffu, ab[j][e], o);
+      }
+  }
+  float* my = colacc + (size_t)warp * 2 * C;
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int v = l + LPP * j;
+      if (v < VPR) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { my[v * 8 + e] = aw[j][e]; my[C + v * 8 + e] = ab[j][e]; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += LN_WARPS * 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < LN_WARPS; ++wv) sum += colacc[(size_t)wv * 2 * C + i];
+    partial[(int64_t)blockIdx.x * 2 * C + i] = sum;
+  }
+}
+
+static bool ln_v3_off() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_LN_V3");
+    v = (e && e[0] == '0') ? 1 : 0;
+  }
+  return v != 0;
+}
+
+static int launch_ln_bwd_v3(const bf16* dxn, const bf16* y, const float* mean, const float* rstd, const float* ln_w, int64_t M,
+                            int64_t C, bf16* dy, float* partial, int P, cudaStream_t s, int pH, int pW, bool* handled) {
+  *handled = false;
+  const int vpr = (int)(C / 8);
+  if (C % 8 != 0 || vpr > 128 || ln_v1() || ln_v3_off()) return 0;
+  if ((((uintptr_t)dxn) | ((uintptr_t)y) | ((uintptr_t)dy)) & 15) return 0;
+  int lpp = 4;
+  while ((vpr + lpp - 1) / lpp > 4) lpp <<= 1;
+  const int nj = (vpr + lpp - 1) / lpp;
+  const size_t smem = (size_t)(LN_WARPS * 2 + 1) * C * sizeof(float);
+  *handled = true;
+#define CNX_LNB3(NJ, LPP, U)                                                                                      \
+  do {                                                                                                            \
+    auto k = ln_bwd_v3_kernel<NJ, LPP, U>;                                                                        \
+    if (smem > 48 * 1024) {                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+      if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }          \
+    }                                                                                                             \
+    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>(dxn, y, mean, rstd, ln_w, M, (int)C, dy, partial, pH, pW);         \
+    return check_launch("ln_bwd");                                                                                \
+  } while (0)
+#define CNX_LNB3_NJ(LPP)                     \
+  switch (nj) {                              \
+    case 1: CNX_LNB3(1, LPP, 4);             \
+    case 2: CNX_LNB3(2, LPP, 2);             \
+    case 3: CNX_LNB3(3, LPP, 1);             \
+    default: CNX_LNB3(4, LPP, 1);            \
+  }
+  switch (lpp) {
+    case 4: CNX_LNB3_NJ(4);
+    case 8: CNX_LNB3_NJ(8);
+    case 16: CNX_LNB3_NJ(16);
+    default: CNX_LNB3_NJ(32);
+  }
+#undef CNX_LNB3_NJ
+#undef CNX_LNB3
+  return 0;
+}
+
 static inline int nj_for(int64_t C) { return (int)((C / 4 + 31) / 32); }
 
 #define CNX_NJ_SWITCH(nj, ...)                                   \
@@ -475,7 +685,12 @@ static int ln_bwd_impl(const void* dxn, int dxn_dtype, const void* y, int y_dtyp
   const int key = (dxn_dtype << 2) | (y_dtype << 1) | dy_dtype;
   switch (key) {
     case 0: return launch_ln_bwd<float, float, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
-    case 7: return launch_ln_bwd<bf16, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    case 7: {
+      bool handled = false;
+      int rc = launch_ln_bwd_v3((const bf16*)dxn, (const bf16*)y, mean, rstd, ln_w, M, C, (bf16*)dy, partial, P, s, pH, pW, &handled);
+      if (handled) return rc;
+      return launch_ln_bwd<bf16, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
+    }
     case 1: return launch_ln_bwd<float, float, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
     case 2: return launch_ln_bwd<float, bf16, float>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);
     case 3: return launch_ln_bwd<float, bf16, bf16>(dxn, y, mean, rstd, ln_w, M, C, dy, partial, P, s, pH, pW);

@@ -13,6 +13,9 @@ What differs, without changing results:
     torch.amp.autocast('cuda') defaults to fp16 + scaler).
   * per-class TP/FP/FN are accumulated ON THE DEVICE with three bincounts per step instead of 3*num_classes
     `.item()` host syncs (engine.py:84-87/93-96), and read back once at the end of the epoch.
+  * host batches reach the device one step AHEAD: the H2D copy of batch i+1 (engine.py:40-41's `.to(device, non_blocking=True)`)
+    is issued on a side stream while step i computes (`DevicePrefetcher`); same tensors, same values, no PCIe time on the
+    compute stream.  `prefetch=False` restores the in-line copy.
   * rich progress bar / tensorboard / wandb plumbing is the caller's business: `log_writer` / `wandb_logger` are
     accepted and fed the same keys, but nothing is imported here.
 """
@@ -24,6 +27,8 @@ from typing import Iterable, Optional
 
 import torch
 
+from .mixup import Mixup as _Mixup
+
 
 def _class_counts(preds, targets, num_classes):
     """(true_pos, pred_count, target_count) per class as int64 device vectors."""
@@ -33,12 +38,85 @@ def _class_counts(preds, targets, num_classes):
             torch.bincount(targets, minlength=num_classes)[:num_classes])
 
 
+class DevicePrefetcher:
+    """Iterate a loader of (samples, targets) one batch ahead: the host->device copies of the NEXT batch are issued on a
+    side stream before the current batch is handed out, so they overlap the current step's kernels.  Batches that are
+    already on the device pass through untouched.
+
+    The copies land in two persistent device buffers per tensor shape (no caching-allocator traffic on the side stream).
+    Ordering: the consumer's stream waits on the copy's event before it touches a batch; before a buffer is overwritten
+    (two batches later) the side stream waits on an event recorded on the consumer's stream when the consumer asked for
+    the following batch, i.e. after all work on the buffer's previous batch was enqueued.  A consumer that keeps a batch
+    beyond the next TWO `next()` calls must clone it."""
+
+    def __init__(self, loader, device):
+        self.loader = loader
+        self.device = torch.device(device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        dev = self.device
+        it = iter(self.loader)
+        side = None
+        bufs = {}                  # (slot, which, shape, dtype) -> device tensor
+        released = [None, None]    # per slot: event on the consumer stream after which the slot may be overwritten
+        count = 0
+
+        def fetch():
+            nonlocal side, count
+            try:
+                s, t = next(it)
+            except StopIteration:
+                return None
+            if s.is_cuda and t.is_cuda:
+                return s, t, None, None
+            if side is None:
+                side = torch.cuda.Stream(dev)
+            slot = count & 1
+            count += 1
+            out = []
+            with torch.cuda.stream(side):
+                if released[slot] is not None:
+                    side.wait_event(released[slot])
+                for which, h in enumerate((s, t)):
+                    if h.is_cuda:
+                        out.append(h)
+                        continue
+                    key = (slot, which, tuple(h.shape), h.dtype)
+                    d = bufs.get(key)
+                    if d is None:
+                        d = bufs[key] = torch.empty(h.shape, dtype=h.dtype, device=dev)
+                    d.copy_(h, non_blocking=True)
+                    out.append(d)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            return out[0], out[1], ev, slot
+
+        nxt = fetch()
+        prev_slot = None
+        while nxt is not None:
+            s, t, ev, slot = nxt
+            cur = torch.cuda.current_stream(dev)
+            if prev_slot is not None:
+                # everything the consumer did with the previous batch is on `cur` by now
+                released[prev_slot] = torch.cuda.Event()
+                released[prev_slot].record(cur)
+            if ev is not None:
+                cur.wait_event(ev)
+            prev_slot = slot
+            nxt = fetch()
+            yield s, t
+
+
 def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loader: Iterable,
                     optimizer: torch.optim.Optimizer, device: torch.device, epoch: int, loss_scaler=None,
                     max_norm: float = 0, model_ema=None, mixup_fn=None, log_writer=None, wandb_logger=None,
                     start_steps: Optional[int] = 0, lr_schedule_values=None, wd_schedule_values=None,
                     num_training_steps_per_epoch: Optional[int] = None, update_freq: Optional[int] = 1,
-                    use_amp: bool = False, num_classes: int = 2, verbose: bool = True):
+                    use_amp: bool = False, num_classes: int = 2, verbose: bool = True,
+                    prefetch: bool = True):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "
@@ -56,7 +134,8 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
     acc_sum = torch.zeros((), dtype=torch.float32, device=device)
     loss_total, n_updates = 0.0, 0
 
-    for data_iter_step, (samples, targets) in enumerate(data_loader):
+    batches = DevicePrefetcher(data_loader, device) if prefetch else data_loader
+    for data_iter_step, (samples, targets) in enumerate(batches):
         step = data_iter_step // update_freq
         if step >= num_training_steps_per_epoch:
             continue
@@ -73,8 +152,12 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
         original_samples, original_targets = samples, targets
         if mixup_fn is not None:
             # the reference makes a second device copy (engine.py:40) because mixup mutates `samples` in place
-            original_samples = samples.clone() if samples.is_cuda else samples
-            samples, targets = mixup_fn(samples, targets)
+            if isinstance(mixup_fn, _Mixup):
+                original_samples = torch.empty_like(samples)         # filled by the mixing kernel itself
+                samples, targets = mixup_fn(samples, targets, original_out=original_samples)
+            else:
+                original_samples = samples.clone() if samples.is_cuda else samples
+                samples, targets = mixup_fn(samples, targets)
 
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp)):
             output = model(samples)

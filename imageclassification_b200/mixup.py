@@ -3,11 +3,13 @@
 
 Host side keeps timm's numpy RNG call sequence exactly (np.random.rand / beta / randint), so with the same
 `np.random.seed` the same lambda and cut-mix box are drawn (train.py:116-118 seeds numpy per rank).  The label
-mixing is one libcnx kernel, bit-exact in fp32.  Image mixing stays an in-place torch
-expression with timm's rounding order (SURVEY.md §8f row 3 lists its fusion as "next")."""
+mixing is one libcnx kernel, bit-exact in fp32.  Image mixing is one in-place libcnx pass over the
+sample pairs with timm's rounding order (`cnx_mixup_batch`: mixup blend or cutmix box swap, optionally writing the un-mixed
+copy the engine keeps); other dtypes / layouts use timm's own tensor expression."""
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from . import ops
 
@@ -90,22 +92,37 @@ class Mixup:
             lam = float(lam_mix)
         return lam, use_cutmix
 
-    def _mix_batch(self, x):
+    def _mix_batch(self, x, original_out=None):
         lam, use_cutmix = self._params_per_batch()
+        fused = x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
         if lam == 1.0:
+            if original_out is not None:
+                original_out.copy_(x)
             return 1.0
         if use_cutmix:
             (yl, yh, xl, xh), lam = cutmix_bbox_and_lam(x.shape, lam, ratio_minmax=self.cutmix_minmax,
                                                         correct_lam=self.correct_lam)
+            if fused:
+                ops.mixup_batch(x, lam, box=(yl, yh, xl, xh), original_out=original_out)
+                return lam
+            if original_out is not None:
+                original_out.copy_(x)
             x[:, :, yl:yh, xl:xh] = x.flip(0)[:, :, yl:yh, xl:xh]
         else:
-            x_flipped = x.flip(0).mul_(1.0 - lam)
+            if fused:
+                ops.mixup_batch(x, lam, original_out=original_out)       # one pass instead of flip / mul_ / mul_ / add_
+                return lam
+            if original_out is not None:
+                original_out.copy_(x)
+            x_flipped = x.flip(0).mul_(1.0 - lam)                       # other dtypes / layouts: timm's own tensor ops
             x.mul_(lam).add_(x_flipped)
         return lam
 
-    def __call__(self, x, target):
+    def __call__(self, x, target, original_out=None):
+        """`original_out` (extension, used by this package's engine): a tensor like `x` that receives the un-mixed batch in
+        the same pass — the copy engine.py:40 keeps for the accuracy forward."""
         if len(x) % 2 != 0:
             raise ValueError("Batch size should be even when using this")
-        lam = self._mix_batch(x)
+        lam = self._mix_batch(x, original_out)
         target = mixup_target(target, self.num_classes, lam, self.label_smoothing)
         return x, target

