@@ -44,13 +44,17 @@ def parse():
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW instead of the fused AdamW+EMA")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: in-line H2D copies on the compute stream")
+    ap.add_argument("--acc-fp32", action="store_true",
+                    help="accuracy forward outside autocast (fp32), exactly where the reference puts it (engine.py:89-97)")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
     return ap.parse_args()
 
 
 def workload_name(a):
     return (f"{a.model} {a.img}x{a.img} bf16 autocast, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
-            f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward (engine.py:27-97)")
+            f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward "
+            f"{'in fp32 outside autocast as the reference places it' if getattr(a, 'acc_fp32', False) else 'under the same bf16 autocast'}"
+            f" (engine.py:27-97)")
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -248,7 +252,8 @@ def run_ours(a):
         if a.no_acc_forward:
             return _fast_epoch(batches)
         return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=True,
-                                       num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch)
+                                       num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch,
+                                       acc_forward_fp32=a.acc_fp32)
 
     def _fast_epoch(batches):
         net.train(True)

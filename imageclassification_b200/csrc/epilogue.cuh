@@ -11,7 +11,9 @@ enum {
   EPI_PLAIN = 0,        // out0 = acc (+bias)                                  [out dtype = TOUT]
   EPI_BIAS_GELU = 1,    // h = round(acc + b1); GELU'(h) -> out0 (optional, saved for backward), g = GELU(h) -> out1 [act dtype]
   EPI_SCALE_RES = 2,    // out0 = shortcut + dp[row/rps] * gamma[n] * (acc + b2[n])  [stream dtype]
-  EPI_DGELU = 3         // out0 = acc * gp[m,n]                                 [act dtype], aux = gp = GELU'(h) saved by BIAS_GELU
+  EPI_DGELU = 3,        // out0 = acc * gp[m,n]                                 [act dtype], aux = gp = GELU'(h) saved by BIAS_GELU
+  EPI_BIAS_GELU3 = 4    // fp32-accurate forward: g = GELU_erf(acc + b1) in fp32 -> out1 bf16 [M, 3N] = [hi(g) | mid(g) | hi(g)]
+                        // (split operand of the next GEMM; tcgen05 slab epilogue only)
 };
 
 struct EpiParams {

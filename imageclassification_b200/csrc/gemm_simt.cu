@@ -201,6 +201,28 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const TS* __restrict__ d
   }
 }
 
+// fp32 [M, C] -> bf16 [M, 3C] = [hi | mid | hi]: the A-side split operand (x ~ hi + mid to 2^-17 relative); 8 elements per thread
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int64_t M, int64_t C, bf16* __restrict__ out) {
+  const int64_t vpr = C >> 3, total = M * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / vpr, v = i - m * vpr;
+    float a[8], r[8];
+    load8(x + m * C + v * 8, a);
+    uint4 hi;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h2[k] = __floats2bfloat162_rn(a[2 * k], a[2 * k + 1]);
+      r[2 * k] = a[2 * k] - __low2float(h2[k]);
+      r[2 * k + 1] = a[2 * k + 1] - __high2float(h2[k]);
+    }
+    bf16* o = out + m * 3 * C + v * 8;
+    *reinterpret_cast<uint4*>(o) = hi;
+    store8(o + C, r);
+    *reinterpret_cast<uint4*>(o + 2 * C) = hi;
+  }
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, int64_t R, int64_t Cc,
                                                           const float* __restrict__ row_scale, int mode,
@@ -223,6 +245,19 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
     for (int i = ty; i < 32; i += 8) {
       int64_t r = r0 + i, c = c0 + tx;
       if (r < R && c < Cc) out[r * Cc + c] = from_f32<TO>(tile[i][tx]);
+    }
+  } else if (mode == 3) {
+    // split operand, B side: out[r, 0:Cc] = hi, [Cc:2Cc] = hi, [2Cc:3Cc] = mid   (hi = bf16(w), mid = bf16(w - hi))
+    for (int i = ty; i < 32; i += 8) {
+      int64_t r = r0 + i, c = c0 + tx;
+      if (r < R && c < Cc) {
+        const float w = tile[i][tx];
+        const TO hi = from_f32<TO>(w);
+        const TO mid = from_f32<TO>(w - to_f32(hi));
+        out[r * 3 * Cc + c] = hi;
+        out[r * 3 * Cc + Cc + c] = hi;
+        out[r * 3 * Cc + 2 * Cc + c] = mid;
+      }
     }
   } else {
     for (int i = ty; i < 32; i += 8) {
@@ -269,10 +304,16 @@ __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const WeightPrep
   for (int i = ty; i < 32; i += 8) {
     int64_t r, c, o;
     float v;
-    if (e.mode == 0) { r = r0 + i; c = c0 + tx; o = r * e.Cc + c; v = tile[i][tx]; }
+    if (e.mode == 0 || e.mode == 3) { r = r0 + i; c = c0 + tx; o = r * e.Cc + c; v = tile[i][tx]; }
     else { c = c0 + i; r = r0 + tx; o = c * e.R + r; v = tile[tx][i]; }
     if (r < e.R && c < e.Cc) {
-      if (e.out_dtype == CNX_F32) reinterpret_cast<float*>(e.out)[o] = v;
+      if (e.mode == 3) {                                   // [hi | hi | mid], bf16 only
+        bf16* o3 = reinterpret_cast<bf16*>(e.out) + r * 3 * e.Cc + c;
+        const bf16 hi = from_f32<bf16>(v);
+        o3[0] = hi;
+        o3[e.Cc] = hi;
+        o3[2 * e.Cc] = from_f32<bf16>(v - to_f32(hi));
+      } else if (e.out_dtype == CNX_F32) reinterpret_cast<float*>(e.out)[o] = v;
       else reinterpret_cast<bf16*>(e.out)[o] = from_f32<bf16>(v);
     }
   }
@@ -336,13 +377,25 @@ int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, int64_t r
 
 int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_scale, int mode, void* out,
                     int out_dtype, void* stream) {
-  CNX_REQUIRE(W && out && R > 0 && Ccols > 0 && mode >= 0 && mode <= 2 && dtype_ok(out_dtype), CNX_E_BADARG,
+  CNX_REQUIRE(W && out && R > 0 && Ccols > 0 && mode >= 0 && mode <= 3 && dtype_ok(out_dtype), CNX_E_BADARG,
               "weight_prep: bad argument");
+  CNX_REQUIRE(mode != 3 || out_dtype == CNX_BF16, CNX_E_BADARG, "weight_prep: mode 3 (split operand) writes bf16");
   dim3 grid((unsigned)((Ccols + 31) / 32), (unsigned)((R + 31) / 32));
   cudaStream_t s = (cudaStream_t)stream;
   if (out_dtype == CNX_F32) weight_prep_kernel<float><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (float*)out);
   else weight_prep_kernel<bf16><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (bf16*)out);
   return check_launch("weight_prep");
+}
+
+int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream) {
+  CNX_REQUIRE(x && out && M > 0 && C > 0, CNX_E_BADARG, "split3: bad argument");
+  CNX_REQUIRE(C % 8 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0, CNX_E_SHAPE,
+              "split3: C=%lld must be a multiple of 8 and the pointers 16-byte aligned", (long long)C);
+  const int64_t total = M * (C / 8);
+  int64_t grid = (total + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  split3_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, M, C, (bf16*)out);
+  return check_launch("split3");
 }
 
 int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_tiles, void* stream) {

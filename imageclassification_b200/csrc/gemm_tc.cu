@@ -523,7 +523,21 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       uint32_t pg[16], pd[16];
-      const bool want_gp = (KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr);
+      const bool want_gp = (KIND == EPI_BIAS_GELU3) || ((KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr));
+      if (KIND == EPI_BIAS_GELU3) {
+        // fp32 h, exact-erf GELU in fp32, g split into two bf16 pieces: g ~ hi + mid to 2^-17 relative
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+          const float g0 = gelu_erf(v[i] + b4.x), g1 = gelu_erf(v[i + 1] + b4.y);
+          const float g2 = gelu_erf(v[i + 2] + b4.z), g3 = gelu_erf(v[i + 3] + b4.w);
+          const uint32_t ha = pack_bf16(g0, g1), hb = pack_bf16(g2, g3);
+          pg[i / 2] = ha;
+          pg[i / 2 + 1] = hb;
+          pd[i / 2] = pack_bf16(g0 - bf16_lo(ha), g1 - bf16_hi(ha));
+          pd[i / 2 + 1] = pack_bf16(g2 - bf16_lo(hb), g3 - bf16_hi(hb));
+        }
+      }
       if (KIND == EPI_BIAS_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -575,7 +589,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const uint32_t addr = slab + row_off + (((uint32_t)j ^ swz) << 4);
-        if (KIND == EPI_BIAS_GELU) {               // two bf16 outputs share the slab: g in the first 2 KB, GELU' in the second
+        if (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3) {   // two bf16 outputs share the slab: g (hi) in the first 2 KB, GELU' (mid) in the second
           sts128(addr, pg[4 * j], pg[4 * j + 1], pg[4 * j + 2], pg[4 * j + 3]);
           if (want_gp) sts128(addr + 2048u, pd[4 * j], pd[4 * j + 1], pd[4 * j + 2], pd[4 * j + 3]);
         } else if (sizeof(TOUT) == 4)
@@ -591,7 +605,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int32_t x, y;
         chunk_coords(t_cur, c_cur, x, y);
         tma_store_2d(&tmOut, slab, x, y);
-        if (want_gp) tma_store_2d(&tmIn, slab + 2048u, x, y);
+        if (KIND == EPI_BIAS_GELU3) {              // [hi | mid | hi] column blocks of the [M, 3N] split operand
+          tma_store_2d(&tmOut, slab + 2048u, x + (int32_t)N, y);
+          tma_store_2d(&tmOut, slab, x + 2 * (int32_t)N, y);
+        } else if (want_gp) {
+          tma_store_2d(&tmIn, slab + 2048u, x, y);
+        }
         bulk_commit();
       }
       buf ^= 1;
@@ -1510,10 +1529,12 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
   if (int rc = make_map(&tmB, B, N, K, Cfg::B_ROWS)) return rc;
   if (SLAB) {
-    void* o = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.out0;
-    const void* in = (KIND == EPI_BIAS_GELU) ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
-    if (int rc = make_slab_map(&tmOut, o, M, N, (int)sizeof(TOUT))) return rc;
-    if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
+    constexpr bool kGelu = (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3);
+    void* o = kGelu ? ep.out1 : ep.out0;
+    const void* in = kGelu ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
+    if (int rc = make_slab_map(&tmOut, o, M, (KIND == EPI_BIAS_GELU3) ? 3 * N : N, (int)sizeof(TOUT))) return rc;
+    if (KIND == EPI_BIAS_GELU3) tmIn = tmOut;
+    else if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
   } else {
     tmOut = tmA;
     tmIn = tmA;
@@ -1548,17 +1569,23 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
 template <int BN, int KIND, typename TOUT, int NCTA>
 static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
   // slab epilogue: whole 32-column chunks, an input slab only where the epilogue has one
-  constexpr bool kSlabKind = (BN % 32 == 0) && (KIND != EPI_BIAS_GELU || sizeof(TOUT) == 2);
+  constexpr bool kGelu = (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3);
+  constexpr bool kSlabKind = (BN % 32 == 0) && (!kGelu || sizeof(TOUT) == 2);
   if constexpr (kSlabKind) {
     const bool need_in = (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
-    const void* o = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.out0;
-    if (slab_enabled() && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
+    const void* o = kGelu ? ep.out1 : ep.out0;
+    if ((slab_enabled() || KIND == EPI_BIAS_GELU3) && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
       // the GELU epilogue is issue-bound: 16 epilogue warps (4 per scheduler) where the tile has >= 4 column chunks
-      if constexpr (KIND == EPI_BIAS_GELU && BN >= 128) return launch_tn_impl<BN, KIND, TOUT, NCTA, true, 16>(A, B, M, N, K, ep, s);
+      if constexpr (kGelu && BN >= 128) return launch_tn_impl<BN, KIND, TOUT, NCTA, true, 16>(A, B, M, N, K, ep, s);
       else return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
     }
   }
-  return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
+  if constexpr (KIND == EPI_BIAS_GELU3) {
+    set_error("gemm_bias_gelu_fwd_x3: N=%lld must be a multiple of 32", (long long)N);
+    return CNX_E_SHAPE;
+  } else {
+    return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
+  }
 }
 
 
@@ -1646,6 +1673,7 @@ CNX_INST(EPI_BIAS_GELU, bf16)
 CNX_INST(EPI_SCALE_RES, float)
 CNX_INST(EPI_SCALE_RES, bf16)
 CNX_INST(EPI_DGELU, bf16)
+CNX_INST(EPI_BIAS_GELU3, bf16)
 #undef CNX_INST
 
 // tile plan of the wgrad GEMM: CTA pairs (256 x BN) where both dimensions carry at least a tile, single CTAs otherwise

@@ -8,6 +8,10 @@ What is kept exactly (results identical to engine.py on the same inputs):
     `loss.item()` + non-finite guard that skips the step (:54-59), `loss /= update_freq; backward; step every
     update_freq; zero_grad; model_ema.update` (:61-77), the second no-grad forward on the un-mixed batch for train
     accuracy when mixup is on (:89-97), per-class TP/FP/FN totals and the returned {loss, class_acc} global averages.
+What differs:
+  * under `use_amp=True` the accuracy forward (:89-97) runs inside the same bf16 autocast as the training forward; the
+    reference leaves it outside its autocast block (fp32).  Parameters, EMA and loss are unaffected; `class_acc` and the
+    TP/FP/FN counts can differ on argmax near-ties.  `acc_forward_fp32=True` reproduces the reference's placement.
 What differs, without changing results:
   * `use_amp=True` means bf16 autocast with no GradScaler (the BASELINE north-star precision; the reference's
     torch.amp.autocast('cuda') defaults to fp16 + scaler).
@@ -116,7 +120,7 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
                     start_steps: Optional[int] = 0, lr_schedule_values=None, wd_schedule_values=None,
                     num_training_steps_per_epoch: Optional[int] = None, update_freq: Optional[int] = 1,
                     use_amp: bool = False, num_classes: int = 2, verbose: bool = True,
-                    prefetch: bool = True):
+                    prefetch: bool = True, acc_forward_fp32: bool = False):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "
@@ -184,7 +188,7 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
             if mixup_fn is None:
                 ref_out, ref_t = output, targets
             else:
-                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp)):
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp) and not acc_forward_fp32):
                     ref_out = model(original_samples)
                 ref_t = original_targets
             preds = ref_out.max(1)[1]
@@ -228,3 +232,73 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
             print(f"Class {i}: Precision: {precision:.5f}, Recall: {recall:.5f}")
     train_one_epoch.last_class_counts = stats_extra
     return stats
+
+
+@torch.no_grad()
+def evaluate(data_loader, model, device, num_classes, use_amp=False, verbose: bool = True, prefetch: bool = True):
+    """The reference's validation loop (engine.py:145-225): same arguments, same returned keys and values
+    ({loss, acc1, avg_precision, avg_recall, precision_i, recall_i} as global averages).  The forward runs the libcnx kernels
+    (no-grad path: fused MLP where the hidden activation fits on chip); per-class TP / predicted / target counts and the loss and
+    top-1 sums stay on the device (three bincounts per batch instead of 3*num_classes `.item()` syncs) and are read back once."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "
+                           "use oracle/engine.py for CPU reference numbers")
+    criterion = torch.nn.CrossEntropyLoss()
+    model.eval()
+    tp = torch.zeros(num_classes, dtype=torch.int64, device=device)
+    pc = torch.zeros_like(tp)
+    tc = torch.zeros_like(tp)
+    sums = torch.zeros(2, dtype=torch.float64, device=device)          # sum of batch losses, number of correct top-1
+    n_batches = n_samples = 0
+    batches = DevicePrefetcher(_first_last(data_loader), device) if prefetch else _first_last(data_loader)
+    for images, target in batches:
+        images = images.to(device, non_blocking=True)
+        target = target.to(device, non_blocking=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bool(use_amp)):
+            output = model(images)
+            loss = criterion(output, target)
+        preds = output.max(1)[1]
+        a, b, c = _class_counts(preds, target, num_classes)
+        tp += a
+        pc += b
+        tc += c
+        sums[0] += loss.double()
+        sums[1] += (preds == target).sum().double()    # top-1 of timm accuracy(): argmax, first index on ties as topk gives
+        n_batches += 1
+        n_samples += int(images.shape[0])
+    loss_sum, correct = sums.tolist()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        # utils.py:80-88 synchronize_between_processes: (count, total) of every meter summed over ranks
+        t = torch.tensor([n_batches, loss_sum, n_samples, correct], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t)
+        n_batches, loss_sum, n_samples, correct = t.tolist()
+    stats = {"loss": loss_sum / max(n_batches, 1), "acc1": 100.0 * correct / max(n_samples, 1)}
+    tp_l, pc_l, tc_l = tp.tolist(), pc.tolist(), tc.tolist()
+    precs, recs = [], []
+    for i in range(num_classes):
+        precs.append(tp_l[i] / pc_l[i] if pc_l[i] > 0 else 0)          # TP + FP = predicted count
+        recs.append(tp_l[i] / tc_l[i] if tc_l[i] > 0 else 0)           # TP + FN = target count
+        stats[f"precision_{i}"] = precs[-1]
+        stats[f"recall_{i}"] = recs[-1]
+        if verbose and num_classes <= 16:
+            print(f"Class {i}: Precision: {precs[-1]:.5f}, Recall: {recs[-1]:.5f}")
+    stats["avg_precision"] = sum(precs) / len(precs)
+    stats["avg_recall"] = sum(recs) / len(recs)
+    if verbose:
+        print(f"Average Precision: {stats['avg_precision']:.5f}, Average Recall: {stats['avg_recall']:.5f}")
+    return stats
+
+
+class _first_last:
+    """engine.py:170-171 takes `batch[0]` and `batch[-1]` of whatever the loader yields."""
+
+    def __init__(self, loader):
+        self.loader = loader
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for batch in self.loader:
+            yield batch[0], batch[-1]

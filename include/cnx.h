@@ -175,6 +175,20 @@ CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, cons
                                      int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,
                                      void* stream);
 
+/* fp32-ACCURATE forward on the tensor cores ("x3" operands).  A value x is carried as two bf16 pieces, hi = bf16(x) and
+ * mid = bf16(x - hi) (x = hi + mid to 2^-17 relative).  With the A operand laid out [hi | mid | hi] and the B operand
+ * [hi | hi | mid] along K, ONE ordinary bf16 GEMM over K3 = 3K accumulates a_hi.b_hi + a_mid.b_hi + a_hi.b_mid in fp32 —
+ * everything of the fp32 product except the 2^-16 a_mid.b_mid term.  Used for the no-grad forward outside autocast (the
+ * accuracy forward of engine.py:89-97 and evaluate(), engine.py:145-225, run in fp32 in the reference).
+ *   cnx_split3                  x fp32 [M,C] -> out bf16 [M,3C] = [hi | mid | hi]                    (A side)
+ *   cnx_weight_prep mode 3      W fp32 [R,C] -> out bf16 [R,3C] = [hi | hi | mid]                    (B side)
+ *   cnx_gemm_bias_gelu_fwd_x3   g3 bf16 [M,3N] = [hi | mid | hi] of GELU_erf(A.W^T + b1) (fp32 epilogue), A3 [M,K3], W3 [N,K3]
+ *   fc2: cnx_gemm_bias_scale_residual_fwd(A = g3, W2 = mode-3 weight, K = 3*4C, dtype = CNX_BF16, stream_dtype = CNX_F32)
+ *   plain: cnx_gemm_plain(A3, B3, ..., out fp32, K = 3K, dtype = CNX_BF16) */
+CNX_API int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream);
+CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
+                              void* g3, void* stream);
+
 /* Fused no-grad MLP forward for the HBM-bound stages (C in {96, 128, 192}; bf16 operands, fp32 residual stream):
  *   out[m,:] = shortcut[m,:] + dp[m / rows_per_sample] * gamma * (GELU_erf(xn[m,:].W1^T + b1).W2^T + b2)
  * in one kernel — the [M,4C] hidden activation stays in shared / tensor memory (convnext.py:48-55 in one pass).
@@ -208,7 +222,8 @@ CNX_API int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, i
 /* Weight prep (tiny, [R,Ccols] fp32 -> act dtype):
  *   mode 0: out[r,c]   = W[r,c]                       (cast)
  *   mode 1: out[c,r]   = W[r,c]                       (transpose + cast)      -> W1^T for dgrad fc1
- *   mode 2: out[c,r]   = row_scale[r] * W[r,c]        (scale rows, transpose) -> (gamma.W2)^T for dgrad fc2 */
+ *   mode 2: out[c,r]   = row_scale[r] * W[r,c]        (scale rows, transpose) -> (gamma.W2)^T for dgrad fc2
+ *   mode 3: out[r, 0:C | C:2C | 2C:3C] = hi, hi, mid of W[r,c]   (bf16 only; B-side split operand, see cnx_split3) */
 CNX_API int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_scale, int mode, void* out,
                     int out_dtype, void* stream);
 

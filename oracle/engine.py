@@ -76,3 +76,46 @@ def train_one_epoch(model, criterion, data_loader, optimizer, device, epoch, los
         count += 1
     return {"loss": loss_sum / max(count, 1), "class_acc": acc_sum / max(count, 1),
             "true_positives": tp, "false_positives": fp, "false_negatives": fn}
+
+
+@torch.no_grad()
+def evaluate(data_loader, model, device, num_classes, use_amp=False, amp_dtype=torch.bfloat16):
+    """engine.py:145-225 restated: eval-mode forward, CrossEntropyLoss, per-class TP/FP/FN by 3*K masked sums, top-1 accuracy in
+    percent (timm.utils.accuracy), returned as the MetricLogger's global averages: loss = mean over batches, acc1 = mean
+    weighted by batch size, precision_i / recall_i and their unweighted class averages."""
+    criterion = torch.nn.CrossEntropyLoss()
+    tp, fp, fn = [0] * num_classes, [0] * num_classes, [0] * num_classes
+    model.eval()
+    loss_sum, n_batches, acc_sum, n_samples = 0.0, 0, 0.0, 0
+    for batch in data_loader:
+        images, target = batch[0].to(device, non_blocking=True), batch[-1].to(device, non_blocking=True)   # engine.py:170-174
+        if use_amp:
+            with torch.amp.autocast(torch.device(device).type, dtype=amp_dtype):
+                output = model(images)
+                loss = criterion(output, target)
+        else:
+            output = model(images)
+            loss = criterion(output, target)
+        _, preds = torch.max(output, 1)
+        for i in range(num_classes):                                                                       # engine.py:188-191
+            tp[i] += torch.sum((preds == i) & (target == i)).item()
+            fp[i] += torch.sum((preds == i) & (target != i)).item()
+            fn[i] += torch.sum((preds != i) & (target == i)).item()
+        maxk = min(5, output.size(1))                                                                      # timm accuracy(topk=(1, 5))
+        pred = output.topk(maxk, 1, True, True)[1].t()
+        correct = pred.eq(target.reshape(1, -1).expand_as(pred))
+        acc1 = correct[:1].reshape(-1).float().sum(0) * 100.0 / target.size(0)
+        loss_sum += loss.item()
+        n_batches += 1
+        acc_sum += acc1.item() * images.shape[0]
+        n_samples += images.shape[0]
+    out = {"loss": loss_sum / max(n_batches, 1), "acc1": acc_sum / max(n_samples, 1)}
+    precs, recs = [], []
+    for i in range(num_classes):                                                                           # engine.py:203-214
+        precs.append(tp[i] / (tp[i] + fp[i]) if tp[i] + fp[i] > 0 else 0)
+        recs.append(tp[i] / (tp[i] + fn[i]) if tp[i] + fn[i] > 0 else 0)
+        out[f"precision_{i}"] = precs[-1]
+        out[f"recall_{i}"] = recs[-1]
+    out["avg_precision"] = sum(precs) / len(precs)
+    out["avg_recall"] = sum(recs) / len(recs)
+    return out

@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-run() { echo "== $*"; env $1 timeout 300 python bench.py ${@:2} --no-breakdown --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'])"; }
-run A=1 --steps 10 --warmup 3
-run A=1 --steps 20 --warmup 5
-run CNX_CLOCK_PERIOD=0.5 --steps 20 --warmup 5
-run A=1 --steps 40 --warmup 5
-run CNX_CLOCK_PERIOD=0.5 --steps 40 --warmup 5
+timeout 600 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -n 5
+N=${NGPU:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_${N}gpu.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines()[-1])
+d.pop('kernels',None); print(d)
+PY

@@ -94,6 +94,21 @@ def engine_golden():
     np.savez_compressed(os.path.join(HERE, "engine_step.npz"), **out)
 
 
+def evaluate_golden():
+    """evaluate.npz: the dict the reference's own engine.evaluate (engine.py:145-225, imported unmodified) returns for a seeded
+    ConvNeXt-T (3 classes, uneven batch sizes so the batch-mean loss and the sample-weighted acc1 differ), CPU fp32."""
+    eng = shim.import_reference_engine()
+    torch.manual_seed(5)
+    model = OC.create_model("convnext_tiny", num_classes=3, ls_init_value=1.0)
+    with torch.no_grad():
+        model.head.fc.weight.normal_(0, 0.5)          # spread the logits so that all three classes get predicted
+    data = [(torch.randn(b, 3, 64, 64), torch.randint(0, 3, (b,))) for b in (8, 8, 5)]
+    stats = eng.evaluate(data, model, torch.device("cpu"), 3, use_amp=False)
+    np.savez_compressed(os.path.join(HERE, "evaluate.npz"), keys=np.array(sorted(stats)),
+                        values=np.array([float(stats[k]) for k in sorted(stats)]))
+    print("evaluate", stats)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     ref = shim.import_reference_backbone()
@@ -102,3 +117,4 @@ if __name__ == "__main__":
     block_golden(ref, 64, 12, 1, 3, 1e-6)
     ln_golden(ref)
     engine_golden()
+    evaluate_golden()

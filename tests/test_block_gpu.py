@@ -127,3 +127,27 @@ def test_convnext_tiny_fwd_bwd(mode, gamma_init, dpr):
     tot_p = math.sqrt(sum((gp[n].double() ** 2).sum().item() for n in go))
     tot_d = math.sqrt(sum(((gp[n].double() - go[n].double()) ** 2).sum().item() for n in go))
     assert tot_d / tot_p <= tol, (tot_d / tot_p)
+
+
+@pytest.mark.parametrize("name,img,batch", [("convnext_base", 64, 4), ("convnext_large", 96, 2)])
+def test_convnext_base_large_fwd_bwd_bf16(name, img, batch):
+    """BASELINE configs 3 and 4 model families (widths 128..1024 and 192..1536, depths 3/3/27/3) at a reduced resolution:
+    logits and the global gradient vector vs the oracle under bf16 autocast, mixup-style soft targets."""
+    import math
+    o, p = _pair_model(name, 1000, 0.1, 1.0, 5)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(batch, 3, img, img, generator=g).to(DEV)
+    t = torch.softmax(torch.randn(batch, 1000, generator=g), -1).to(DEV)
+    outs = []
+    for m in (o, p):
+        torch.manual_seed(7)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m(x)
+            loss = torch.sum(-t * torch.log_softmax(logits.float(), -1), -1).mean()
+        loss.backward()
+        outs.append((logits.float(), {n: q.grad for n, q in m.named_parameters()}))
+    (lo, go), (lp, gp) = outs
+    assert max_rel(lp, lo) <= 2e-2
+    tot_p = math.sqrt(sum((gp[n].double() ** 2).sum().item() for n in go))
+    tot_d = math.sqrt(sum(((gp[n].double() - go[n].double()) ** 2).sum().item() for n in go))
+    assert tot_d / tot_p <= 2e-2, (tot_d / tot_p)

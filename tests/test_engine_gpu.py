@@ -125,3 +125,31 @@ def test_prefetched_batches_give_identical_results():
     for k, (l, p) in res.items():
         assert l == l0 and torch.equal(p, p0), k
     assert len(PE.DevicePrefetcher(data, DEV)) == 3
+
+
+def test_evaluate_matches_reference_golden_and_oracle():
+    """engine.evaluate: same keys and values as the reference's own evaluate on the golden case (fp32),
+    and as the oracle's evaluate on the device under bf16 autocast (loss within the bf16 bar; counts from the same argmax)."""
+    z = np.load(os.path.join(GOLD, "evaluate.npz"))
+    gold = dict(zip([str(k) for k in z["keys"]], z["values"].tolist()))
+    torch.manual_seed(5)
+    o = OC.create_model("convnext_tiny", num_classes=3, ls_init_value=1.0)
+    with torch.no_grad():
+        o.head.fc.weight.normal_(0, 0.5)
+    data = [(torch.randn(b, 3, 64, 64), torch.randint(0, 3, (b,))) for b in (8, 8, 5)]
+    p = P.create_model("convnext_tiny", num_classes=3, ls_init_value=1.0)
+    p.load_state_dict(o.state_dict())
+    p.to(DEV)
+    p.train()                                                    # evaluate() must switch to eval mode itself
+    stats = PE.evaluate(data, p, DEV, 3, use_amp=False, verbose=False)
+    assert not p.training and sorted(stats) == sorted(gold)
+    for k, v in gold.items():
+        assert abs(stats[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, stats[k], v)
+    # a 3-tuple loader (engine.py:170-171 takes batch[0], batch[-1]) and no prefetch
+    stats2 = PE.evaluate([(a, None, b) for a, b in data], p, DEV, 3, use_amp=False, verbose=False, prefetch=False)
+    assert stats2 == stats
+    o.to(DEV)
+    so = OEng.evaluate(data, o, DEV, 3, use_amp=True)
+    sp = PE.evaluate(data, p, DEV, 3, use_amp=True, verbose=False)
+    assert abs(sp["loss"] - so["loss"]) <= 2e-2 * abs(so["loss"])
+    assert abs(sp["acc1"] - so["acc1"]) <= 100.0 / 21 + 1e-6       # at most one near-tie argmax flip among 21 samples

@@ -77,6 +77,27 @@ def test_oracle_engine_matches_reference_engine(tag, img, gamma_init, dpr):
     np.testing.assert_allclose(ps, z[f"{tag}.param_sums"], rtol=0, atol=2e-3 * np.abs(z[f"{tag}.param_norms"]).max())
 
 
+def _eval_case():
+    torch.manual_seed(5)
+    model = OC.create_model("convnext_tiny", num_classes=3, ls_init_value=1.0)
+    with torch.no_grad():
+        model.head.fc.weight.normal_(0, 0.5)
+    data = [(torch.randn(b, 3, 64, 64), torch.randint(0, 3, (b,))) for b in (8, 8, 5)]
+    return model, data
+
+
+def test_oracle_evaluate_matches_reference_evaluate():
+    """oracle/engine.py evaluate restates engine.py:145-225; the golden dict is what the reference's own evaluate returned."""
+    z = np.load(os.path.join(GOLD, "evaluate.npz"))
+    gold = dict(zip([str(k) for k in z["keys"]], z["values"].tolist()))
+    torch.set_num_threads(8)
+    model, data = _eval_case()
+    stats = OEng.evaluate(data, model, "cpu", 3)
+    assert sorted(stats) == sorted(gold)
+    for k, v in gold.items():
+        assert abs(stats[k] - v) <= 1e-5 * max(1.0, abs(v)), (k, stats[k], v)
+
+
 def test_param_counts():
     # SURVEY.md §7 step 0 self-check
     assert sum(p.numel() for p in OC.create_model("convnext_tiny", num_classes=1000).parameters()) == 28_589_128
