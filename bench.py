@@ -44,8 +44,10 @@ def parse():
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW instead of the fused AdamW+EMA")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e leg: in-line H2D copies on the compute stream")
-    ap.add_argument("--acc-fp32", action="store_true",
-                    help="accuracy forward outside autocast (fp32), exactly where the reference puts it (engine.py:89-97)")
+    ap.add_argument("--acc-autocast", action="store_true",
+                    help="headline with the accuracy forward under bf16 autocast instead of fp32 outside autocast, where the "
+                         "reference puts it (engine.py:89-97); by default that variant is only reported under `variants`")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra timed region of the `variants` key")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
     return ap.parse_args()
 
@@ -53,7 +55,7 @@ def parse():
 def workload_name(a):
     return (f"{a.model} {a.img}x{a.img} bf16 autocast, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
             f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward "
-            f"{'in fp32 outside autocast as the reference places it' if getattr(a, 'acc_fp32', False) else 'under the same bf16 autocast'}"
+            f"{'under the same bf16 autocast' if getattr(a, 'acc_autocast', False) else 'in fp32 outside autocast as the reference places it'}"
             f" (engine.py:27-97)")
 
 
@@ -180,10 +182,24 @@ def kernel_work(name, a):
         M, N, K = a[3:6]
         e = es(a[8])
         return (M * K + N * K + M * N * (2 if a[6] else 1)) * e, 2 * M * N * K, f"fc1_gelu K{K}"
+    if name == "cnx_gemm_bias_gelu_fwd_x3":
+        M, N, K3 = a[3:6]
+        return (M * K3 + N * K3 + M * 2 * N) * 2, 2 * M * N * K3, f"fc1_gelu_x3 K{K3 // 3}"
+    if name == "cnx_dwconv7_ln_fwd_x3":
+        N, H, W, C = a[6:10]
+        MC = N * H * W * C
+        return MC * (4 + 4 + 6) + 8 * N * H * W + 52 * C * 4, 106 * MC, f"dwconv7_ln_fwd_x3 C{C} H{H}"
+    if name == "cnx_split3":
+        M, C = a[1:3]
+        return M * C * (4 + 6), 0, f"split3 C{C}"
+    if name == "cnx_mixup_batch":
+        B, C, H, W = a[2:6]
+        return B * C * H * W * 4 * (3 if a[1] else 2), 0, "mixup_batch"
     if name == "cnx_gemm_bias_scale_residual_fwd":
         M, N, K = a[9:12]
         e, s = es(a[12]), es(a[8])
-        return (M * K + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
+        ka = K * 2 // 3 if (a[13] & 2) else K                      # CNX_GEMM_A_SPLIT2: A holds 2 of the 3 K segments
+        return (M * ka + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
     if name == "cnx_mlp_fused_fwd":
         M, C = a[10:12]
         return M * C * (2 + 4 + 4) + 8 * C * C * 2, 16 * M * C * C, f"mlp_fused_fwd C{C}"
@@ -248,12 +264,14 @@ def run_ours(a):
              torch.randint(0, a.classes, (B,), generator=g).pin_memory()) for _ in range(n_host)]
     devb = [(x.to(dev), t.to(dev)) for x, t in host]
 
+    acc_fp32 = [not a.acc_autocast]
+
     def epoch(batches):
         if a.no_acc_forward:
             return _fast_epoch(batches)
         return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=True,
                                        num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch,
-                                       acc_forward_fp32=a.acc_fp32)
+                                       acc_forward_fp32=acc_fp32[0])
 
     def _fast_epoch(batches):
         net.train(True)
@@ -288,13 +306,22 @@ def run_ours(a):
 
     # warm-up (both input sources), then the two timed regions
     timed(devb, max(a.warmup, 3))
-    timed(host, 2)
+    timed(host, max(a.warmup, 3))                                 # (first host-fed steps grow the allocator's pools: seen as a 300 ms one-off)
     names_top = None
     with ClockSampler(local) as clk:
         c0 = L.gpu_launches()
         ms_dev, stats = timed(devb, a.steps)
         launches = L.gpu_launches() - c0
         ms_e2e, _ = timed(host, a.steps)
+        variants = None
+        if not a.no_variants and not a.no_acc_forward:
+            # the same step with the accuracy forward on the other side of the autocast boundary (see engine.py docstring)
+            acc_fp32[0] = not acc_fp32[0]
+            timed(devb, 3)
+            ms_v, _ = timed(devb, a.steps)
+            acc_fp32[0] = not acc_fp32[0]
+            variants = {("accuracy_forward_fp32_outside_autocast" if a.acc_autocast else "accuracy_forward_under_bf16_autocast"):
+                        {"value": round(B * world * a.steps / (ms_v * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_v / a.steps, 3)}}
     clocks = clk.summary()
 
     # per-kernel breakdown pass (untimed for the headline): every C-ABI call bracketed by CUDA events
@@ -352,7 +379,7 @@ def run_ours(a):
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / a.steps, 3), "api": "imageclassification_b200.engine.train_one_epoch on pinned host batches (H2D of batch i+1 on a side stream during step i)"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "variants": variants, "kernels": table,
     }
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:

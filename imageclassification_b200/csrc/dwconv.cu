@@ -615,6 +615,8 @@ int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* 
                       float* rstd, cudaStream_t s);
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
                      int64_t H, int64_t W, int64_t C, cudaStream_t s);
+int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, float* mean, float* rstd, cudaStream_t s);
 int dwconv7_wgrad_v2(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W, int64_t C,
                      float* partial, int P, cudaStream_t s);
 static bool dw_v1() {
@@ -655,6 +657,15 @@ int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* wt, const float*
     return pick_conv<MODE_FWD, bf16, bf16>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
   set_error("dwconv7_ln_fwd: bf16 stream with fp32 activations is not a supported combination");
   return CNX_E_BADARG;
+}
+
+int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                          int64_t N, int64_t H, int64_t W, int64_t C, float* y_scratch, void* xn3, float* mean, float* rstd,
+                          void* stream) {
+  CNX_REQUIRE(x && wt && bias && ln_w && ln_b && y_scratch && xn3 && mean && rstd, CNX_E_BADARG, "dwconv7_ln_fwd_x3: null pointer");
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_ln_fwd_x3: bad shape");
+  CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_ln_fwd_x3: C=%lld must be a multiple of 32", (long long)C);
+  return dwconv7_ln_fwd_x3_v2(x, wt, bias, ln_w, ln_b, eps, N, H, W, C, y_scratch, xn3, mean, rstd, (cudaStream_t)stream);
 }
 
 int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype,

@@ -106,6 +106,22 @@ __device__ __forceinline__ uint4 pack16(const float (&v)[4], float*) {
   return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
 }
 
+// fp32-accurate forward ("x3", include/cnx.h): the normalised row leaves as the A-side split operand [hi | mid | hi] (bf16,
+// row stride 3C) instead of fp32 xn — 4 values per lane, three 8-byte stores
+__device__ __forceinline__ void store_split3(bf16* row3, int C, int col, const float (&x)[4]) {
+  uint2 hi, mid;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(x[1]), "f"(x[0]));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(x[3]), "f"(x[2]));
+  const float r0 = x[0] - __uint_as_float(hi.x << 16), r1 = x[1] - __uint_as_float(hi.x & 0xffff0000u);
+  const float r2 = x[2] - __uint_as_float(hi.y << 16), r3 = x[3] - __uint_as_float(hi.y & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.x) : "f"(r1), "f"(r0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.y) : "f"(r3), "f"(r2));
+  *reinterpret_cast<uint2*>(row3 + col) = hi;
+  *reinterpret_cast<uint2*>(row3 + C + col) = mid;
+  *reinterpret_cast<uint2*>(row3 + 2 * C + col) = hi;
+}
+__device__ __forceinline__ void store_split3(bf16*, int, int, const float (&)[8]) {}   // bf16 activations: never taken
+
 // tile pixel slot p (row-major over [NB][ROWS][TW]) -> global pixel index, or -1 outside the tensor
 template <class G, bool EXACT>
 __device__ __forceinline__ int64_t tile_pixel(const TileCoord& t, int p, int N, int H, int W) {
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(ConvCfg<G, MODE, TIN>::NT, 1)
 dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int N, int H, int W, int C,
                   int tiles_x, int tiles_y, int ntiles, const float* __restrict__ bias, const TOUT* __restrict__ dres,
                   TOUT* out, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TOUT* __restrict__ xn,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ xn3) {
   typedef ConvCfg<G, MODE, TIN> Cfg;
   constexpr int STAGES = Cfg::STAGES, NWC = Cfg::NWC, NLN = Cfg::NLN;
   constexpr int NPIX = G::CPW * G::TH;
@@ -280,7 +296,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const float2* stp = stats + tb * STATS_STRIDE;
         for (int p0 = lw * ppw; p0 < G::P; p0 += LNW * ppw * U) {
           uint4 raw[U];
-          int64_t off[U];
+          int64_t off[U], mm[U];
           float2 ms[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -290,6 +306,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               const int64_t m = tile_pixel<G, EXACT>(t, p, N, H, W);
               if (m >= 0) {
                 off[u] = m * C + v * VEC;
+                mm[u] = m;
                 raw[u] = ld_global_16(out + off[u]);
                 ms[u] = stp[p];
               }
@@ -302,7 +319,8 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               unpack16(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
               for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-              *reinterpret_cast<uint4*>(xn + off[u]) = pack16(x, (TOUT*)nullptr);
+              if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mm[u] * 3 * C, C, v * VEC, x);
+              else *reinterpret_cast<uint4*>(xn + off[u]) = pack16(x, (TOUT*)nullptr);
             }
           }
         }
@@ -348,7 +366,8 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   unpack16(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
                   for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-                  *reinterpret_cast<uint4*>(xn + mrow[u] * C + v * VEC) = pack16(x, (TOUT*)nullptr);
+                  if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mrow[u] * 3 * C, C, v * VEC, x);
+                  else *reinterpret_cast<uint4*>(xn + mrow[u] * C + v * VEC) = pack16(x, (TOUT*)nullptr);
                 }
               }
             }
@@ -364,7 +383,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 template <class G, int MODE, typename TIN, typename TOUT, bool EXACT>
 static int launch_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                        const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
-                       int64_t H, int64_t W, int64_t C, cudaStream_t s) {
+                       int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr) {
   typedef ConvCfg<G, MODE, TIN> Cfg;
   CUtensorMap tmX, tmW;
   if (int rc = make_map_nhwc(&tmX, x, x_dtype, N, H, W, C, G::HW, G::HH, G::NB)) return rc;
@@ -378,20 +397,20 @@ static int launch_conv(const void* x, int x_dtype, const float* wt, const float*
   int grid = sm_count();
   if (grid > nt) grid = (int)nt;
   k<<<grid, Cfg::NT, Cfg::SMEM, s>>>(tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias, (const TOUT*)dres,
-                                     (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd);
+                                     (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd, (bf16*)xn3);
   return check_launch(MODE == MODE_FWD ? "dwconv7_ln_fwd" : "dwconv7_dgrad");
 }
 
 template <int MODE, typename TIN, typename TOUT>
 static int pick_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                      const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
-                     int64_t H, int64_t W, int64_t C, cudaStream_t s) {
+                     int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr) {
   const int gid = pick_geo(N, H, W);
   CNX_GEO_SWITCH(gid, {
     const bool exact = (W % G::TW == 0) && (H % G::ROWS == 0) && (N % G::NB == 0);
     if (exact)
-      return launch_conv<G, MODE, TIN, TOUT, true>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
-    return launch_conv<G, MODE, TIN, TOUT, false>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
+      return launch_conv<G, MODE, TIN, TOUT, true>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3);
+    return launch_conv<G, MODE, TIN, TOUT, false>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3);
   });
   return CNX_E_BADARG;
 }
@@ -574,6 +593,13 @@ int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* 
     return pick_conv<MODE_FWD, bf16, bf16>(x, x_dtype, wt, bias, nullptr, y, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s);
   set_error("dwconv7_ln_fwd: bf16 stream with fp32 activations is not a supported combination");
   return CNX_E_BADARG;
+}
+
+// fp32 stream, fp32 conv + LayerNorm; the normalised rows leave as the split operand xn3 bf16 [M, 3C]; y is fp32 scratch
+int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, float* mean, float* rstd, cudaStream_t s) {
+  using namespace dw2;
+  return pick_conv<MODE_FWD, float, float>(x, CNX_F32, wt, bias, nullptr, y, ln_w, ln_b, eps, y, mean, rstd, N, H, W, C, s, xn3);
 }
 
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,

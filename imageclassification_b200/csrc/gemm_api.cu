@@ -58,6 +58,12 @@ int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float*
   CNX_REQUIRE(dtype_ok(stream_dtype) && rows_per_sample > 0, CNX_E_BADARG, "gemm_bias_scale_residual_fwd: bad argument");
   EpiParams ep = {b2, gamma, dp, rows_per_sample, shortcut, out, nullptr, N};
   cudaStream_t s = (cudaStream_t)stream;
+  if (flags & CNX_GEMM_A_SPLIT2) {
+    // A is the [hi | mid] split operand written by cnx_gemm_bias_gelu_fwd_x3 (2K/3 columns); K counts all three segments
+    CNX_REQUIRE(dtype == CNX_BF16 && !(flags & CNX_GEMM_FORCE_SIMT) && K % 3 == 0 && (K / 3) % 64 == 0, CNX_E_SHAPE,
+                "gemm_bias_scale_residual_fwd: CNX_GEMM_A_SPLIT2 needs bf16 operands and K/3 a multiple of 64 (K=%lld)", (long long)K);
+    ep.a_wrap = (int32_t)(2 * (K / 3));
+  }
   if (dtype == CNX_F32) {
     CNX_REQUIRE(stream_dtype == CNX_F32, CNX_E_BADARG, "fp32 GEMM needs an fp32 residual stream");
     return gemm_tn_simt<float, float, EPI_SCALE_RES>(A, W2, M, N, K, ep, s);

@@ -8,10 +8,11 @@ What is kept exactly (results identical to engine.py on the same inputs):
     `loss.item()` + non-finite guard that skips the step (:54-59), `loss /= update_freq; backward; step every
     update_freq; zero_grad; model_ema.update` (:61-77), the second no-grad forward on the un-mixed batch for train
     accuracy when mixup is on (:89-97), per-class TP/FP/FN totals and the returned {loss, class_acc} global averages.
-What differs:
-  * under `use_amp=True` the accuracy forward (:89-97) runs inside the same bf16 autocast as the training forward; the
-    reference leaves it outside its autocast block (fp32).  Parameters, EMA and loss are unaffected; `class_acc` and the
-    TP/FP/FN counts can differ on argmax near-ties.  `acc_forward_fp32=True` reproduces the reference's placement.
+Placement of the accuracy forward: the reference runs `model(original_samples)` (:89-97) OUTSIDE its autocast block, i.e. in
+fp32 even when `use_amp=True`; so does this function by default (`acc_forward_fp32=True`: fp32-accurate split-operand tcgen05
+GEMMs, include/cnx.h "x3").  `acc_forward_fp32=False` runs it under the same bf16 autocast as the training forward instead —
+cheaper (bench.py reports both), parameters / EMA / loss unaffected, `class_acc` and the TP/FP/FN counts can differ on argmax
+near-ties.
 What differs, without changing results:
   * `use_amp=True` means bf16 autocast with no GradScaler (the BASELINE north-star precision; the reference's
     torch.amp.autocast('cuda') defaults to fp16 + scaler).
@@ -120,7 +121,7 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
                     start_steps: Optional[int] = 0, lr_schedule_values=None, wd_schedule_values=None,
                     num_training_steps_per_epoch: Optional[int] = None, update_freq: Optional[int] = 1,
                     use_amp: bool = False, num_classes: int = 2, verbose: bool = True,
-                    prefetch: bool = True, acc_forward_fp32: bool = False):
+                    prefetch: bool = True, acc_forward_fp32: bool = True):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "

@@ -26,6 +26,10 @@ FUSED_MLP = os.environ.get("CNX_FUSED_MLP", "1") != "0"
 # stages 1-3 instead (a third less activation traffic there, still inside the bf16 tolerance) — NOT the reference's dtypes,
 # so it is opt-in and bench.py names it in `config` when set.
 KEEP_BF16_STREAM = os.environ.get("CNX_BF16_STREAM", "0") == "1"
+# fp32 (no autocast) no-grad forward — the reference's accuracy forward (engine.py:89-97) and evaluate() — on the tensor cores
+# with split bf16 operands (include/cnx.h "x3"): fp32-accurate (~2^-16 per product), 3 MMAs per product instead of CUDA-core
+# FMAs.  CNX_X3_FWD=0 selects the CUDA-core fp32 GEMMs for comparison.
+X3_FWD = os.environ.get("CNX_X3_FWD", "1") != "0"
 
 
 def _act_dtype() -> torch.dtype:
@@ -98,7 +102,8 @@ class _PrepRegistry:
         e = self.entries.get(k)
         if e is None or e["w"]() is not w:
             R, Cc = w.shape
-            out = torch.empty((R, Cc) if mode == 0 else (Cc, R), dtype=out_dtype, device=w.device)
+            shape = (R, Cc) if mode == 0 else ((R, 3 * Cc) if mode == 3 else (Cc, R))
+            out = torch.empty(shape, dtype=out_dtype, device=w.device)
             e = {"w": weakref.ref(w), "scale": weakref.ref(scale) if scale is not None else None, "out": out, "key": None,
                  "mode": mode, "dtype": out_dtype}
             self.entries[k] = e
@@ -187,11 +192,31 @@ class _BlockFn(torch.autograd.Function):
         dev = x.device
         sd, ad = L.dt(xl), L.dt(act_dtype)
         st = L.stream()
+        C4 = w1.shape[0]
+        # `track` = grad mode of the CALLER (inside Function.forward grad mode is always off; needs_input_grad alone is True
+        # for parameters even under torch.no_grad())
+        need_grad = track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:10]))
         y = torch.empty((M, C), dtype=act_dtype, device=dev)
-        xn = torch.empty((M, C), dtype=act_dtype, device=dev)
         mean = torch.empty((M,), dtype=torch.float32, device=dev)
         rstd = torch.empty((M,), dtype=torch.float32, device=dev)
         wt = _conv_weight_tap_major(conv_w)
+        if not need_grad and X3_FWD and act_dtype == torch.float32 and C % 32 == 0 and C4 % 64 == 0:
+            # fp32 no-grad pass on the tensor cores: split operands [hi | mid | hi] x [hi | hi | mid], K' = 3K; the LayerNorm half
+            # of the dwconv kernel writes the split operand itself
+            bf = torch.bfloat16
+            a3 = torch.empty((M, 3 * C), dtype=bf, device=dev)
+            L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(xl), L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C,
+                                              L.ptr(y), L.ptr(a3), L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd_x3")
+            g2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)            # [hi | mid] of g
+            L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), M, C4, 3 * C,
+                                                  L.ptr(g2), st), "gemm_bias_gelu_fwd_x3")
+            del a3
+            out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+            L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g2), L.ptr(_weight_prep(w2, 3, None, bf)), L.ptr(b2), L.ptr(gamma),
+                                                         L.ptr(dp), H * W, L.ptr(xl), L.ptr(out), sd, M, C, 3 * C4, L.dt(bf),
+                                                         L.CNX_GEMM_A_SPLIT2, st), "gemm_bias_scale_residual_fwd(x3)")
+            return out.permute(0, 3, 1, 2)
+        xn = torch.empty((M, C), dtype=act_dtype, device=dev)
         L.check(lib.cnx_dwconv7_ln_fwd(L.ptr(xl), sd, L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps,
                                        N, H, W, C, L.ptr(y), L.ptr(xn), ad, L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd")
         if act_dtype == torch.float32:
@@ -199,10 +224,6 @@ class _BlockFn(torch.autograd.Function):
         else:
             w1a = _weight_prep(w1, 0, None, act_dtype)
             w2a = _weight_prep(w2, 0, None, act_dtype)
-        C4 = w1.shape[0]
-        # `track` = grad mode of the CALLER (inside Function.forward grad mode is always off; needs_input_grad alone is True
-        # for parameters even under torch.no_grad())
-        need_grad = track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:10]))
         if (not need_grad and FUSED_MLP and act_dtype == torch.bfloat16 and xl.dtype == torch.float32 and C in (96, 128, 192)
                 and C4 == 4 * C and M >= 128):
             # no-grad pass (engine.py:89-97 accuracy forward, evaluate()): fc1 -> GELU -> fc2 -> gamma / drop-path / residual
@@ -356,6 +377,27 @@ def _gemm_plain(A, B, bias, out_dtype):
     return out
 
 
+def _gemm_plain_x3(A, conv_w, channels_last_taps: bool, bias):
+    """fp32 out[M,N] = A[M,K] . W[N,K]^T + bias on the tensor cores with split bf16 operands (fp32-accurate, no-grad forward)."""
+    lib = L.load()
+    M, K = A.shape
+    bf = torch.bfloat16
+
+    def build():
+        w2 = _patch_weight(conv_w, torch.float32, channels_last_taps)
+        out = torch.empty((w2.shape[0], 3 * w2.shape[1]), dtype=bf, device=w2.device)
+        L.check(lib.cnx_weight_prep(L.ptr(w2), w2.shape[0], w2.shape[1], None, 3, L.ptr(out), L.dt(bf), L.stream()), "weight_prep(x3)")
+        return out
+    B3 = _derived((conv_w,), ("patchw_x3", channels_last_taps), build)
+    a3 = torch.empty((M, 3 * K), dtype=bf, device=A.device)
+    L.check(lib.cnx_split3(L.ptr(A), M, K, L.ptr(a3), L.stream()), "split3")
+    Nn = B3.shape[0]
+    out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    L.check(lib.cnx_gemm_plain(L.ptr(a3), L.ptr(B3), L.ptr(bias), L.ptr(out), L.dt(torch.float32), M, Nn, 3 * K, L.dt(bf), 0,
+                               L.stream()), "gemm_plain(x3)")
+    return out
+
+
 def _ln_fwd(x2, w, b, eps, out_dtype):
     lib = L.load()
     M, C = x2.shape
@@ -405,7 +447,10 @@ class _StemFn(torch.autograd.Function):
         M = N * (H // 4) * (W // 4)
         A = torch.empty((M, Cin * 16), dtype=act_dtype, device=x.device)
         L.check(lib.cnx_patchify4_nchw(L.ptr(xc), N, Cin, H, W, L.ptr(A), L.dt(act_dtype), L.stream()), "patchify4")
-        y = _gemm_plain(A, _patch_weight(conv_w, act_dtype, False), conv_b, act_dtype)
+        if not track and X3_FWD and act_dtype == torch.float32 and Cout % 8 == 0:
+            y = _gemm_plain_x3(A, conv_w, False, conv_b)
+        else:
+            y = _gemm_plain(A, _patch_weight(conv_w, act_dtype, False), conv_b, act_dtype)
         out, mean, rstd = _ln_fwd(y, ln_w, ln_b, eps, torch.float32)
         if track and any(ctx.needs_input_grad[1:5]):
             ctx.save_for_backward(A, y, mean, rstd, conv_w, ln_w)
@@ -439,7 +484,10 @@ class _DownsampleFn(torch.autograd.Function):
         rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
         L.check(lib.cnx_ln_fwd_patch2(L.ptr(xl), L.dt(xl), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C, L.ptr(A), L.dt(act_dtype),
                                       L.ptr(mean), L.ptr(rstd), L.stream()), "ln_fwd_patch2")
-        out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
+        if not track and X3_FWD and act_dtype == torch.float32 and C2 % 8 == 0:
+            out = _gemm_plain_x3(A, conv_w, True, conv_b)
+        else:
+            out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
         if track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5])):
             ctx.save_for_backward(xl, mean, rstd, A, conv_w, ln_w)
             ctx.shape = (N, C, H, W)

@@ -162,6 +162,9 @@ CNX_API int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, i
  * kernel (test-only cross-check of the tensor-core path).
  * ---------------------------------------------------------------------------------------------- */
 #define CNX_GEMM_FORCE_SIMT 1
+/* cnx_gemm_bias_scale_residual_fwd only: A is a two-segment split operand [hi | mid] with 2K/3 columns (written by
+ * cnx_gemm_bias_gelu_fwd_x3); the K loop covers three segments and the third re-reads the first ([hi | mid | hi]). */
+#define CNX_GEMM_A_SPLIT2 2
 
 /* fc1: h = round_dtype(A.W1^T + b1) ; g_out = GELU_erf(h) ; gprime_out = GELU_erf'(h) (what backward needs of h:
  * saved instead of h so the dgrad epilogue is one multiply).  gprime_out may be NULL (no-grad forward). */
@@ -182,10 +185,16 @@ CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, cons
  * accuracy forward of engine.py:89-97 and evaluate(), engine.py:145-225, run in fp32 in the reference).
  *   cnx_split3                  x fp32 [M,C] -> out bf16 [M,3C] = [hi | mid | hi]                    (A side)
  *   cnx_weight_prep mode 3      W fp32 [R,C] -> out bf16 [R,3C] = [hi | hi | mid]                    (B side)
- *   cnx_gemm_bias_gelu_fwd_x3   g3 bf16 [M,3N] = [hi | mid | hi] of GELU_erf(A.W^T + b1) (fp32 epilogue), A3 [M,K3], W3 [N,K3]
- *   fc2: cnx_gemm_bias_scale_residual_fwd(A = g3, W2 = mode-3 weight, K = 3*4C, dtype = CNX_BF16, stream_dtype = CNX_F32)
+ *   cnx_gemm_bias_gelu_fwd_x3   g2 bf16 [M,2N] = [hi | mid] of GELU_erf(A.W^T + b1) (fp32 epilogue), A3 [M,K3], W3 [N,K3]
+ *   fc2: cnx_gemm_bias_scale_residual_fwd(A = g2, W2 = mode-3 weight, K = 3*4C, dtype = CNX_BF16, stream_dtype = CNX_F32,
+ *        flags = CNX_GEMM_A_SPLIT2: the third K segment re-reads g2's hi columns, so g leaves and re-enters HBM as 2 pieces)
  *   plain: cnx_gemm_plain(A3, B3, ..., out fp32, K = 3K, dtype = CNX_BF16) */
 CNX_API int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream);
+/* cnx_dwconv7_ln_fwd on an fp32 stream whose LayerNorm rows leave directly as the A-side split operand xn3 bf16 [M,3C]
+ * (no fp32 xn, no separate cnx_split3 pass).  y_scratch fp32 [M,C] holds the conv output between the two halves of the kernel. */
+CNX_API int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
+                          float eps, int64_t N, int64_t H, int64_t W, int64_t C, float* y_scratch, void* xn3, float* mean,
+                          float* rstd, void* stream);
 CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
                               void* g3, void* stream);
 

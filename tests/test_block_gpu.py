@@ -151,3 +151,37 @@ def test_convnext_base_large_fwd_bwd_bf16(name, img, batch):
     tot_p = math.sqrt(sum((gp[n].double() ** 2).sum().item() for n in go))
     tot_d = math.sqrt(sum(((gp[n].double() - go[n].double()) ** 2).sum().item() for n in go))
     assert tot_d / tot_p <= 2e-2, (tot_d / tot_p)
+
+
+@pytest.mark.parametrize("C,H", SWEEP + [(64, 5)])
+def test_block_fp32_nograd_forward_on_tensor_cores(C, H):
+    """fp32 no-grad forward (the reference's accuracy forward / evaluate run outside autocast): split-operand tcgen05 GEMMs
+    (include/cnx.h "x3") vs the oracle in fp32 — the fp32 bar (1e-4) — and vs this package's CUDA-core fp32 path."""
+    from imageclassification_b200 import ops
+    o, p = _pair_block(C, 0.0, 1.0, 3 * C + H)
+    N = 3 if C * H * H < 200000 else 2
+    x = torch.randn(N, C, H, H, device=DEV)
+    with torch.no_grad():
+        yo = o(x)
+        assert ops.X3_FWD
+        yp = p(x)
+        ops.X3_FWD = False
+        try:
+            ys = p(x)
+        finally:
+            ops.X3_FWD = True
+    assert yp.dtype == torch.float32
+    assert max_rel(yp, yo) <= 1e-4
+    assert max_rel(yp, ys) <= 1e-4
+    # the branch itself (what the GEMMs produce), not hidden behind the shortcut
+    assert max_rel(yp - x, yo - x) <= 1e-4
+
+
+def test_convnext_tiny_fp32_nograd_forward_on_tensor_cores():
+    o, p = _pair_model("convnext_tiny", 10, 0.0, 1.0, 17)
+    x = torch.randn(4, 3, 224, 224, device=DEV)
+    o.eval()
+    p.eval()
+    with torch.no_grad():
+        lo, lp = o(x), p(x)
+    assert max_rel(lp, lo) <= 1e-4

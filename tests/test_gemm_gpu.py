@@ -132,3 +132,53 @@ def test_fused_mlp_forward_matches_two_gemm_path(M, C, with_dp):
     z = F.gelu(h).to(torch.bfloat16).float() @ W2.float().t() + b2
     s = dp.repeat_interleave(rps)[:M, None] if with_dp else 1.0
     assert max_rel(out, sc + s * (gamma * z)) <= 2e-2
+
+
+@pytest.mark.parametrize("M,C", [(300, 96), (1000, 40), (128, 768), (5, 8)])
+def test_split_operands_reconstruct_fp32(M, C):
+    """cnx_split3 / weight-prep mode 3: [hi | mid | hi] and [hi | hi | mid]; hi + mid = x to 2^-16 relative."""
+    from imageclassification_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device=DEV).manual_seed(M + C)
+    x = torch.randn(M, C, device=DEV, generator=g) * 3
+    a3 = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.cnx_split3(L.ptr(x), M, C, L.ptr(a3), L.stream()), "split3")
+    hi, mid, hi2 = a3[:, :C].float(), a3[:, C:2 * C].float(), a3[:, 2 * C:].float()
+    assert torch.equal(hi, hi2) and torch.equal(hi, x.to(torch.bfloat16).float())
+    assert ((hi + mid - x).abs() <= x.abs() * 2 ** -16 + 1e-30).all()
+    b3 = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.cnx_weight_prep(L.ptr(x), M, C, None, 3, L.ptr(b3), L.dt(torch.bfloat16), L.stream()), "weight_prep")
+    assert torch.equal(b3[:, :C], a3[:, :C]) and torch.equal(b3[:, C:2 * C], a3[:, :C]) and torch.equal(b3[:, 2 * C:], a3[:, C:2 * C])
+
+
+@pytest.mark.parametrize("M,C", [(3136, 96), (777, 128), (1000, 384), (130, 768)])
+def test_x3_mlp_forward_is_fp32_accurate(M, C):
+    """fc1 + GELU + fc2 + layer-scale + residual with split operands vs float64 on the SAME fp32 inputs: 1e-5 typical."""
+    from imageclassification_b200 import _lib as L
+    lib = L.load()
+    A, W1, b1, W2, b2, gamma = _mk(M, C, torch.float32, 11 * M + C)
+    sc = torch.randn(M, C, device=DEV)
+    bf = torch.bfloat16
+    a3 = torch.empty(M, 3 * C, dtype=bf, device=DEV)
+    w13 = torch.empty(4 * C, 3 * C, dtype=bf, device=DEV)
+    w23 = torch.empty(C, 12 * C, dtype=bf, device=DEV)
+    g2 = torch.empty(M, 8 * C, dtype=bf, device=DEV)
+    out = torch.empty(M, C, device=DEV)
+    st = L.stream()
+    L.check(lib.cnx_split3(L.ptr(A), M, C, L.ptr(a3), st))
+    L.check(lib.cnx_weight_prep(L.ptr(W1), 4 * C, C, None, 3, L.ptr(w13), L.dt(bf), st))
+    L.check(lib.cnx_weight_prep(L.ptr(W2), C, 4 * C, None, 3, L.ptr(w23), L.dt(bf), st))
+    L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C, L.ptr(g2), st))
+    gd = F.gelu(A.double() @ W1.double().t() + b1.double())
+    ghat = g2[:, :4 * C].double() + g2[:, 4 * C:].double()
+    assert max_rel(ghat, gd) <= 2e-5
+    L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g2), L.ptr(w23), L.ptr(b2), L.ptr(gamma), None, 49, L.ptr(sc), L.ptr(out),
+                                                 L.dt(torch.float32), M, C, 12 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st))
+    ref = sc.double() + gamma.double() * (gd @ W2.double().t() + b2.double())
+    assert max_rel(out.double() - sc.double(), ref - sc.double()) <= 3e-5
+    # the same fc2 from an explicit three-segment operand (no wrap): identical MMAs, identical result
+    g3 = torch.cat([g2, g2[:, :4 * C]], dim=1).contiguous()
+    out3 = torch.empty_like(out)
+    L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g3), L.ptr(w23), L.ptr(b2), L.ptr(gamma), None, 49, L.ptr(sc), L.ptr(out3),
+                                                 L.dt(torch.float32), M, C, 12 * C, L.dt(bf), 0, st))
+    assert torch.equal(out, out3)
