@@ -23,6 +23,14 @@ namespace dw2 {
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };
 constexpr int LNW = 4;                                   // LayerNorm warps
+// rows in flight per LayerNorm warp (narrow rows: several pixels per pass / wide rows: one pixel per pass): the LN half streams
+// the tile back from L2 and is latency-bound, so its throughput is the bytes it keeps in flight
+#ifndef CNX_DW_LNU1
+#define CNX_DW_LNU1 8
+#endif
+#ifndef CNX_DW_LNU2
+#define CNX_DW_LNU2 4
+#endif
 
 template <class G, int MODE, typename TIN>
 struct ConvCfg {
@@ -288,7 +296,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float w[VEC], b[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { w[e] = active ? __ldg(ln_w + v * VEC + e) : 0.f; b[e] = active ? __ldg(ln_b + v * VEC + e) : 0.f; }
-      constexpr int U = 4;
+      constexpr int U = CNX_DW_LNU1;
       for (int i = 0; i < my_tiles; ++i) {
         const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
         const int tb = i & 1;
@@ -329,7 +337,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     } else {
       // wide rows: one pixel per warp pass, lanes stride over the row; two pixels in flight
-      constexpr int U = 2;
+      constexpr int U = CNX_DW_LNU2;
       for (int i = 0; i < my_tiles; ++i) {
         const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
         const int tb = i & 1;

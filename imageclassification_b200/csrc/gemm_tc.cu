@@ -287,6 +287,26 @@ __device__ __forceinline__ float gelu_as(float h) {
   return h * phi;
 }
 
+// the same on two elements at a time: packed fp32x2 FMAs for everything but the two MUFU pairs and the sign select
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float2 gelu_as2(float2 h) {
+  const float2 d = __ffma2_rn(make_float2(fabsf(h.x), fabsf(h.y)), make_float2(0.23164190398f, 0.23164190398f), make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_fast(d.x), rcp_fast(d.y));
+  float2 p = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  p = __ffma2_rn(p, t, make_float2(0.7107068705f, 0.7107068705f));
+  p = __ffma2_rn(p, t, make_float2(-0.142248368f, -0.142248368f));
+  p = __ffma2_rn(p, t, make_float2(0.127414796f, 0.127414796f));
+  p = __fmul2_rn(p, t);
+  const float2 a = __fmul2_rn(__fmul2_rn(h, h), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  const float2 q = __fmul2_rn(p, make_float2(exp2f_fast(a.x), exp2f_fast(a.y)));
+  const float2 phi = make_float2(h.x >= 0.f ? 1.0f - q.x : q.x, h.y >= 0.f ? 1.0f - q.y : q.y);
+  return __fmul2_rn(h, phi);
+}
+
 constexpr int kSlabBytes = 4096;                 // one epilogue slab: [32 rows][32 columns] of <= 4-byte elements
 template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
   static constexpr int THREADS = (kFirstEpiWarp + NEPI) * 32;
@@ -545,13 +565,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
-          const float g0 = gelu_as(v[i] + b4.x), g1 = gelu_as(v[i + 1] + b4.y);
-          const float g2 = gelu_as(v[i + 2] + b4.z), g3 = gelu_as(v[i + 3] + b4.w);
-          const uint32_t ha = pack_bf16(g0, g1), hb = pack_bf16(g2, g3);
+          const float2 ga = gelu_as2(__fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y)));
+          const float2 gb = gelu_as2(__fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w)));
+          const uint32_t ha = pack_bf16(ga.x, ga.y), hb = pack_bf16(gb.x, gb.y);
           pg[i / 2] = ha;
           pg[i / 2 + 1] = hb;
-          pd[i / 2] = pack_bf16(g0 - bf16_lo(ha), g1 - bf16_hi(ha));
-          pd[i / 2 + 1] = pack_bf16(g2 - bf16_lo(hb), g3 - bf16_hi(hb));
+          const float2 ra = __fadd2_rn(ga, make_float2(-bf16_lo(ha), -bf16_hi(ha)));
+          const float2 rb = __fadd2_rn(gb, make_float2(-bf16_lo(hb), -bf16_hi(hb)));
+          pd[i / 2] = pack_bf16(ra.x, ra.y);
+          pd[i / 2 + 1] = pack_bf16(rb.x, rb.y);
         }
       }
       if (KIND == EPI_BIAS_GELU) {

@@ -76,6 +76,7 @@ for si in [int(s) for s in args.stages.split(",")]:
     tag = f"C{C}_H{H}"
     if only is None or "dwconv" in only:
         timeit(f"dwconv7_ln_fwd {tag}", lambda: cabi.dwconv7_ln_fwd(x, w, b, lw, lb, 1e-6, bf))
+        timeit(f"dwconv7_ln_fwd_x3 {tag}", lambda: cabi.dwconv7_ln_fwd_x3(x, w, b, lw, lb, 1e-6))
         dy = torch.randn(M, C, device=dev, generator=g).to(bf)
         timeit(f"dwconv7_dgrad {tag}", lambda: cabi.dwconv7_dgrad(dy, w, x, (N, H, H, C), f32))
         timeit(f"dwconv7_wgrad {tag}", lambda: cabi.dwconv7_wgrad(dy, x, P=max(1, L.load().cnx_sm_count() // (C // 32))))
@@ -100,6 +101,20 @@ for si in [int(s) for s in args.stages.split(",")]:
         if C <= 192:
             timeit(f"mlp_fused_fwd {tag}", lambda: cabi.mlp_fused_fwd(A, W1, b1, W2, b2, gam, None, H * H, xs))
         timeit(f"fc2_scale_res {tag}", lambda: cabi.gemm_scale_res(gg, W2, b2, gam, None, H * H, xs, f32))
+        # fp32-accurate forward GEMMs on split operands (x3)
+        lib = L.load()
+        a3 = torch.randn(M, 3 * C, device=dev, generator=g).to(bf)
+        w13 = (torch.randn(4 * C, 3 * C, device=dev, generator=g) / C ** 0.5).to(bf)
+        w23 = (torch.randn(C, 12 * C, device=dev, generator=g) / (4 * C) ** 0.5).to(bf)
+        g2 = torch.empty(M, 8 * C, dtype=bf, device=dev)
+        o32 = torch.empty(M, C, device=dev)
+        st = L.stream()
+        timeit(f"fc1_gelu_x3 {tag}", lambda: L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C,
+                                                                                     L.ptr(g2), st)))
+        timeit(f"fc2_scale_res_x3 {tag}", lambda: L.check(lib.cnx_gemm_bias_scale_residual_fwd(
+            L.ptr(g2), L.ptr(w23), L.ptr(b2), L.ptr(gam), None, H * H, L.ptr(xs), L.ptr(o32), L.dt(f32), M, C, 12 * C, L.dt(bf),
+            L.CNX_GEMM_A_SPLIT2, st)))
+        del a3, g2, o32
         W2t = W2.t().contiguous()
         timeit(f"dgrad_fc2_gelu {tag}", lambda: cabi.gemm_dgelu(A, W2t, hh))
         W1t = W1.t().contiguous()

@@ -91,3 +91,22 @@ def test_dwconv_bwd(shape, dtypes):
     assert max_rel(db, br.grad) <= 1e-4
     dw2, _ = dwconv7_wgrad(dy, x, P=64)                   # different CTA count -> same sums within fp32 reassociation
     assert max_rel(dw2, wr.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_dwconv_ln_fwd_split_operand(shape):
+    """cnx_dwconv7_ln_fwd_x3: the LayerNorm half writes [hi | mid | hi] of the fp32 xn that cnx_dwconv7_ln_fwd produces."""
+    from cabi import dwconv7_ln_fwd_x3
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(N * H + C)
+    x = torch.randn(N, H, W, C, generator=g).to(DEV)
+    w = (0.1 * torch.randn(C, 1, 7, 7, generator=g)).to(DEV)
+    b = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    lw = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV)
+    lb = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    y, xn, mean, rstd = dwconv7_ln_fwd(x, w, b, lw, lb, 1e-6, torch.float32)
+    y3, a3, mean3, rstd3 = dwconv7_ln_fwd_x3(x, w, b, lw, lb, 1e-6)
+    assert torch.equal(y, y3) and torch.equal(mean, mean3) and torch.equal(rstd, rstd3)
+    hi, mid = a3[:, :C], a3[:, C:2 * C]
+    assert torch.equal(hi, xn.to(torch.bfloat16)) and torch.equal(a3[:, 2 * C:], hi)
+    assert torch.equal(mid, (xn - hi.float()).to(torch.bfloat16))
