@@ -361,6 +361,15 @@ def run_ours(a):
             else:
                 roof = {"bound": "hbm", "achieved": top["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
                         "frac": top["hbm_frac"], "traffic": None}
+            # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read + _write), if listed
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tr = json.load(f)
+                if top["kernel"] in tr["kernels"]:
+                    roof["traffic"] = tr["kernels"][top["kernel"]]
+                    roof["traffic_source"] = tr["source"]
+            except Exception:
+                pass
             roof.update({"kernel": top["kernel"], "launches_per_step": top["calls_per_step"],
                          "avg_launch_ms": round(d["ms"] / d["n"], 4), "peak_source": peaks["src"] + " (sustained; timed inside the step)",
                          "cnx_kernels_ms_per_step": round(tot / bsteps, 3), "step_ms_with_events": round(ms_b / bsteps, 3)})
