@@ -22,20 +22,27 @@ namespace cnx {
 namespace dw2 {
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };
-constexpr int LNW = 4;                                   // LayerNorm warps
 // rows in flight per LayerNorm warp (narrow rows: several pixels per pass / wide rows: one pixel per pass): the LN half streams
 // the tile back from L2 and is latency-bound, so its throughput is the bytes it keeps in flight
+#ifndef CNX_DW_LNW32
+#define CNX_DW_LNW32 8
+#endif
 #ifndef CNX_DW_LNU1
 #define CNX_DW_LNU1 8
 #endif
 #ifndef CNX_DW_LNU2
 #define CNX_DW_LNU2 4
 #endif
+// LayerNorm warps: 4 for bf16 activations; 8 for fp32 activations (twice the bytes to stream back and, for the split operand,
+// 1.5x the bytes to write: with 4 warps the LN half, not the FMA half, set the kernel time)
+// (only where 1 + NWC + 8 warps still leave 128 registers per thread: the exact 56 / 28 / 14 / 7-pixel geometries)
+template <typename TOUT, int NWC> struct LnWarps { static constexpr int N = (sizeof(TOUT) == 4 && NWC <= 7) ? CNX_DW_LNW32 : 4; };
 
-template <class G, int MODE, typename TIN>
+
+template <class G, int MODE, typename TIN, typename TOUT>
 struct ConvCfg {
   static constexpr int NWC = G::NWC;
-  static constexpr int NLN = (MODE == MODE_FWD) ? LNW : 0;
+  static constexpr int NLN = (MODE == MODE_FWD) ? LnWarps<TOUT, G::NWC>::N : 0;
   static constexpr int NT = (1 + NWC + NLN) * 32;
   static constexpr int HALO_BYTES = G::HALO_ELEMS * (int)sizeof(TIN);
   static constexpr int HALO_PAD = round128(HALO_BYTES);
@@ -144,12 +151,12 @@ __device__ __forceinline__ int64_t tile_pixel(const TileCoord& t, int p, int N, 
 // dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT
 // ------------------------------------------------------------------------------------------------
 template <class G, int MODE, typename TIN, typename TOUT, bool EXACT>
-__global__ void __launch_bounds__(ConvCfg<G, MODE, TIN>::NT, 1)
+__global__ void __launch_bounds__(ConvCfg<G, MODE, TIN, TOUT>::NT, 1)
 dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int N, int H, int W, int C,
                   int tiles_x, int tiles_y, int ntiles, const float* __restrict__ bias, const TOUT* __restrict__ dres,
                   TOUT* out, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TOUT* __restrict__ xn,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ xn3) {
-  typedef ConvCfg<G, MODE, TIN> Cfg;
+  typedef ConvCfg<G, MODE, TIN, TOUT> Cfg;
   constexpr int STAGES = Cfg::STAGES, NWC = Cfg::NWC, NLN = Cfg::NLN;
   constexpr int NPIX = G::CPW * G::TH;
   extern __shared__ uint8_t smem_raw[];
@@ -302,13 +309,13 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int tb = i & 1;
         mbar_wait(lnfull_bar(tb), (uint32_t)((i >> 1) & 1));
         const float2* stp = stats + tb * STATS_STRIDE;
-        for (int p0 = lw * ppw; p0 < G::P; p0 += LNW * ppw * U) {
+        for (int p0 = lw * ppw; p0 < G::P; p0 += NLN * ppw * U) {
           uint4 raw[U];
           int64_t off[U], mm[U];
           float2 ms[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int p = p0 + u * LNW * ppw + psub;
+            const int p = p0 + u * NLN * ppw + psub;
             off[u] = -1;
             if (active && p < G::P) {
               const int64_t m = tile_pixel<G, EXACT>(t, p, N, H, W);
@@ -343,12 +350,12 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int tb = i & 1;
         mbar_wait(lnfull_bar(tb), (uint32_t)((i >> 1) & 1));
         const float2* stp = stats + tb * STATS_STRIDE;
-        for (int p0 = lw; p0 < G::P; p0 += LNW * U) {
+        for (int p0 = lw; p0 < G::P; p0 += NLN * U) {
           int64_t mrow[U];
           float2 ms[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int p = p0 + u * LNW;
+            const int p = p0 + u * NLN;
             mrow[u] = (p < G::P) ? tile_pixel<G, EXACT>(t, p, N, H, W) : -1;
             ms[u] = (p < G::P) ? stp[p] : make_float2(0.f, 0.f);
           }
@@ -392,7 +399,7 @@ template <class G, int MODE, typename TIN, typename TOUT, bool EXACT>
 static int launch_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                        const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
                        int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr) {
-  typedef ConvCfg<G, MODE, TIN> Cfg;
+  typedef ConvCfg<G, MODE, TIN, TOUT> Cfg;
   CUtensorMap tmX, tmW;
   if (int rc = make_map_nhwc(&tmX, x, x_dtype, N, H, W, C, G::HW, G::HH, G::NB)) return rc;
   if (int rc = make_map_wt(&tmW, wt, C)) return rc;
