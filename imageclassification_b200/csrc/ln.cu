@@ -11,6 +11,7 @@ namespace cnx {
 
 constexpr int LN_WARPS = 8;
 
+static bool ln_v3_off();
 static bool ln_v1() {
   static int v = -1;
   if (v < 0) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restr
 
 // ---- LayerNorm forward, second generation: LPP lanes per row, 8-element vectors, U rows in flight per warp pass ----
 template <typename TX, typename TO, int NJ, int LPP, int U>
-__global__ void __launch_bounds__(LN_WARPS * 32, 3) ln_fwd_v2_kernel(const TX* __restrict__ x, const float* __restrict__ ln_w,
+__global__ void __launch_bounds__(LN_WARPS * 32, (NJ >= 3 ? 2 : 3)) ln_fwd_v2_kernel(const TX* __restrict__ x, const float* __restrict__ ln_w,
                                                                      const float* __restrict__ ln_b, float eps, int64_t M, int C,
                                                                      TO* __restrict__ out, float* __restrict__ mean_out,
                                                                      float* __restrict__ rstd_out, int pH, int pW) {
@@ -594,6 +595,18 @@ static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, fl
   int64_t blocks = (M + LN_WARPS - 1) / LN_WARPS;
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  if (C % 24 == 0 && M >= 4096 && !ln_v1() && !ln_v3_off()) {
+    // rows of 3 x 2^k sixteen-byte vectors (C = 96, 192): 3 vectors per lane, 4 / 8 lanes per row, no idle lanes
+    const int lpp = (int)(C / 24);
+    int64_t b3 = (int64_t)sm_count() * 2;
+#define CNX_LNF3(LPP)                                                                                                              \
+    ln_fwd_v2_kernel<TX, TO, 3, LPP, 2><<<(unsigned)b3, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, \
+                                                                                mean, rstd, pH, pW)
+    if (lpp == 4) { CNX_LNF3(4); return check_launch("ln_fwd"); }
+    if (lpp == 8) { CNX_LNF3(8); return check_launch("ln_fwd"); }
+    // (C = 384 / 768 measured no better than the one-warp-per-row kernel below: profiles/r01i_kbench_ln_fwd.txt)
+#undef CNX_LNF3
+  }
   if (C % 8 == 0 && C <= 256 && M >= 4096 && !ln_v1()) {
     int64_t b2 = (int64_t)sm_count() * 3;
     if (C <= 128)

@@ -81,6 +81,12 @@ for si in [int(s) for s in args.stages.split(",")]:
         timeit(f"dwconv7_dgrad {tag}", lambda: cabi.dwconv7_dgrad(dy, w, x, (N, H, H, C), f32))
         timeit(f"dwconv7_wgrad {tag}", lambda: cabi.dwconv7_wgrad(dy, x, P=max(1, L.load().cnx_sm_count() // (C // 32))))
         del dy
+    if only is None or "lnf" in only:
+        yb = torch.randn(M, C, device=dev, generator=g).to(bf)
+        timeit(f"ln_fwd bf16->f32 {tag}", lambda: cabi.ln_fwd(yb, lw, lb, 1e-6, f32))
+        xf = x.view(M, C)
+        timeit(f"ln_fwd f32->bf16 {tag}", lambda: cabi.ln_fwd(xf, lw, lb, 1e-6, bf))
+        del yb
     if only is None or "ln" in only:
         y = torch.randn(M, C, device=dev, generator=g).to(bf)
         dxn = torch.randn(M, C, device=dev, generator=g).to(bf)
