@@ -101,7 +101,7 @@ class _PrepRegistry:
         k = (id(w), mode, out_dtype)
         e = self.entries.get(k)
         if e is None or e["w"]() is not w:
-            R, Cc = w.shape
+            R, Cc = w.shape[0], w.numel() // w.shape[0]          # [C,1,7,7] conv weights count as [C, 49]
             shape = (R, Cc) if mode == 0 else ((R, 3 * Cc) if mode == 3 else (Cc, R))
             out = torch.empty(shape, dtype=out_dtype, device=w.device)
             e = {"w": weakref.ref(w), "scale": weakref.ref(scale) if scale is not None else None, "out": out, "key": None,
@@ -126,7 +126,7 @@ class _PrepRegistry:
         if self.table is None or self.table[3] != [(k, w.data_ptr(), sc.data_ptr() if sc is not None else 0) for k, e, w, sc in live]:
             rows, start = [], 0
             for k, e, w, sc in live:
-                R, Cc = w.shape
+                R, Cc = w.shape[0], w.numel() // w.shape[0]
                 tx, ty = (Cc + 31) // 32, (R + 31) // 32
                 rows.append(L.WeightPrepEntry(w.data_ptr(), sc.data_ptr() if sc is not None else None, e["out"].data_ptr(), R, Cc,
                                               e["mode"], L.dt(e["dtype"]), start, tx))
@@ -155,7 +155,11 @@ def _weight_prep(w: torch.Tensor, mode: int, row_scale, out_dtype) -> torch.Tens
 
 
 def _conv_weight_tap_major(conv_w: torch.Tensor) -> torch.Tensor:
-    """[C,1,7,7] -> [49,C] fp32 (what the dwconv kernels fetch by TMA)."""
+    """[C,1,7,7] -> [49,C] fp32 (what the dwconv kernels fetch by TMA): a transpose of the [C,49] matrix, refreshed together
+    with every other derived weight layout by the one cnx_weight_prep_multi launch per optimizer step."""
+    if conv_w.dtype == torch.float32 and conv_w.is_contiguous() and conv_w.shape[1:] == (1, 7, 7):
+        return _weight_prep(conv_w, 1, None, torch.float32)
+
     def build():
         lib = L.load()
         C = conv_w.shape[0]

@@ -1,3 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dwconv_ln_gpu.py tests/test_patchify_gpu.py tests/test_block_gpu.py -x -q 2>&1 | tail -n 4
-for v in 1 0; do echo "== CNX_LN_V3=$v"; CNX_LN_V3=$v timeout 300 python profiles/kbench.py --only lnf --iters 3 2>&1 | grep ln_; done
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 5
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench10.json 2> gpurun_out/bench10.err; echo "bench rc=$?"; tail -3 gpurun_out/bench10.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench10.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['clocks'], d['variants'], d['gpu_launches'])
+PY
