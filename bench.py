@@ -47,13 +47,15 @@ def parse():
     ap.add_argument("--acc-autocast", action="store_true",
                     help="headline with the accuracy forward under bf16 autocast instead of fp32 outside autocast, where the "
                          "reference puts it (engine.py:89-97); by default that variant is only reported under `variants`")
+    ap.add_argument("--no-amp", action="store_true",
+                    help="fp32 everywhere (the reference's --use_amp false default) instead of the headline's bf16 autocast")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra timed region of the `variants` key")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"{a.model} {a.img}x{a.img} bf16 autocast, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
+    return (f"{a.model} {a.img}x{a.img} {'fp32 (no autocast)' if getattr(a, 'no_amp', False) else 'bf16 autocast'}, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
             f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward "
             f"{'under the same bf16 autocast' if getattr(a, 'acc_autocast', False) else 'in fp32 outside autocast as the reference places it'}"
             f" (engine.py:27-97)")
@@ -269,7 +271,7 @@ def run_ours(a):
     def epoch(batches):
         if a.no_acc_forward:
             return _fast_epoch(batches)
-        return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=True,
+        return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=not a.no_amp,
                                        num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch,
                                        acc_forward_fp32=acc_fp32[0])
 
@@ -314,7 +316,7 @@ def run_ours(a):
         launches = L.gpu_launches() - c0
         ms_e2e, _ = timed(host, a.steps)
         variants = None
-        if not a.no_variants and not a.no_acc_forward:
+        if not a.no_variants and not a.no_acc_forward and not a.no_amp:
             # the same step with the accuracy forward on the other side of the autocast boundary (see engine.py docstring)
             acc_fp32[0] = not acc_fp32[0]
             timed(devb, 3)
@@ -378,7 +380,7 @@ def run_ours(a):
     out = {
         "metric": METRIC, "value": round(imgs / (ms_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms_dev / a.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (randn images, random labels; random-init weights)",
+        "vs_baseline": None, "dtype": "f32" if a.no_amp else "bf16", "data": "synthetic (randn images, random labels; random-init weights)",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "params": n_params, "optimizer": "torch.optim.AdamW" if a.torch_adamw else "libcnx fused AdamW+EMA",
                    "l2": "activation footprint per step >> 126 MB L2 (inputs larger than L2, no explicit flush)",
