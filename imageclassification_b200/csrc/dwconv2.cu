@@ -592,8 +592,6 @@ int dwconv7_wgrad_v2(const void* dy, int dy_dtype, const void* x, int x_dtype, i
   return CNX_E_BADARG;
 }
 
-namespace dw2 {
-}  // namespace dw2
 
 // entry points used by the extern "C" layer in dwconv.cu
 int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* bias, const float* ln_w, const float* ln_b,

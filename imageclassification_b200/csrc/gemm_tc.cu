@@ -1678,8 +1678,6 @@ int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void
   return CNX_E_SHAPE;
 }
 
-namespace tc_unused {
-}  // namespace tc_unused
 
 template <int KIND, typename TOUT>
 int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
