@@ -72,6 +72,8 @@ SIGNATURES = {
     "cnx_weight_prep_multi": (c_int, [_P, _I, _L, _P]),
     "cnx_layerscale_finalize": (c_int, [_P, _P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P]),
     "cnx_cast_f32_to_bf16": (c_int, [_P, _L, _P, _P]),
+    "cnx_avgpool_nhwc_fwd": (c_int, [_P, _I, _L, _L, _L, _P, _P]),
+    "cnx_avgpool_nhwc_bwd": (c_int, [_P, _L, _L, _L, _P, _I, _P]),
     "cnx_patchify4_nchw": (c_int, [_P, _L, _L, _L, _L, _P, _I, _P]),
     "cnx_patch2": (c_int, [_P, _I, _L, _L, _L, _L, _P, _I, _P]),
     "cnx_ln_fwd_patch2": (c_int, [_P, _I, _P, _P, _F, _L, _L, _L, _L, _P, _I, _P, _P, _P]),
@@ -87,7 +89,7 @@ KERNELS_PER_CALL = {
     "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_dwconv7_weight_prep": 1, "cnx_gemm_bias_gelu_fwd": 1,
     "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2,
     "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_weight_prep_multi": 1, "cnx_mlp_fused_fwd": 1, "cnx_split3": 1, "cnx_dwconv7_ln_fwd_x3": 1, "cnx_gemm_bias_gelu_fwd_x3": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,
-    "cnx_patchify4_nchw": 1, "cnx_patch2": 1, "cnx_ln_fwd_patch2": 1, "cnx_ln_bwd_patch2": 1,
+    "cnx_avgpool_nhwc_fwd": 1, "cnx_avgpool_nhwc_bwd": 1, "cnx_patchify4_nchw": 1, "cnx_patch2": 1, "cnx_ln_fwd_patch2": 1, "cnx_ln_bwd_patch2": 1,
 }
 CALL_COUNTS = {k: 0 for k in KERNELS_PER_CALL}
 

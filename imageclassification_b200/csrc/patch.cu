@@ -45,6 +45,46 @@ __global__ void __launch_bounds__(256) patch2_kernel(const uint4* __restrict__ i
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// head: global average pool over the H*W pixels of a channels-last map (timm SelectAdaptivePool2d('avg'), the first op of
+// NormMlpClassifierHead) and its backward.  One thread per (sample, 4 channels): the HW rows of a sample are read with
+// coalesced 16-byte (fp32) / 8-byte (bf16) vectors, fp32 accumulation in pixel order (deterministic).
+// ------------------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const TX* __restrict__ x, int64_t N, int HW, int C, float* __restrict__ out) {
+  const int c4 = C >> 2;
+  const int64_t total = N * c4;
+  const float inv = 1.0f / (float)HW;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t n = i / c4;
+    const int c = (int)(i - n * c4) * 4;
+    const TX* p = x + n * HW * C + c;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < HW; ++r) {
+      float v[4];
+      load4(p + (int64_t)r * C, v);
+      a[0] += v[0]; a[1] += v[1]; a[2] += v[2]; a[3] += v[3];
+    }
+    a[0] *= inv; a[1] *= inv; a[2] *= inv; a[3] *= inv;
+    store4(out + n * C + c, a);
+  }
+}
+template <typename TX>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, int64_t N, int HW, int C, TX* __restrict__ dx) {
+  const int c4 = C >> 2;
+  const int64_t total = N * HW * c4;
+  const float inv = 1.0f / (float)HW;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / c4;
+    const int c = (int)(i - m * c4) * 4;
+    const int64_t n = m / HW;
+    float v[4];
+    load4(dout + n * C + c, v);
+    v[0] *= inv; v[1] *= inv; v[2] *= inv; v[3] *= inv;
+    store4(dx + m * C + c, v);
+  }
+}
+
 }  // namespace cnx
 
 using namespace cnx;
@@ -81,6 +121,28 @@ int cnx_patch2(const void* in, int dtype, int64_t N, int64_t H, int64_t W, int64
   patch2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (int)N, (int)H, (int)W, vpc, (uint4*)out,
                                                                      gather);
   return check_launch("patch2");
+}
+
+int cnx_avgpool_nhwc_fwd(const void* x, int x_dtype, int64_t N, int64_t HW, int64_t C, float* out, void* stream) {
+  CNX_REQUIRE(x && out && N > 0 && HW > 0 && C > 0 && dtype_ok(x_dtype), CNX_E_BADARG, "avgpool_fwd: bad argument");
+  CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "avgpool_fwd: C=%lld must be a multiple of 4", (long long)C);
+  int64_t blocks = (N * (C / 4) + 255) / 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == CNX_F32) avgpool_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, N, (int)HW, (int)C, out);
+  else avgpool_fwd_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>((const bf16*)x, N, (int)HW, (int)C, out);
+  return check_launch("avgpool_fwd");
+}
+
+int cnx_avgpool_nhwc_bwd(const float* dout, int64_t N, int64_t HW, int64_t C, void* dx, int dx_dtype, void* stream) {
+  CNX_REQUIRE(dout && dx && N > 0 && HW > 0 && C > 0 && dtype_ok(dx_dtype), CNX_E_BADARG, "avgpool_bwd: bad argument");
+  CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "avgpool_bwd: C=%lld must be a multiple of 4", (long long)C);
+  int64_t blocks = (N * HW * (C / 4) + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dx_dtype == CNX_F32) avgpool_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(dout, N, (int)HW, (int)C, (float*)dx);
+  else avgpool_bwd_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(dout, N, (int)HW, (int)C, (bf16*)dx);
+  return check_launch("avgpool_bwd");
 }
 
 }  // extern "C"

@@ -143,6 +143,10 @@ class NormMlpClassifierHead(nn.Module):
         self.fc = nn.Linear(in_features, num_classes) if num_classes > 0 else nn.Identity()
 
     def forward(self, x, pre_logits: bool = False):
+        if (not pre_logits and isinstance(self.fc, nn.Linear) and self.fc.bias is not None and ops.head_supported(x, self.fc.weight)
+                and not (self.training and self.drop.p > 0)):
+            # pool -> LayerNorm -> fc on the libcnx kernels; other shapes (e.g. 2 classes) use the ATen modules
+            return ops.head_forward(x, self.norm.weight, self.norm.bias, self.fc.weight, self.fc.bias, self.norm.eps)
         x = self.global_pool(x)
         x = self.norm(x)
         x = self.flatten(x)

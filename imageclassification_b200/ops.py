@@ -541,6 +541,66 @@ def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float):
     return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype(), torch.is_grad_enabled())
 
 
+class _HeadFn(torch.autograd.Function):
+    """timm NormMlpClassifierHead (global avg pool -> LayerNorm2d -> flatten -> fc) on libcnx kernels: cnx_avgpool_nhwc,
+    cnx_ln_fwd / cnx_ln_bwd on the [N, C] rows, fc as the tcgen05 GEMM (bf16 autocast) with its wgrad + bias column sums.
+    dtypes follow ATen's autocast policies: pooled and normalised features fp32, logits in the autocast dtype."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, fc_w, fc_b, eps, act_dtype, track):
+        lib = L.load()
+        L.require_cuda(x, ln_w, fc_w)
+        N, C, H, W = x.shape
+        K = fc_w.shape[0]
+        xl = _nhwc(x.detach())
+        pooled = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        L.check(lib.cnx_avgpool_nhwc_fwd(L.ptr(xl), L.dt(xl), N, H * W, C, L.ptr(pooled), L.stream()), "avgpool_fwd")
+        xn, mean, rstd = _ln_fwd(pooled, ln_w, ln_b, eps, act_dtype)      # fp32 LayerNorm, rounded once to the GEMM operand dtype
+        if act_dtype == torch.float32:
+            if not track and X3_FWD and C % 8 == 0:
+                logits = _gemm_plain_x3(xn, fc_w, False, fc_b)
+            else:
+                logits = _gemm_plain(xn, fc_w, fc_b, torch.float32)
+        else:
+            logits = _gemm_plain(xn, _weight_prep(fc_w, 0, None, act_dtype), fc_b, act_dtype)
+        if track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5])):
+            ctx.save_for_backward(pooled, xn, mean, rstd, ln_w, fc_w)
+            ctx.meta = (N, C, H, W, xl.dtype, act_dtype)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = L.load()
+        pooled, xn, mean, rstd, ln_w, fc_w = ctx.saved_tensors
+        N, C, H, W, sdt, act_dtype = ctx.meta
+        K = fc_w.shape[0]
+        d = dlogits.contiguous()
+        if d.dtype != act_dtype:
+            d = d.to(act_dtype)
+        # d xn = d logits . W   (B operand = W^T [C, K]);  dW = d logits^T . xn, db = column sums of d logits
+        wt = _weight_prep(fc_w, 1, None, act_dtype) if act_dtype != torch.float32 else _derived(
+            (fc_w,), ("fcT",), lambda: fc_w.detach().t().contiguous())
+        dxn = _gemm_plain(d, wt, None, act_dtype)
+        dW, db = _wgrad(d, xn, N, K, C, True)
+        dpooled, dlw, dlb = _ln_bwd(dxn, pooled, mean, rstd, ln_w, torch.float32)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxl = torch.empty((N, H, W, C), dtype=sdt, device=d.device)
+            L.check(lib.cnx_avgpool_nhwc_bwd(L.ptr(dpooled), N, H * W, C, L.ptr(dxl), L.dt(sdt), L.stream()), "avgpool_bwd")
+            dx = dxl.permute(0, 3, 1, 2)
+        return dx, dlw, dlb, dW, db, None, None, None
+
+
+def head_forward(x, ln_w, ln_b, fc_w, fc_b, eps: float):
+    """NormMlpClassifierHead forward on a logical [N,C,H,W] stream -> logits [N,K]."""
+    return _HeadFn.apply(x, ln_w, ln_b, fc_w, fc_b, float(eps), _act_dtype(), torch.is_grad_enabled())
+
+
+def head_supported(x, fc_w) -> bool:
+    """shapes the kernels take: C a multiple of 8 (16-byte bf16 rows), K a multiple of 8 (GEMM N / wgrad N1)"""
+    return x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and fc_w.shape[0] % 8 == 0 and x.dtype in (torch.float32, torch.bfloat16)
+
+
 def mixup_batch(x: torch.Tensor, lam: float, box=None, original_out: torch.Tensor | None = None) -> torch.Tensor:
     """timm Mixup._mix_batch's tensor work on a contiguous fp32 CUDA batch, in place and in one pass (bit-exact with the
     flip / mul_ / mul_ / add_ sequence): `box=(yl, yh, xl, xh)` selects the cutmix box swap.  `original_out`, when given,

@@ -265,6 +265,12 @@ CNX_API int cnx_patch2(const void* in, int dtype, int64_t N, int64_t H, int64_t 
 /* Elementwise fp32 -> bf16 cast of a flat buffer (parameter shadow copies). */
 CNX_API int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream);
 
+/* head  timm NormMlpClassifierHead.global_pool (SelectAdaptivePool2d 'avg') on a channels-last [N, HW, C] map and its backward:
+ *   out[n,c] = mean_hw x[n,hw,c] (fp32);   dx[n,hw,c] = dout[n,c] / HW.   The head's LayerNorm2d and fc then run on the
+ *   cnx_ln_fwd / cnx_ln_bwd and cnx_gemm_plain / cnx_gemm_wgrad kernels ([N,C] rows). */
+CNX_API int cnx_avgpool_nhwc_fwd(const void* x, int x_dtype, int64_t N, int64_t HW, int64_t C, float* out, void* stream);
+CNX_API int cnx_avgpool_nhwc_bwd(const float* dout, int64_t N, int64_t HW, int64_t C, void* dx, int dx_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

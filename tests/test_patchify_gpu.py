@@ -121,3 +121,39 @@ def test_weight_prep_registry_refreshes_all_in_one_launch():
     for w, o in zip(ws, again):
         assert torch.equal(o, w.t().to(torch.bfloat16))
     assert torch.equal(again[3], (ws[0] * sc[:, None]).t().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,C,H,K", [(8, 768, 7, 1000), (256, 768, 7, 1000), (5, 96, 3, 16), (4, 1536, 12, 1000), (3, 128, 1, 8)])
+def test_head_fwd_bwd(mode, N, C, H, K):
+    """NormMlpClassifierHead (pool -> LayerNorm2d -> fc) on libcnx kernels vs the oracle head: logits, input and all parameter
+    gradients.  K not a multiple of 8 (e.g. the 2-class config) keeps the ATen modules and is covered by the model tests."""
+    from imageclassification_b200 import modules as PM
+    from oracle import convnext as OC
+    torch.manual_seed(N + C + K)
+    o = OC.Head(C, K).to(DEV)
+    p = PM.NormMlpClassifierHead(C, K).to(DEV)
+    with torch.no_grad():
+        o.norm.weight.add_(0.1 * torch.randn_like(o.norm.weight))
+        o.norm.bias.normal_(0, 0.1)
+        o.fc.weight.normal_(0, 0.05)
+        o.fc.bias.normal_(0, 0.1)
+    p.load_state_dict(o.state_dict())
+    x = torch.randn(N, C, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    dout = torch.randn(N, K, device=DEV)
+    res = []
+    for m in (o, p):
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            y = m(xi)
+        y.backward(dout.to(y.dtype))
+        res.append((y, xi.grad, {n: q.grad for n, q in m.named_parameters()}))
+    (yo, dxo, go), (yp, dxp, gp) = res
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert yp.dtype == yo.dtype and yp.shape == yo.shape
+    assert max_rel(yp, yo) <= tol
+    assert max_rel(dxp, dxo) <= tol
+    for n in go:
+        assert max_rel(gp[n], go[n]) <= tol, n
+    with torch.no_grad():                                    # fp32 no-grad: split-operand tensor-core GEMM
+        assert max_rel(p(x), o(x)) <= 1e-4
