@@ -306,6 +306,24 @@ def run_ours(a):
             ms = t.item()
         return ms, stats
 
+    # host->device link check for the e2e leg: one standalone copy of a batch from the pinned buffers (GB/s), and whether the
+    # buffers really are page-locked (a pageable source would make the "non-blocking" copy block the launching thread)
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = torch.empty_like(devb[0][0])
+    scratch.copy_(host[0][0], non_blocking=True)
+    h0.record()
+    scratch.copy_(host[1 % n_host][0], non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = round(host[0][0].numel() * 4 / (h0.elapsed_time(h1) * 1e-3) / 1e9, 1)
+    pinned = all(x.is_pinned() and t.is_pinned() for x, t in host)
+    del scratch
+    if world > 1:                                                  # slowest link / any unpinned buffer over the ranks
+        lt = torch.tensor([h2d_gbps, 1.0 if pinned else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(lt, op=dist.ReduceOp.MIN)
+        h2d_gbps, pinned = round(lt[0].item(), 1), bool(lt[1].item() > 0.5)
+
     # warm-up (both input sources), then the two timed regions
     timed(devb, max(a.warmup, 3))
     timed(host, max(a.warmup, 3))                                 # (first host-fed steps grow the allocator's pools: seen as a 300 ms one-off)
@@ -389,7 +407,7 @@ def run_ours(a):
                    if os.environ.get("CNX_BF16_STREAM", "0") == "1" else "fp32 (reference's autocast type promotion)"},
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / a.steps, 3), "api": "imageclassification_b200.engine.train_one_epoch on pinned host batches (H2D of batch i+1 on a side stream during step i)"},
+                "ms_per_step": round(ms_e2e / a.steps, 3), "host_buffers_pinned": pinned, "h2d_link_GBps": h2d_gbps, "api": "imageclassification_b200.engine.train_one_epoch on pinned host batches (H2D of batch i+1 on a side stream during step i)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "variants": variants, "kernels": table,
     }
     if rank == 0:
