@@ -48,11 +48,14 @@ class DevicePrefetcher:
     side stream before the current batch is handed out, so they overlap the current step's kernels.  Batches that are
     already on the device pass through untouched.
 
-    The copies land in two persistent device buffers per tensor shape (no caching-allocator traffic on the side stream).
+    The copies land in two device buffers per tensor shape; the side stream and the buffers are created once per device and
+    kept for the life of the process (no stream creation, no caching-allocator traffic and no cudaMalloc inside an epoch).
     Ordering: the consumer's stream waits on the copy's event before it touches a batch; before a buffer is overwritten
-    (two batches later) the side stream waits on an event recorded on the consumer's stream when the consumer asked for
-    the following batch, i.e. after all work on the buffer's previous batch was enqueued.  A consumer that keeps a batch
-    beyond the next TWO `next()` calls must clone it."""
+    (two batches later, or by the next epoch) the side stream waits on an event recorded on the consumer's stream when the
+    consumer asked for the following batch, i.e. after all work on the buffer's previous batch was enqueued.  A consumer
+    that keeps a batch beyond the next TWO `next()` calls must clone it."""
+
+    _state = {}                    # device index -> {"stream", "bufs", "released": [event | None, event | None]}
 
     def __init__(self, loader, device):
         self.loader = loader
@@ -61,24 +64,30 @@ class DevicePrefetcher:
     def __len__(self):
         return len(self.loader)
 
+    def _dev_state(self):
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        st = DevicePrefetcher._state.get(idx)
+        if st is None:
+            st = DevicePrefetcher._state[idx] = {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None]}
+        return st
+
     def __iter__(self):
         dev = self.device
         it = iter(self.loader)
-        side = None
-        bufs = {}                  # (slot, which, shape, dtype) -> device tensor
-        released = [None, None]    # per slot: event on the consumer stream after which the slot may be overwritten
+        st = None
         count = 0
 
         def fetch():
-            nonlocal side, count
+            nonlocal st, count
             try:
                 s, t = next(it)
             except StopIteration:
                 return None
             if s.is_cuda and t.is_cuda:
                 return s, t, None, None
-            if side is None:
-                side = torch.cuda.Stream(dev)
+            if st is None:
+                st = self._dev_state()
+            side, bufs, released = st["stream"], st["bufs"], st["released"]
             slot = count & 1
             count += 1
             out = []
@@ -99,20 +108,29 @@ class DevicePrefetcher:
                 ev.record(side)
             return out[0], out[1], ev, slot
 
+        def release(slot):
+            # everything the consumer did with the batch in `slot` is on its stream by now
+            e = torch.cuda.Event()
+            e.record(torch.cuda.current_stream(dev))
+            st["released"][slot] = e
+
         nxt = fetch()
         prev_slot = None
-        while nxt is not None:
-            s, t, ev, slot = nxt
-            cur = torch.cuda.current_stream(dev)
-            if prev_slot is not None:
-                # everything the consumer did with the previous batch is on `cur` by now
-                released[prev_slot] = torch.cuda.Event()
-                released[prev_slot].record(cur)
-            if ev is not None:
-                cur.wait_event(ev)
-            prev_slot = slot
-            nxt = fetch()
-            yield s, t
+        try:
+            while nxt is not None:
+                s, t, ev, slot = nxt
+                if prev_slot is not None:
+                    release(prev_slot)
+                if ev is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev)
+                prev_slot = slot
+                nxt = fetch()
+                yield s, t
+        finally:
+            # the buffers outlive this epoch: the next one must not overwrite them under the last steps of this one
+            if st is not None:
+                for sl in (0, 1):
+                    release(sl)
 
 
 def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loader: Iterable,

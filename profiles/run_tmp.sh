@@ -1,1 +1,1 @@
-for v in 0 1; do echo "== CNX_GEMM_NCTA=$v"; CNX_GEMM_NCTA=$v timeout 300 python profiles/kbench.py --only gemm --stages 2,3 --iters 5 2>&1 | grep -E "fc1|fc2|dgrad|wgrad" | cut -c1-110; done
+for i in 1 2 3 4 5 6; do timeout 600 python bench.py --no-cpu-baseline --no-breakdown --no-variants 2>/dev/null | python profiles/show_bench.py; done
