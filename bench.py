@@ -369,7 +369,17 @@ def run_ours(a):
     # the limiter engages with a transient (one step of 40-190 ms at a fixed position of the run, whichever region was being
     # timed then); W warm-up steps of 35 ms end before it
     extra_warm = 0
-    while time.perf_counter() - t_warm < float(os.environ.get("CNX_BENCH_SETTLE_S", "3.0")) and extra_warm < 120:
+    settle_s = float(os.environ.get("CNX_BENCH_SETTLE_S", "3.0"))
+
+    def settled():
+        el = time.perf_counter() - t_warm
+        if world > 1:                                              # one decision for all ranks (timed() has a barrier)
+            t = torch.tensor([el], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            el = t.item()
+        return el >= settle_s
+
+    while extra_warm < 120 and not settled():
         timed(devb, 4)
         extra_warm += 4                                 # (first host-fed steps grow the allocator's pools: seen as a 300 ms one-off)
     names_top = None
