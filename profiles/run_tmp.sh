@@ -1,2 +1,4 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 5 2>/dev/null | python profiles/show_bench.py
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 20 --warmup 5 --impl reference 2>/dev/null | tail -1 | cut -c1-200
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 3
+timeout 600 python bench.py > gpurun_out/bench13.json 2> gpurun_out/bench13.err; echo "bench rc=$?"; tail -2 gpurun_out/bench13.err
+python profiles/show_bench.py < gpurun_out/bench13.json
