@@ -68,7 +68,12 @@ class DevicePrefetcher:
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         st = DevicePrefetcher._state.get(idx)
         if st is None:
-            st = DevicePrefetcher._state[idx] = {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None]}
+            st = DevicePrefetcher._state[idx] = {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None],
+                                                 "busy": False}
+        if st["busy"]:
+            # a second loader iterated while another one is live on this device (nested loops): private stream and buffers
+            return {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None], "busy": True}
+        st["busy"] = True
         return st
 
     def __iter__(self):
@@ -131,6 +136,7 @@ class DevicePrefetcher:
             if st is not None:
                 for sl in (0, 1):
                     release(sl)
+                st["busy"] = False
 
 
 def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loader: Iterable,

@@ -153,3 +153,19 @@ def test_evaluate_matches_reference_golden_and_oracle():
     sp = PE.evaluate(data, p, DEV, 3, use_amp=True, verbose=False)
     assert abs(sp["loss"] - so["loss"]) <= 2e-2 * abs(so["loss"])
     assert abs(sp["acc1"] - so["acc1"]) <= 100.0 / 21 + 1e-6       # at most one near-tie argmax flip among 21 samples
+
+
+def test_nested_prefetchers_do_not_share_buffers():
+    """Two loaders iterated at the same time on one device (a validation pass inside a training loop): the second one gets its
+    own stream and buffers, so neither sees the other's batches."""
+    g = torch.Generator().manual_seed(4)
+    a = [(torch.randn(4, 3, 8, 8, generator=g), torch.full((4,), i)) for i in range(5)]
+    b = [(torch.randn(4, 3, 8, 8, generator=g), torch.full((4,), 100 + i)) for i in range(3)]
+    seen = []
+    for xa, ta in PE.DevicePrefetcher(a, DEV):
+        inner = [(xb.clone(), tb.clone()) for xb, tb in PE.DevicePrefetcher(b, DEV)]
+        assert [int(t[0]) for _, t in inner] == [100, 101, 102]
+        assert all(torch.equal(x.cpu(), b[i][0]) for i, (x, _) in enumerate(inner))
+        seen.append((xa.clone(), int(ta[0])))
+    assert [t for _, t in seen] == [0, 1, 2, 3, 4]
+    assert all(torch.equal(x.cpu(), a[i][0]) for i, (x, _) in enumerate(seen))
