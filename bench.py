@@ -202,6 +202,12 @@ def kernel_work(name, a):
     if name == "cnx_split3":
         M, C = a[1:3]
         return M * C * (4 + 6), 0, f"split3 C{C}"
+    if name == "cnx_avgpool_nhwc_fwd":
+        N, HW, C = a[2:5]
+        return N * HW * C * es(a[1]) + N * C * 4, 0, f"avgpool_fwd C{C}"
+    if name == "cnx_avgpool_nhwc_bwd":
+        N, HW, C = a[1:4]
+        return N * HW * C * es(a[5]) + N * C * 4, 0, f"avgpool_bwd C{C}"
     if name == "cnx_mixup_batch":
         B, C, H, W = a[2:6]
         return B * C * H * W * 4 * (3 if a[1] else 2), 0, "mixup_batch"
