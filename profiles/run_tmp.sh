@@ -1,5 +1,5 @@
-run() { echo "== $1"; env $1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus 2 --steps 20 --warmup 5 --no-breakdown --no-variants 2>/dev/null | python profiles/show_bench.py; }
-run A=1 29551
-run NCCL_MAX_CTAS=4 29552
-run NCCL_MAX_CTAS=2 29553
-run "NCCL_MAX_CTAS=8 NCCL_ALGO=Ring" 29554
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 1
+timeout 600 python bench.py > gpurun_out/bench14.json 2> gpurun_out/bench14.err; echo "bench rc=$?"; tail -2 gpurun_out/bench14.err
+python profiles/show_bench.py < gpurun_out/bench14.json
