@@ -287,7 +287,7 @@ def run_ours(a):
             return _fast_epoch(batches)
         return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=not a.no_amp,
                                        num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch,
-                                       acc_forward_fp32=acc_fp32[0])
+                                       acc_forward_fp32=acc_fp32[0], tune_gc=os.environ.get("CNX_ENGINE_TUNE_GC", "1") != "0")
 
     def _fast_epoch(batches):
         net.train(True)
@@ -332,7 +332,8 @@ def run_ours(a):
         # measured to stop the launching thread for 40-190 ms at a fixed step of the run (one long host interval, always the
         # same index), which is an artefact of the process's object count, not of the step being measured
         gc.collect()
-        gc.disable()
+        if os.environ.get("CNX_BENCH_KEEP_GC", "0") != "1":         # (=1: leave the collector on, to measure the engine's own handling)
+            gc.disable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

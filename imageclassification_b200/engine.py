@@ -21,11 +21,14 @@ What differs, without changing results:
   * host batches reach the device one step AHEAD: the H2D copy of batch i+1 (engine.py:40-41's `.to(device, non_blocking=True)`)
     is issued on a side stream while step i computes (`DevicePrefetcher`); same tensors, same values, no PCIe time on the
     compute stream.  `prefetch=False` restores the in-line copy.
+  * for the duration of an epoch the cyclic garbage collector is tuned (`tune_gc=True`: live objects frozen, young-generation
+    threshold raised; restored on return) — it cost ~1 ms of a 35 ms step.
   * rich progress bar / tensorboard / wandb plumbing is the caller's business: `log_writer` / `wandb_logger` are
     accepted and fed the same keys, but nothing is imported here.
 """
 from __future__ import annotations
 
+import gc
 import math
 import time
 from typing import Iterable, Optional
@@ -145,7 +148,7 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
                     start_steps: Optional[int] = 0, lr_schedule_values=None, wd_schedule_values=None,
                     num_training_steps_per_epoch: Optional[int] = None, update_freq: Optional[int] = 1,
                     use_amp: bool = False, num_classes: int = 2, verbose: bool = True,
-                    prefetch: bool = True, acc_forward_fp32: bool = True):
+                    prefetch: bool = True, acc_forward_fp32: bool = True, tune_gc: bool = True):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("imageclassification_b200.engine runs on CUDA devices only (no CPU fallback); "
@@ -164,6 +167,29 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
     loss_total, n_updates = 0.0, 0
 
     batches = DevicePrefetcher(data_loader, device) if prefetch else data_loader
+    # Python's cyclic collector was measured to cost ~1 ms of a 35 ms step here (hundreds of young-generation passes per step over
+    # an object graph dominated by long-lived model / optimizer state).  For the duration of the epoch: everything alive now
+    # is frozen out of the collector's reach and the young-generation threshold is raised; both are restored on return.
+    gc_state = None
+    if tune_gc and gc.isenabled():
+        gc_state = gc.get_threshold()
+        gc.collect()
+        gc.freeze()
+        gc.set_threshold(max(gc_state[0], 50_000), gc_state[1], gc_state[2])
+    try:
+        return _train_loop(model, criterion, batches, optimizer, device, loss_scaler, max_norm, model_ema, mixup_fn, log_writer,
+                           wandb_logger, start_steps, lr_schedule_values, wd_schedule_values, num_training_steps_per_epoch,
+                           update_freq, use_amp, num_classes, verbose, acc_forward_fp32, tp, pc, tc, acc_sum, start_time)
+    finally:
+        if gc_state is not None:
+            gc.set_threshold(*gc_state)
+            gc.unfreeze()
+
+
+def _train_loop(model, criterion, batches, optimizer, device, loss_scaler, max_norm, model_ema, mixup_fn, log_writer, wandb_logger,
+                start_steps, lr_schedule_values, wd_schedule_values, num_training_steps_per_epoch, update_freq, use_amp, num_classes,
+                verbose, acc_forward_fp32, tp, pc, tc, acc_sum, start_time):
+    loss_total, n_updates = 0.0, 0
     for data_iter_step, (samples, targets) in enumerate(batches):
         step = data_iter_step // update_freq
         if step >= num_training_steps_per_epoch:

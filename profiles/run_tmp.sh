@@ -1,5 +1,6 @@
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -n 3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 1
-timeout 600 python bench.py > gpurun_out/bench14.json 2> gpurun_out/bench14.err; echo "bench rc=$?"; tail -2 gpurun_out/bench14.err
-python profiles/show_bench.py < gpurun_out/bench14.json
+run() { echo "== $*"; env $* timeout 300 python bench.py --no-cpu-baseline --no-breakdown --no-variants 2>/dev/null | python profiles/show_bench.py | cut -c1-230; }
+run CNX_BENCH_KEEP_GC=1 CNX_ENGINE_TUNE_GC=1
+run CNX_BENCH_KEEP_GC=1 CNX_ENGINE_TUNE_GC=0
+run CNX_BENCH_KEEP_GC=1 CNX_ENGINE_TUNE_GC=1
+run CNX_BENCH_KEEP_GC=1 CNX_ENGINE_TUNE_GC=0
+timeout 300 python -m pytest tests/test_engine_gpu.py -x -q 2>&1 | tail -n 2
