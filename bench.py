@@ -52,6 +52,9 @@ def parse():
                     help="fp32 everywhere (the reference's --use_amp false default) instead of the headline's bf16 autocast")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra timed region of the `variants` key")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
+    ap.add_argument("--kernels-out", default=None,
+                    help="side file for the per-shape kernel table / family table / launch timeline "
+                         "(default gpurun_out/bench_kernels_N<gpus>.json)")
     return ap.parse_args()
 
 
@@ -193,8 +196,10 @@ def kernel_work(name, a):
         e = es(a[8])
         return (M * K + N * K + M * N * (2 if a[6] else 1)) * e, 2 * M * N * K, f"fc1_gelu K{K}"
     if name == "cnx_gemm_bias_gelu_fwd_x3":
+        # fp32-accurate GEMM on split bf16 operands: ALGORITHMIC flops are those of the fp32 product (2MNK); the kernel
+        # executes 3x that on the tensor pipe by design (include/cnx.h "x3")
         M, N, K3 = a[3:6]
-        return (M * K3 + N * K3 + M * 2 * N) * 2, 2 * M * N * K3, f"fc1_gelu_x3 K{K3 // 3}"
+        return (M * K3 + N * K3 + M * 2 * N) * 2, 2 * M * N * (K3 // 3), f"fc1_gelu_x3 K{K3 // 3}"
     if name == "cnx_dwconv7_ln_fwd_x3":
         N, H, W, C = a[6:10]
         MC = N * H * W * C
@@ -214,8 +219,9 @@ def kernel_work(name, a):
     if name == "cnx_gemm_bias_scale_residual_fwd":
         M, N, K = a[9:12]
         e, s = es(a[12]), es(a[8])
-        ka = K * 2 // 3 if (a[13] & 2) else K                      # CNX_GEMM_A_SPLIT2: A holds 2 of the 3 K segments
-        return (M * ka + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
+        if a[13] & 2:                                              # CNX_GEMM_A_SPLIT2 (x3): A holds 2 of the 3 K segments
+            return (M * (K * 2 // 3) + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * (K // 3), f"fc2_scale_res_x3 K{K // 3}"
+        return (M * K + N * K) * e + M * N * s * (2 if a[6] else 1), 2 * M * N * K, f"fc2_scale_res K{K}"
     if name == "cnx_mlp_fused_fwd":
         M, C = a[10:12]
         return M * C * (2 + 4 + 4) + 8 * C * C * 2, 16 * M * C * C, f"mlp_fused_fwd C{C}"
@@ -409,79 +415,187 @@ def run_ours(a):
     clocks = clk.summary()
 
     # per-kernel breakdown pass (untimed for the headline): every C-ABI call bracketed by CUDA events
-    roof, table = None, []
+    roof, table, families, timeline = None, [], [], None
     peaks = _peaks()
-    if not a.no_breakdown and rank == 0 or (not a.no_breakdown and world > 1):
+    if not a.no_breakdown:
         L.TIMER = L.KernelTimer()
         bsteps = 3
+        L.TIMER.mark_base()
         ms_b, _ = timed(devb, bsteps)
         recs = L.TIMER.summary()
+        tl = L.TIMER.timeline()
         L.TIMER = None
-        agg = {}
-        for name, lst in recs.items():
-            for ms, args in lst:
-                by, fl, label = kernel_work(name, args)
-                d = agg.setdefault(label, {"ms": 0.0, "n": 0, "bytes": 0, "flops": 0, "name": name})
-                d["ms"] += ms
-                d["n"] += 1
-                d["bytes"] += by or 0
-                d["flops"] += fl
-        tot = sum(d["ms"] for d in agg.values())
-        for label, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else None
-            tfs = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["flops"] else None
-            table.append({"kernel": label, "calls_per_step": d["n"] / bsteps, "ms_per_step": round(d["ms"] / bsteps, 4),
-                          "share_of_cnx": round(d["ms"] / tot, 4), "GBps": gbs and round(gbs, 1),
-                          "hbm_frac": gbs and round(gbs / peaks["hbm"], 4), "TFLOPs": tfs and round(tfs, 2),
-                          "tensor_frac": tfs and round(tfs / peaks["tensor"], 4)})
-        if table:
-            top = table[0]
-            d = agg[top["kernel"]]
-            hb = (top["hbm_frac"] or 0)
-            tf = (top["tensor_frac"] or 0) if d["name"].startswith("cnx_gemm") else 0
-            if tf > hb:
-                roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": peaks["tensor"], "unit": "TFLOP/s",
-                        "frac": top["tensor_frac"], "traffic": None}
-            else:
-                roof = {"bound": "hbm", "achieved": top["GBps"], "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": top["hbm_frac"], "traffic": None}
-            # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (dram__bytes_read + _write), if listed
-            try:
-                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    tr = json.load(f)
-                if top["kernel"] in tr["kernels"]:
-                    roof["traffic"] = tr["kernels"][top["kernel"]]
-                    roof["traffic_source"] = tr["source"]
-            except Exception:
-                pass
-            roof.update({"kernel": top["kernel"], "launches_per_step": top["calls_per_step"],
-                         "avg_launch_ms": round(d["ms"] / d["n"], 4), "peak_source": peaks["src"] + " (sustained; timed inside the step)",
-                         "cnx_kernels_ms_per_step": round(tot / bsteps, 3), "step_ms_with_events": round(ms_b / bsteps, 3)})
+        table, families, roof = roofline_tables(recs, bsteps, peaks, ms_b)
+        timeline = timeline_summary(tl, bsteps)
 
     imgs = B * world * a.steps
     out = {
         "metric": METRIC, "value": round(imgs / (ms_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms_dev / a.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if a.no_amp else "bf16", "data": "synthetic (randn images, random labels; random-init weights)",
-        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
-                   "params": n_params, "optimizer": "torch.optim.AdamW" if a.torch_adamw else "libcnx fused AdamW+EMA",
-                   "l2": "activation footprint per step >> 126 MB L2 (inputs larger than L2, no explicit flush)",
-                   "final_loss": stats.get("loss"),
-                   "settle_warmup_steps": extra_warm,   # untimed steps beyond W until the GPU has been under load for 3 s (see above)
-                   "residual_stream": "bf16 in stages 1-3 (CNX_BF16_STREAM=1, not the reference's promotion)"
-                   if os.environ.get("CNX_BF16_STREAM", "0") == "1" else "fp32 (reference's autocast type promotion)"},
+        "config": config_dict(a, world),
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
                 "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e / a.steps, 3), "host_buffers_pinned": pinned, "h2d_link_GBps": h2d_gbps, "host_step_interval_ms": host_iv, "api": "imageclassification_b200.engine.train_one_epoch on pinned host batches (H2D of batch i+1 on a side stream during step i)"},
-        "host_step_interval_ms": dev_iv, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "variants": variants, "kernels": table,
+                "ms_per_step": round(ms_e2e / a.steps, 3), "host_buffers_pinned": pinned, "h2d_link_GBps": h2d_gbps,
+                "api": "engine.train_one_epoch on pinned host batches"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "families": families,
+        "run": {"params": n_params, "final_loss": stats.get("loss"), "settle_warmup_steps": extra_warm,
+                "optimizer": "torch.optim.AdamW" if a.torch_adamw else "libcnx fused AdamW+EMA",
+                "residual_stream": "bf16 stages 1-3 (CNX_BF16_STREAM=1)" if os.environ.get("CNX_BF16_STREAM", "0") == "1" else "fp32 (reference promotion)",
+                "host_step_interval_ms": {"resident": dev_iv, "e2e": host_iv}},
+        "variants": variants,
     }
     if rank == 0:
         if not a.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_step_rate(a, steps=2, warmup=1)
-        print(json.dumps(out))
+        # the full per-shape kernel table, the per-family table and the launch timeline go to a side file: the JSON line stays
+        # small enough for any log tail (round 1's 20 KB line was cut by the driver's tail and did not parse)
+        side = a.kernels_out or os.path.join(ROOT, "gpurun_out", f"bench_kernels_N{world}.json")
+        try:
+            os.makedirs(os.path.dirname(side), exist_ok=True)
+            with open(side, "w") as f:
+                json.dump({"line": out, "kernels": table, "families_all": families_all(table), "timeline": timeline}, f, indent=1)
+            out["kernels_file"] = os.path.relpath(side, ROOT)
+        except OSError as e:
+            out["kernels_file"] = f"not written: {e}"
+        line = json.dumps(out, separators=(",", ":"))
+        if len(line) > 3900:                                       # never let optional detail endanger the contract keys
+            for k in ("variants", "run", "families"):
+                out.pop(k, None)
+                line = json.dumps(out, separators=(",", ":"))
+                if len(line) <= 3900:
+                    break
+        print(line, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config_dict(a, world):
+    """`config` of the JSON line: identical for this arm and for `--impl reference` (the driver compares them)."""
+    return {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": f"dp{world}",
+            "l2": "per-step activation footprint >> 126 MB L2 (inputs larger than L2, no explicit flush)"}
+
+
+_NOT_TRAINING = ("_x3", "split3")          # the reference's fp32 accuracy forward (engine.py:89-97): in the step, not in fwd+bwd
+
+
+def _family(label):
+    return label.split(" ")[0]
+
+
+def roofline_tables(recs, bsteps, peaks, ms_b):
+    """per-shape table, per-family table and the `roofline` object (dominant training-path kernel family: all launches of
+    one kernel entry point over all its shapes; achieved = total algorithmic bytes or flops / total CUDA-event time)."""
+    agg = {}
+    for name, lst in recs.items():
+        for ms, args in lst:
+            by, fl, label = kernel_work(name, args)
+            d = agg.setdefault(label, {"ms": 0.0, "n": 0, "bytes": 0, "flops": 0, "name": name})
+            d["ms"] += ms
+            d["n"] += 1
+            d["bytes"] += by or 0
+            d["flops"] += fl
+    tot = sum(d["ms"] for d in agg.values())
+    table = []
+    for label, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else None
+        tfs = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["flops"] else None
+        is_gemm = d["name"].startswith("cnx_gemm") or d["name"].startswith("cnx_mlp")
+        # time the launch would take at the roof that bounds it (max of the HBM time and, for GEMMs, the tensor time)
+        roof_ms = max(d["bytes"] / (peaks["hbm"] * 1e9), (d["flops"] / (peaks["tensor"] * 1e12)) if is_gemm else 0.0) * 1e3
+        table.append({"kernel": label, "family": _family(label), "calls_per_step": d["n"] / bsteps,
+                      "ms_per_step": round(d["ms"] / bsteps, 4), "share_of_cnx": round(d["ms"] / tot, 4),
+                      "bytes_per_launch": d["bytes"] // max(d["n"], 1), "flops_per_launch": d["flops"] // max(d["n"], 1),
+                      "GBps": gbs and round(gbs, 1), "hbm_frac": gbs and round(gbs / peaks["hbm"], 4),
+                      "TFLOPs": tfs and round(tfs, 2), "tensor_frac": (tfs and round(tfs / peaks["tensor"], 4)) if is_gemm else None,
+                      "roof_ms_per_step": round(roof_ms / bsteps, 4), "gemm": is_gemm})
+    fams = families_all(table)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+    except Exception:
+        tr = {"kernels": {}, "source": None}
+    roof = None
+    train = [f for f in fams if not any(t in f["family"] for t in _NOT_TRAINING) and f["frac"] is not None]
+    if train:
+        top = train[0]
+        rows = [r for r in table if r["family"] == top["family"]]
+        n = sum(r["calls_per_step"] for r in rows)
+        ms = sum(r["ms_per_step"] for r in rows)
+        if top["bound"] == "tensor":
+            ach = sum(r["flops_per_launch"] * r["calls_per_step"] for r in rows) / (ms * 1e-3) / 1e12
+            peak, unit = peaks["tensor"], "TFLOP/s"
+        else:
+            ach = sum(r["bytes_per_launch"] * r["calls_per_step"] for r in rows) / (ms * 1e-3) / 1e9
+            peak, unit = peaks["hbm"], "GB/s"
+        # DRAM bytes per launch (read + write) from the committed `ncu --set full` capture, launch-weighted over the family's shapes
+        known = [r for r in rows if r["kernel"] in tr["kernels"]]
+        traffic = None
+        if known and sum(r["calls_per_step"] for r in known) >= 0.5 * n:
+            traffic = round(sum(tr["kernels"][r["kernel"]] * r["calls_per_step"] for r in known) / sum(r["calls_per_step"] for r in known))
+        roof = {"bound": top["bound"], "achieved": round(ach, 1), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+                "traffic": traffic, "kernel": top["family"], "launches_per_step": n, "avg_launch_ms": round(ms / n, 4),
+                "ms_per_step": round(ms, 3), "share_of_step_kernels": top["share"], "roof_time_frac": top["roof_time_frac"],
+                "algorithmic_bytes_per_launch": round(sum(r["bytes_per_launch"] * r["calls_per_step"] for r in rows) / n),
+                "traffic_source": tr.get("source") if traffic else None,
+                "peak_source": peaks["src"] + " MEASURED_PEAKS.json, sustained (timed inside the step)",
+                "how": "all launches of the family over its shapes: sum of algorithmic work / sum of CUDA-event time",
+                "cnx_kernels_ms_per_step": round(tot / bsteps, 3), "step_ms_with_events": round(ms_b / bsteps, 3)}
+    compact = [{k: f[k] for k in ("family", "ms", "share", "bound", "frac")} for f in fams[:12]]
+    return table, compact, roof
+
+
+def families_all(table):
+    """Aggregate the per-shape rows by kernel family.  frac = achieved / peak on the family's dominant roof (the one with the
+    larger share of roof time); roof_time_frac = sum over shapes of the time at the bounding roof / measured time."""
+    fam = {}
+    tot = sum(r["ms_per_step"] for r in table) or 1.0
+    for r in table:
+        f = fam.setdefault(r["family"], {"ms": 0.0, "n": 0.0, "bytes": 0.0, "flops": 0.0, "roof_ms": 0.0, "gemm": r["gemm"],
+                                         "t_hbm": 0.0, "t_tensor": 0.0})
+        f["ms"] += r["ms_per_step"]
+        f["n"] += r["calls_per_step"]
+        f["bytes"] += r["bytes_per_launch"] * r["calls_per_step"]
+        f["flops"] += r["flops_per_launch"] * r["calls_per_step"]
+        f["roof_ms"] += r["roof_ms_per_step"]
+    peaks = _peaks()
+    out = []
+    for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        hb = f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peaks["hbm"] if f["bytes"] and f["ms"] else None
+        tf = f["flops"] / (f["ms"] * 1e-3) / 1e12 / peaks["tensor"] if (f["flops"] and f["gemm"] and f["ms"]) else None
+        if hb is None and tf is None:
+            bound, frac = None, None
+        elif tf is not None and tf > (hb or 0):
+            bound, frac = "tensor", round(tf, 4)
+        else:
+            bound, frac = "hbm", round(hb, 4)
+        out.append({"family": name, "ms": round(f["ms"], 3), "launches": f["n"], "share": round(f["ms"] / tot, 4), "bound": bound,
+                    "frac": frac, "hbm_frac": hb and round(hb, 4), "tensor_frac": tf and round(tf, 4),
+                    "roof_time_frac": round(f["roof_ms"] / f["ms"], 4) if f["ms"] and f["roof_ms"] else None})
+    return out
+
+
+def timeline_summary(tl, bsteps):
+    """From (name, host issue, gpu start, gpu end) per C-ABI call: how much of the pass the GPU spent inside libcnx kernels, in
+    the gaps between them (ATen kernels + idle), and how many calls found the GPU waiting for the launching thread."""
+    if not tl:
+        return None
+    starved = [r for r in tl if r[2] - r[1] < 0.03]                  # kernel started < 30 us after the host issued it
+    busy = sum(r[3] - r[2] for r in tl)
+    gaps = [(tl[i][2] - tl[i - 1][3], tl[i][0], tl[i - 1][0]) for i in range(1, len(tl))]
+    span = tl[-1][3] - tl[0][2]
+    big = sorted(gaps, key=lambda g: -g[0])[:8]
+    lead = [r[2] - r[1] for r in tl]
+    by_name = {}
+    for r in starved:
+        by_name[r[0]] = by_name.get(r[0], 0) + 1
+    return {"calls": len(tl), "span_ms_per_step": round(span / bsteps, 3), "cnx_busy_ms_per_step": round(busy / bsteps, 3),
+            "gap_ms_per_step": round(sum(g[0] for g in gaps) / bsteps, 3),
+            "starved_calls_per_step": round(len(starved) / bsteps, 1), "starved_by_call": by_name,
+            "queue_lead_ms": {"median": round(sorted(lead)[len(lead) // 2], 3), "min": round(min(lead), 3), "max": round(max(lead), 3)},
+            "largest_gaps_ms": [{"gap": round(g[0], 3), "before": g[1], "after": g[2]} for g in big],
+            "rows": [[r[0], round(r[1], 3), round(r[2], 3), round(r[3], 3)] for r in tl[:len(tl) // bsteps]]}
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU baseline
@@ -518,21 +632,22 @@ def cpu_step_rate(a, steps, warmup):
 
 
 def run_reference(a):
+    """The reference arm: the reference's own CPU implementation of the step (oracle port of engine.py:27-97; the reference
+    itself cannot be installed: no setup.py, needs timm) on all host cores, EXACTLY --steps timed after --warmup untimed steps,
+    each step a bounded sample (batch --cpu-sample-batch) of this arm's workload.  Same `config`, metric and unit as ours."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    steps = max(1, min(a.steps, 3))
-    warm = 1 if a.warmup > 0 else 0
-    cb = cpu_step_rate(a, steps=steps, warmup=warm)
-    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-           "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    cb = cpu_step_rate(a, steps=max(1, a.steps), warmup=max(0, a.warmup))
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
+           "warmup": max(0, a.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic (randn images, random labels; random-init weights)",
-           "config": {"workload": workload_name(a), "note": "reference train.py CPU path: the reference cannot be installed "
-                      "(timm absent, no network); oracle port of engine.py's step on the host cores; each step is a bounded "
-                      f"sample of batch {a.cpu_sample_batch}; steps capped at 3 to bound the run"},
+           "config": config_dict(a, max(1, a.gpus)),
+           "note": "reference train.py CPU path (fp32: CUDA autocast does not apply on CPU); not installable (timm absent, no "
+                   "network) -> oracle port of engine.py's step on the host cores; img/s = sample batch / step time",
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    print(json.dumps(out, separators=(",", ":")), flush=True)
 
 
 if __name__ == "__main__":

@@ -6,8 +6,10 @@ from .ema import ModelEmaV3, get_state_dict
 from .loss import SoftTargetCrossEntropy
 from .mixup import Mixup, mixup_target
 from .modules import ConvNeXt, ConvNeXtBlock, LayerNorm, LayerNorm2d, create_model, list_models
+from .utils import NativeScaler, NativeScalerWithGradNormCount, clip_grad_norm_, get_grad_norm_
 
 ModelEma = ModelEmaV3
 
 __all__ = ["ConvNeXt", "ConvNeXtBlock", "LayerNorm", "LayerNorm2d", "create_model", "list_models",
-           "SoftTargetCrossEntropy", "ModelEmaV3", "ModelEma", "get_state_dict", "Mixup", "mixup_target"]
+           "SoftTargetCrossEntropy", "ModelEmaV3", "ModelEma", "get_state_dict", "Mixup", "mixup_target",
+           "NativeScaler", "NativeScalerWithGradNormCount", "clip_grad_norm_", "get_grad_norm_"]

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint, c_void_p
 
 import torch
@@ -44,7 +45,9 @@ SIGNATURES = {
     "cnx_last_error_string": (c_char_p, []),
     "cnx_sm_count": (c_int, []),
     "cnx_ema_lerp_multi": (c_int, [_P, _I, _L, _F, _P]),
-    "cnx_adamw_ema_multi": (c_int, [_P, _I, _L, _F, _F, _F, _F, _F, _F, _F, _F, _P]),
+    "cnx_adamw_ema_multi": (c_int, [_P, _I, _L, _D, _D, _D, _D, _D, _D, _D, _F, _P]),
+    "cnx_grad_sumsq_multi": (c_int, [_P, _I, _L, _P, _F, _P, _P]),
+    "cnx_scale_multi": (c_int, [_P, _I, _L, _P, _P]),
     "cnx_soft_target_ce_fwd": (c_int, [_P, _I, _P, _L, _L, _P, _P, _P, _P, _P]),
     "cnx_soft_target_ce_bwd": (c_int, [_P, _I, _P, _P, _P, _L, _L, _P, _I, _P]),
     "cnx_mixup_target": (c_int, [_P, _L, _L, _D, _D, _P, _P]),
@@ -84,7 +87,7 @@ SIGNATURES = {
 # C-ABI calls that launch kernels, and how many kernels one call launches (for bench.py's `gpu_launches`;
 # cnx_gemm_wgrad launches the GEMM + one partial reduction, + one more when the bias gradient is requested).
 KERNELS_PER_CALL = {
-    "cnx_ema_lerp_multi": 1, "cnx_adamw_ema_multi": 1, "cnx_soft_target_ce_fwd": 1, "cnx_soft_target_ce_bwd": 1,
+    "cnx_ema_lerp_multi": 1, "cnx_adamw_ema_multi": 1, "cnx_grad_sumsq_multi": 2, "cnx_scale_multi": 1, "cnx_soft_target_ce_fwd": 1, "cnx_soft_target_ce_bwd": 1,
     "cnx_mixup_target": 1, "cnx_mixup_batch": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1,
     "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_dwconv7_weight_prep": 1, "cnx_gemm_bias_gelu_fwd": 1,
     "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2,
@@ -100,13 +103,25 @@ class KernelTimer:
 
     def __init__(self, names=None):
         self.names = set(names) if names is not None else None
-        self.records = []   # (name, start_event, end_event, int args)
+        self.records = []   # (name, start_event, end_event, int args, host issue time)
+        self.base = None    # (event, host time) set by mark_base(): origin of timeline()
+
+    def mark_base(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.base = (ev, time.perf_counter())
 
     def summary(self):
         out = {}
-        for name, s, e, a in self.records:
+        for name, s, e, a, _ in self.records:
             out.setdefault(name, []).append((s.elapsed_time(e), a))
         return out
+
+    def timeline(self):
+        """[(name, host issue ms, gpu start ms, gpu end ms)] relative to mark_base(): `gpu start - host issue` close to zero
+        means the GPU was waiting for the launching thread at that call (host-bound), a large lead means it was queued."""
+        ev0, t0 = self.base
+        return [(name, 1e3 * (th - t0), ev0.elapsed_time(s), ev0.elapsed_time(e)) for name, s, e, _, th in self.records]
 
 
 TIMER: KernelTimer | None = None
@@ -118,10 +133,11 @@ def _wrap(name, fn):
         t = TIMER
         if t is not None and (t.names is None or name in t.names):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            th = time.perf_counter()
             s.record()
             rc = fn(*a)
             e.record()
-            t.records.append((name, s, e, a))
+            t.records.append((name, s, e, a, th))
             return rc
         return fn(*a)
     call.__name__ = name
@@ -176,13 +192,27 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None) -> int:
+    """torch's current stream on `device` (default: the current device).  Ops pass their tensors' device and launch under
+    `torch.cuda.device(...)` when it is not the current one."""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
-def require_cuda(*tensors) -> None:
+def require_same_device(*tensors) -> None:
+    """Kernels are launched on the CURRENT device's stream: a tensor living on another CUDA device would be an illegal
+    address inside the kernel, so refuse it here with a clear message."""
+    cur = torch.cuda.current_device()
+    for t in tensors:
+        if t is not None and t.is_cuda and t.device.index != cur:
+            raise RuntimeError(f"imageclassification_b200: tensor on {t.device} but the current CUDA device is cuda:{cur}; "
+                               "call torch.cuda.set_device(...) (train.py:115 does) or wrap the call in torch.cuda.device(...)")
+
+
+def require_cuda(*tensors, same_device: bool = True) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError(
                 "imageclassification_b200 kernels run on CUDA (sm_100a) tensors only; got a tensor on "
                 f"{t.device}. There is no CPU fallback — use oracle/ for CPU reference numbers.")
+    if same_device:
+        require_same_device(*tensors)

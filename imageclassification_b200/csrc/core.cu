@@ -53,6 +53,13 @@ __device__ __forceinline__ int find_tensor(const Entry* __restrict__ table, int 
   return lo;
 }
 
+// ATen lerp (aten/src/ATen/native/Lerp.h): self + w*diff for |w| < 0.5, end - diff*(1-w) otherwise; nvcc contracts both
+// into one FMA, which is what the explicit fmaf calls below state.
+__device__ __forceinline__ float lerp_aten(float self, float end, float w, float one_minus_w, bool small_w) {
+  float diff = end - self;
+  return small_w ? fmaf(w, diff, self) : fmaf(-diff, one_minus_w, end);
+}
+
 __global__ void __launch_bounds__(256) ema_lerp_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
                                                               float w) {
   __shared__ cnx_ema_entry ent;
@@ -67,6 +74,8 @@ __global__ void __launch_bounds__(256) ema_lerp_multi_kernel(const cnx_ema_entry
   e += base;
   p += base;
   bool aligned = ((((uintptr_t)e) | ((uintptr_t)p)) & 15) == 0;
+  const bool small_w = fabsf(w) < 0.5f;
+  const float omw = 1.0f - w;
   if (aligned && n == CNX_EMA_CHUNK) {
     // 8192 elements / 256 threads = 8 float4 per thread, all loads issued before any use
     float4 ev[8], pv[8];
@@ -80,26 +89,38 @@ __global__ void __launch_bounds__(256) ema_lerp_multi_kernel(const cnx_ema_entry
     for (int i = 0; i < 8; ++i) {
       int idx = (i * 256 + threadIdx.x);
       float4 r;
-      r.x = fmaf(w, pv[i].x - ev[i].x, ev[i].x);
-      r.y = fmaf(w, pv[i].y - ev[i].y, ev[i].y);
-      r.z = fmaf(w, pv[i].z - ev[i].z, ev[i].z);
-      r.w = fmaf(w, pv[i].w - ev[i].w, ev[i].w);
+      r.x = lerp_aten(ev[i].x, pv[i].x, w, omw, small_w);
+      r.y = lerp_aten(ev[i].y, pv[i].y, w, omw, small_w);
+      r.z = lerp_aten(ev[i].z, pv[i].z, w, omw, small_w);
+      r.w = lerp_aten(ev[i].w, pv[i].w, w, omw, small_w);
       reinterpret_cast<float4*>(e)[idx] = r;
     }
   } else {
     for (int i = threadIdx.x; i < n; i += 256) {
-      float ev = e[i];
-      e[i] = fmaf(w, p[i] - ev, ev);
+      e[i] = lerp_aten(e[i], p[i], w, omw, small_w);
     }
   }
 }
 
-// Fused AdamW (+EMA).  torch.optim.AdamW (single-tensor formulation, torch/optim/adam.py):
-//   p *= 1 - lr*wd ; m = lerp(m, g, 1-b1) ; v = b2*v + (1-b2)*g*g ;
-//   denom = sqrt(v)/bc2_sqrt + eps ; p += -(lr/bc1) * m/denom ; then ema = lerp(ema, p, w).
+// Fused AdamW (+EMA).  torch.optim.AdamW as it runs on CUDA by default (torch/optim/adam.py _multi_tensor_adam: every
+// scalar is formed in double on the host and rounded once to fp32, each foreach op rounds its result):
+//   p *= 1 - lr*wd ; m = lerp(m, g, 1-b1) ; v *= b2 ; v += (1-b2) * (g*g) ;
+//   d = sqrt(v) / sqrt(1-b2^t) + eps ; p += -(lr/(1-b1^t)) * (m/d) ; then ema = lerp(ema, p, w).
+struct AdamScalars {
+  float decay, omb1, b1, beta2, omb2, bc2_sqrt, eps, neg_step, ema_w, ema_omw;
+  int small_omb1, small_ema_w;
+};
+
+__device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamScalars& c) {
+  p = __fmul_rn(p, c.decay);
+  m = lerp_aten(m, g, c.omb1, c.b1, c.small_omb1);
+  v = fmaf(c.omb2, __fmul_rn(g, g), __fmul_rn(v, c.beta2));
+  float denom = __fadd_rn(__fdiv_rn(sqrtf(v), c.bc2_sqrt), c.eps);
+  p = fmaf(c.neg_step, __fdiv_rn(m, denom), p);
+}
+
 __global__ void __launch_bounds__(256) adamw_ema_multi_kernel(const cnx_adamw_entry* __restrict__ table, int n_tensors,
-                                                               float lr, float beta1, float beta2, float eps, float wd,
-                                                               float bc1, float bc2_sqrt, float ema_w) {
+                                                               const AdamScalars c) {
   __shared__ cnx_adamw_entry ent;
   int64_t chunk = blockIdx.x;
   if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
@@ -112,18 +133,126 @@ __global__ void __launch_bounds__(256) adamw_ema_multi_kernel(const cnx_adamw_en
   float* __restrict__ m = (float*)ent.exp_avg + base;
   float* __restrict__ v = (float*)ent.exp_avg_sq + base;
   float* __restrict__ e = ent.ema ? (float*)ent.ema + base : nullptr;
-  const float step_size = lr / bc1;
-  const float decay = 1.0f - lr * wd;
-  const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    float pi = p[i], gi = g[i], mi = m[i], vi = v[i];
-    pi = pi * decay;
-    mi = fmaf(omb1, gi - mi, mi);
-    vi = __fadd_rn(__fmul_rn(vi, beta2), __fmul_rn(__fmul_rn(omb2, gi), gi));
-    float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
-    pi = pi - step_size * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-    if (e) { float ei = e[i]; e[i] = fmaf(ema_w, pi - ei, ei); }
+  bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)e)) & 15) == 0;
+  if (aligned && n == CNX_EMA_CHUNK) {
+    // 8192 elements / 256 threads = 8 float4 per thread per array, in two halves of 4 (all loads of a half in flight at once)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 pv[4], gv[4], mv[4], vv[4], ev[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int idx = (h * 4 + i) * 256 + threadIdx.x;
+        pv[i] = reinterpret_cast<const float4*>(p)[idx];
+        gv[i] = __ldg(reinterpret_cast<const float4*>(g) + idx);
+        mv[i] = reinterpret_cast<const float4*>(m)[idx];
+        vv[i] = reinterpret_cast<const float4*>(v)[idx];
+        if (e) ev[i] = reinterpret_cast<const float4*>(e)[idx];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int idx = (h * 4 + i) * 256 + threadIdx.x;
+        adamw_one(pv[i].x, gv[i].x, mv[i].x, vv[i].x, c);
+        adamw_one(pv[i].y, gv[i].y, mv[i].y, vv[i].y, c);
+        adamw_one(pv[i].z, gv[i].z, mv[i].z, vv[i].z, c);
+        adamw_one(pv[i].w, gv[i].w, mv[i].w, vv[i].w, c);
+        reinterpret_cast<float4*>(p)[idx] = pv[i];
+        reinterpret_cast<float4*>(m)[idx] = mv[i];
+        reinterpret_cast<float4*>(v)[idx] = vv[i];
+        if (e) {
+          float4 r;
+          r.x = lerp_aten(ev[i].x, pv[i].x, c.ema_w, c.ema_omw, c.small_ema_w);
+          r.y = lerp_aten(ev[i].y, pv[i].y, c.ema_w, c.ema_omw, c.small_ema_w);
+          r.z = lerp_aten(ev[i].z, pv[i].z, c.ema_w, c.ema_omw, c.small_ema_w);
+          r.w = lerp_aten(ev[i].w, pv[i].w, c.ema_w, c.ema_omw, c.small_ema_w);
+          reinterpret_cast<float4*>(e)[idx] = r;
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      adamw_one(pi, g[i], mi, vi, c);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      if (e) e[i] = lerp_aten(e[i], pi, c.ema_w, c.ema_omw, c.small_ema_w);
+    }
+  }
+}
+
+// Gradient 2-norm over a pointer table (utils.py:456-468, torch.nn.utils.clip_grad_norm_ at utils.py:440): per-chunk sums of
+// squares, then ONE CTA sums the partials in a fixed order (deterministic) and forms norm and the clip coefficient.
+__global__ void __launch_bounds__(256) grad_sumsq_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
+                                                                float* __restrict__ partial) {
+  __shared__ cnx_ema_entry ent;
+  __shared__ float red[8];
+  int64_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
+  __syncthreads();
+  const float* __restrict__ g = (const float*)ent.ema;
+  int64_t base = (chunk - ent.chunk_start) * (int64_t)CNX_EMA_CHUNK;
+  int64_t rem = ent.numel - base;
+  int n = rem < CNX_EMA_CHUNK ? (int)rem : CNX_EMA_CHUNK;
+  g += base;
+  float acc = 0.f;
+  if ((((uintptr_t)g) & 15) == 0 && n == CNX_EMA_CHUNK) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(g) + i * 256 + threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) acc = fmaf(g[i], g[i], acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    partial[chunk] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* __restrict__ partial, int64_t n, float max_norm,
+                                                                 float* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)partial[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 32; ++i) s += red[i];
+    float norm = (float)sqrt(s);
+    out[0] = norm;
+    out[1] = max_norm > 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
+                                                           const float* __restrict__ coef_p) {
+  __shared__ cnx_ema_entry ent;
+  const float coef = __ldg(coef_p);
+  if (coef == 1.0f) return;                    // torch multiplies by 1.0 here: same values, no traffic
+  int64_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
+  __syncthreads();
+  float* __restrict__ g = (float*)ent.ema;
+  int64_t base = (chunk - ent.chunk_start) * (int64_t)CNX_EMA_CHUNK;
+  int64_t rem = ent.numel - base;
+  int n = rem < CNX_EMA_CHUNK ? (int)rem : CNX_EMA_CHUNK;
+  g += base;
+  if ((((uintptr_t)g) & 15) == 0 && n == CNX_EMA_CHUNK) {
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = reinterpret_cast<const float4*>(g)[i * 256 + threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i].x *= coef; v[i].y *= coef; v[i].z *= coef; v[i].w *= coef;
+      reinterpret_cast<float4*>(g)[i * 256 + threadIdx.x] = v[i];
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += 256) g[i] *= coef;
   }
 }
 
@@ -398,15 +527,44 @@ int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunk
   return check_launch("ema_lerp_multi");
 }
 
-int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float lr, float beta1,
-                        float beta2, float eps, float weight_decay, float bias_correction1,
-                        float bias_correction2_sqrt, float ema_w, void* stream) {
+int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, double bias_correction1,
+                        double bias_correction2_sqrt, float ema_w, void* stream) {
   CNX_REQUIRE(table_dev && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "adamw_ema_multi: empty table");
   CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "adamw_ema_multi: too many chunks");
-  adamw_ema_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>(
-      (const cnx_adamw_entry*)table_dev, n_tensors, lr, beta1, beta2, eps, weight_decay, bias_correction1,
-      bias_correction2_sqrt, ema_w);
+  CNX_REQUIRE(bias_correction1 != 0.0 && bias_correction2_sqrt != 0.0, CNX_E_BADARG, "adamw_ema_multi: zero bias correction");
+  AdamScalars c;
+  c.decay = (float)(1.0 - lr * weight_decay);
+  c.omb1 = (float)(1.0 - beta1);
+  c.b1 = 1.0f - c.omb1;                        // ATen lerp's (1 - weight) in fp32
+  c.small_omb1 = fabsf(c.omb1) < 0.5f;
+  c.beta2 = (float)beta2;
+  c.omb2 = (float)(1.0 - beta2);
+  c.bc2_sqrt = (float)bias_correction2_sqrt;
+  c.eps = (float)eps;
+  c.neg_step = (float)(-(lr / bias_correction1));
+  c.ema_w = ema_w;
+  c.ema_omw = 1.0f - ema_w;
+  c.small_ema_w = fabsf(ema_w) < 0.5f;
+  adamw_ema_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_adamw_entry*)table_dev, n_tensors, c);
   return check_launch("adamw_ema_multi");
+}
+
+int cnx_grad_sumsq_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float* partial, float max_norm,
+                         float* out, void* stream) {
+  CNX_REQUIRE(table_dev && partial && out && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "grad_sumsq_multi: bad argument");
+  CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "grad_sumsq_multi: too many chunks");
+  cudaStream_t s = (cudaStream_t)stream;
+  grad_sumsq_multi_kernel<<<(unsigned)total_chunks, 256, 0, s>>>((const cnx_ema_entry*)table_dev, n_tensors, partial);
+  grad_norm_finish_kernel<<<1, 1024, 0, s>>>(partial, total_chunks, max_norm, out);
+  return check_launch("grad_sumsq_multi");
+}
+
+int cnx_scale_multi(const void* table_dev, int n_tensors, int64_t total_chunks, const float* coef, void* stream) {
+  CNX_REQUIRE(table_dev && coef && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "scale_multi: bad argument");
+  CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "scale_multi: too many chunks");
+  scale_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_ema_entry*)table_dev, n_tensors, coef);
+  return check_launch("scale_multi");
 }
 
 int cnx_soft_target_ce_fwd(const void* x, int x_dtype, const float* t, int64_t B, int64_t K, float* loss,

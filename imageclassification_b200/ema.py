@@ -2,7 +2,8 @@
 device=device)` (train.py:201; val.py:19), `.update(model)` after every optimizer step where `model` may be the DDP
 wrapper (engine.py:68,77), `.module` for evaluation and checkpointing (train.py:276,367; utils.py:551,601), `.set(model)`
 (utils.py:603).  The update of every floating state-dict tensor is ONE libcnx launch over a device-resident pointer
-table, bit-exact with ATen lerp: ema <- fmaf(fp32(1-decay), p - ema, ema)."""
+table (SURVEY.md §8a row a10), bit-exact with ATen lerp on both of its branches: w = fp32(1-decay);
+ema <- fmaf(w, p - ema, ema) for |w| < 0.5, p - (p - ema)*(1 - w) otherwise (e.g. w = 1 while get_decay(step) is 0)."""
 from __future__ import annotations
 
 import ctypes
@@ -90,7 +91,7 @@ class ModelEmaV3(nn.Module):
             e.copy_(m)
         if not fl_e:
             return
-        L.require_cuda(*fl_e)
+        L.require_cuda(*fl_e, same_device=False)        # launched under torch.cuda.device(...) below
         key = tuple((e.data_ptr(), m.data_ptr(), e.numel()) for e, m in zip(fl_e, fl_m))
         if key != self._table_key:
             entries, chunk = [], 0
@@ -107,7 +108,10 @@ class ModelEmaV3(nn.Module):
         lib = L.load()
         with torch.cuda.device(fl_e[0].device):
             L.check(lib.cnx_ema_lerp_multi(L.ptr(self._table), len(key), self._chunks, ctypes.c_float(1.0 - decay),
-                                           L.stream()), "ema_lerp_multi")
+                                           L.stream(fl_e[0].device)), "ema_lerp_multi")
+        # written through raw pointers: bump the version counters so that layouts derived from the EMA weights
+        # (ops._derived / ops._PrepRegistry key on (data_ptr, _version)) are rebuilt before the next forward of `.module`
+        torch.autograd.graph.increment_version(fl_e)
 
     @torch.no_grad()
     def set(self, model):

@@ -14,8 +14,11 @@ GEMMs, include/cnx.h "x3").  `acc_forward_fp32=False` runs it under the same bf1
 cheaper (bench.py reports both), parameters / EMA / loss unaffected, `class_acc` and the TP/FP/FN counts can differ on argmax
 near-ties.
 What differs, without changing results:
-  * `use_amp=True` means bf16 autocast with no GradScaler (the BASELINE north-star precision; the reference's
-    torch.amp.autocast('cuda') defaults to fp16 + scaler).
+  * `use_amp=True` means bf16 autocast (the BASELINE north-star precision; the reference's torch.amp.autocast('cuda')
+    defaults to fp16).  A `loss_scaler` object is driven exactly as engine.py:61-68 drives it (it owns
+    backward, unscale, clip / grad-norm and optimizer.step); bf16 needs no loss scaling, so this package's own
+    `utils.NativeScalerWithGradNormCount` keeps utils.py:427-453's interface without a GradScaler.  With `loss_scaler=None`
+    the step is backward -> (clip when max_norm) -> optimizer.step.  Without AMP nothing clips, as in engine.py:70-77.
   * per-class TP/FP/FN are accumulated ON THE DEVICE with three bincounts per step instead of 3*num_classes
     `.item()` host syncs (engine.py:84-87/93-96), and read back once at the end of the epoch.
   * host batches reach the device one step AHEAD: the H2D copy of batch i+1 (engine.py:40-41's `.to(device, non_blocking=True)`)
@@ -36,12 +39,15 @@ from typing import Iterable, Optional
 import torch
 
 from .mixup import Mixup as _Mixup
+from .utils import clip_grad_norm_
 
 
 def _class_counts(preds, targets, num_classes):
-    """(true_pos, pred_count, target_count) per class as int64 device vectors."""
-    hit = preds[preds == targets]
-    return (torch.bincount(hit, minlength=num_classes)[:num_classes],
+    """(true_pos, pred_count, target_count) per class as int64 device vectors; no host synchronisation (a boolean-mask
+    index would need the hit count on the host): hits are counted as bincount weights — exact in fp32 up to 2^24 per class
+    per batch."""
+    hit = torch.bincount(preds, weights=(preds == targets).to(torch.float32), minlength=num_classes)[:num_classes].to(torch.int64)
+    return (hit,
             torch.bincount(preds, minlength=num_classes)[:num_classes],
             torch.bincount(targets, minlength=num_classes)[:num_classes])
 
@@ -171,18 +177,20 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
     # is frozen out of the collector's reach and the young-generation threshold is raised; both are restored on return.
     gc_state = None
     if tune_gc and gc.isenabled():
-        gc_state = gc.get_threshold()
+        gc_state = (gc.get_threshold(), gc.get_freeze_count() == 0)
         gc.collect()
-        gc.freeze()
-        gc.set_threshold(max(gc_state[0], 50_000), gc_state[1], gc_state[2])
+        if gc_state[1]:                      # objects the host application froze itself stay frozen: only undo our own freeze
+            gc.freeze()
+        gc.set_threshold(max(gc_state[0][0], 50_000), gc_state[0][1], gc_state[0][2])
     try:
         return _train_loop(model, criterion, batches, optimizer, device, loss_scaler, max_norm, model_ema, mixup_fn, log_writer,
                            wandb_logger, start_steps, lr_schedule_values, wd_schedule_values, num_training_steps_per_epoch,
                            update_freq, use_amp, num_classes, verbose, acc_forward_fp32, tp, pc, tc, acc_sum, start_time)
     finally:
         if gc_state is not None:
-            gc.set_threshold(*gc_state)
-            gc.unfreeze()
+            gc.set_threshold(*gc_state[0])
+            if gc_state[1]:
+                gc.unfreeze()
 
 
 def _train_loop(model, criterion, batches, optimizer, device, loss_scaler, max_norm, model_ema, mixup_fn, log_writer, wandb_logger,
@@ -224,15 +232,27 @@ def _train_loop(model, criterion, batches, optimizer, device, loss_scaler, max_n
             continue
 
         loss /= update_freq
-        loss.backward()
         grad_norm = None
-        if (data_iter_step + 1) % update_freq == 0:
-            if max_norm:
-                grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
-            optimizer.step()
-            optimizer.zero_grad()
-            if model_ema is not None:
-                model_ema.update(model)
+        update_grad = (data_iter_step + 1) % update_freq == 0
+        if use_amp and loss_scaler is not None:
+            # engine.py:61-68: backward, unscale, gradient norm / clipping and the optimizer step all belong to the caller's
+            # scaler object (utils.py:427-447; this package's bf16 one is `NativeScalerWithGradNormCount` in utils.py)
+            grad_norm = loss_scaler(loss, optimizer, clip_grad=max_norm, parameters=model.parameters(), create_graph=False,
+                                    update_grad=update_grad)
+            if update_grad:
+                optimizer.zero_grad()
+                if model_ema is not None:
+                    model_ema.update(model)
+        else:
+            # engine.py:70-77 (no AMP: never clips) — and bf16 autocast without a scaler object, where `max_norm` clips
+            loss.backward()
+            if update_grad:
+                if use_amp and max_norm:
+                    grad_norm = clip_grad_norm_(model.parameters(), max_norm)
+                optimizer.step()
+                optimizer.zero_grad()
+                if model_ema is not None:
+                    model_ema.update(model)
 
         with torch.no_grad():
             if mixup_fn is None:

@@ -233,8 +233,13 @@ _ARCHS = {
 }
 
 
+def _supported(name: str) -> bool:
+    return all(d % 32 == 0 for d in _ARCHS[name]["dims"])          # libcnx dwconv kernels work on 32-channel chunks
+
+
 def list_models():
-    return sorted(_ARCHS)
+    """the model names create_model accepts (atto / femto / nano have channel counts that are not multiples of 32)"""
+    return sorted(n for n in _ARCHS if _supported(n))
 
 
 def create_model(model_name: str, pretrained: bool = False, num_classes: int = 1000, drop_path_rate: float = 0.0,
@@ -242,8 +247,7 @@ def create_model(model_name: str, pretrained: bool = False, num_classes: int = 1
     """Drop-in for `timm.models.create_model` as called at train.py:187-194 (convnext_* names only)."""
     if model_name not in _ARCHS:
         raise ValueError(f"unknown model {model_name!r}; imageclassification_b200 provides {list_models()}")
-    dims = _ARCHS[model_name]["dims"]
-    if any(d % 32 for d in dims):
+    if not _supported(model_name):
         raise NotImplementedError(f"{model_name}: libcnx dwconv kernels need channel counts that are multiples of 32")
     if pretrained:
         raise RuntimeError("pretrained weights need network access; load a checkpoint with load_state_dict instead")

@@ -69,6 +69,22 @@ class AdamW(torch.optim.Optimizer):
         self._tables = {}
         object.__setattr__(model_ema, "_fused_optimizer", self)
 
+    # the device pointer tables are caches over (param, grad, exp_avg, exp_avg_sq, ema) addresses: anything that can replace
+    # one of those tensors drops them
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._tables = {}
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+        if not hasattr(self, "_uploader"):
+            self._uploader = _TableUploader()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -80,47 +96,53 @@ class AdamW(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            L.require_cuda(*ps)
+            L.require_cuda(*ps, same_device=False)             # launched under torch.cuda.device(...) below
+            by_step = {}                                           # per-parameter step counts, as torch keeps them
             for p in ps:
                 st = self.state[p]
                 if not st:
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            st0 = self.state[ps[0]]
-            st0["step"] += 1
-            t = st0["step"]
-            for p in ps[1:]:
-                self.state[p]["step"] = t
-            key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
-            cached = self._tables.get(gi)
-            if cached is None or cached[0] != key:
-                entries, chunk = [], 0
-                for p in ps:
-                    if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_contiguous() \
-                            or not p.grad.is_contiguous():
-                        raise TypeError("AdamW: libcnx updates contiguous fp32 parameters and gradients")
-                    st = self.state[p]
-                    e = self._ema_map.get(p)
-                    entries.append(L.AdamWEntry(p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(),
-                                                st["exp_avg_sq"].data_ptr(), e.data_ptr() if e is not None else None,
-                                                p.numel(), chunk))
-                    chunk += (p.numel() + L.CNX_EMA_CHUNK - 1) // L.CNX_EMA_CHUNK
-                arr = (L.AdamWEntry * len(entries))(*entries)
-                table = self._uploader.upload(bytes(arr), ps[0].device)
-                cached = (key, table, chunk, len(entries))
-                self._tables[gi] = cached
-            _, table, chunks, n = cached
+                elif isinstance(st["step"], torch.Tensor):          # a state dict written by torch.optim.AdamW
+                    st["step"] = int(st["step"].item())
+                st["step"] += 1
+                by_step.setdefault(st["step"], []).append(p)
             b1, b2 = group["betas"]
-            bc1 = 1.0 - b1 ** t
-            bc2_sqrt = math.sqrt(1.0 - b2 ** t)
             ema_w = (1.0 - self._ema.get_decay()) if self._ema is not None else 0.0
-            f = ctypes.c_float
-            L.check(lib.cnx_adamw_ema_multi(L.ptr(table), n, chunks, f(group["lr"]), f(b1), f(b2), f(group["eps"]),
-                                            f(group["weight_decay"]), f(bc1), f(bc2_sqrt), f(ema_w), L.stream()),
-                    "adamw_ema_multi")
-            # the kernel wrote the parameters through raw pointers: tell autograd / the derived-weight cache
+            for si, (t, sub) in enumerate(sorted(by_step.items())):
+                # one launch per distinct step count: normally one (every parameter receives a gradient every step)
+                key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr(),
+                             self._ema_map[p].data_ptr() if p in self._ema_map else 0) for p in sub)
+                cached = self._tables.get((gi, si))
+                if cached is None or cached[0] != key:
+                    entries, chunk = [], 0
+                    for p in sub:
+                        st = self.state[p]
+                        for q in (p, p.grad, st["exp_avg"], st["exp_avg_sq"]):
+                            if q.dtype != torch.float32 or not q.is_contiguous() or q.device != p.device:
+                                raise TypeError("AdamW: libcnx updates contiguous fp32 parameters, gradients and moments on one device")
+                        e = self._ema_map.get(p)
+                        entries.append(L.AdamWEntry(p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(),
+                                                    st["exp_avg_sq"].data_ptr(), e.data_ptr() if e is not None else None,
+                                                    p.numel(), chunk))
+                        chunk += (p.numel() + L.CNX_EMA_CHUNK - 1) // L.CNX_EMA_CHUNK
+                    arr = (L.AdamWEntry * len(entries))(*entries)
+                    table = self._uploader.upload(bytes(arr), sub[0].device)
+                    cached = (key, table, chunk, len(entries))
+                    self._tables[(gi, si)] = cached
+                _, table, chunks, n = cached
+                bc1 = 1.0 - b1 ** t
+                bc2_sqrt = math.sqrt(1.0 - b2 ** t)
+                with torch.cuda.device(sub[0].device):
+                    L.check(lib.cnx_adamw_ema_multi(L.ptr(table), n, chunks, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                    float(group["weight_decay"]), bc1, bc2_sqrt, ctypes.c_float(ema_w),
+                                                    L.stream(sub[0].device)), "adamw_ema_multi")
+            # the kernel wrote parameters and EMA tensors through raw pointers: tell autograd / the derived-weight caches
             torch.autograd.graph.increment_version(ps)
+            emas = [self._ema_map[p] for p in ps if p in self._ema_map]
+            if emas:
+                torch.autograd.graph.increment_version(emas)
         if self._ema is not None:
             self._ema._fused_done = True
         return loss

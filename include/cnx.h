@@ -49,7 +49,8 @@ CNX_API int cnx_sm_count(void);
  * a10  ModelEmaV3.update  (engine.py:68,77 -> timm ModelEmaV3.apply_update_ -> torch._foreach_lerp_)
  *   ema <- fmaf(w, p - ema, ema) for every tensor of a pointer table, ONE launch.
  *   table_dev: device array of n_tensors cnx_ema_entry, chunk_start ascending; one CTA per chunk of
- *   CNX_EMA_CHUNK elements.  Bit-exact with ATen lerp (|w| < 0.5 branch).
+ *   CNX_EMA_CHUNK elements.  Bit-exact with ATen lerp on both of its branches (|w| < 0.5: fmaf(w, p - ema, ema);
+ *   otherwise p - (p - ema) * (1 - w), e.g. w = 1 while ModelEmaV3.get_decay(step) returns 0).
  * ---------------------------------------------------------------------------------------------- */
 #define CNX_EMA_CHUNK 8192
 typedef struct {
@@ -61,7 +62,9 @@ typedef struct {
 CNX_API int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float w, void* stream);
 
 /* Fused AdamW + EMA over the same kind of pointer table (optim_factory.py:74-75 +
- * engine.py:73-77).  torch.optim.AdamW single-tensor semantics, decoupled weight decay, no amsgrad. */
+ * engine.py:73-77).  torch.optim.AdamW semantics (decoupled weight decay, no amsgrad) with the rounding of its default CUDA
+ * (foreach) path: hyper-parameters cross the ABI as doubles, every derived scalar (1 - lr*wd, 1 - beta1, 1 - beta2,
+ * -lr / bias_correction1, ...) is formed in double and rounded once to fp32 as Python + ATen do. */
 typedef struct {
   void* param;        /* fp32, updated */
   const void* grad;   /* fp32 */
@@ -71,9 +74,18 @@ typedef struct {
   int64_t numel;
   int64_t chunk_start;
 } cnx_adamw_entry;
-CNX_API int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float lr, float beta1,
-                        float beta2, float eps, float weight_decay, float bias_correction1,
-                        float bias_correction2_sqrt, float ema_w, void* stream);
+CNX_API int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chunks, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, double bias_correction1,
+                        double bias_correction2_sqrt, float ema_w, void* stream);
+
+/* Gradient 2-norm and clipping over a pointer table (utils.py:427-468: NativeScalerWithGradNormCount -> get_grad_norm_ /
+ * torch.nn.utils.clip_grad_norm_).  Entries are cnx_ema_entry with `ema` = the gradient tensor (`param` unused).
+ *   cnx_grad_sumsq_multi: partial[total_chunks] scratch; out[0] = ||g||_2 (partials summed in a fixed order, in double),
+ *                         out[1] = clip coefficient min(1, max_norm / (norm + 1e-6)) (1 when max_norm <= 0).  Two launches.
+ *   cnx_scale_multi:      g *= *coef for every tensor of the table (coef is a DEVICE scalar: no host round trip). */
+CNX_API int cnx_grad_sumsq_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float* partial, float max_norm,
+                         float* out, void* stream);
+CNX_API int cnx_scale_multi(const void* table_dev, int n_tensors, int64_t total_chunks, const float* coef, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * a9  SoftTargetCrossEntropy (train.py:257, engine.py:49,52):

@@ -3,6 +3,7 @@ container (TEST ORACLE tooling; used only by tests/golden/make_golden.py and tes
 /root/reference is absent).
 
   engine.py:4-5      timm.data.Mixup ; timm.utils.accuracy, ModelEmaV3
+  val.py:9-10        timm.utils.ModelEmaV3 ; timm.data.constants.IMAGENET_DEFAULT_{MEAN,STD}
   utils.py:7,15      timm.utils.get_state_dict ; tensorboardX.SummaryWriter
   semantic_segmentation/backbone/convnext.py:14-18
                      timm.models.layers.{trunc_normal_, DropPath} ; mmcv_custom.load_checkpoint ;
@@ -49,6 +50,8 @@ def install():
     mod("timm")
     mod("timm.data", Mixup=_mix.Mixup)
     mod("timm.data.mixup", Mixup=_mix.Mixup, mixup_target=_mix.mixup_target)
+    # val.py:10 — public ImageNet normalisation constants (timm/data/constants.py)
+    mod("timm.data.constants", IMAGENET_DEFAULT_MEAN=(0.485, 0.456, 0.406), IMAGENET_DEFAULT_STD=(0.229, 0.224, 0.225))
     mod("timm.utils", accuracy=_accuracy, ModelEmaV3=_ema.ModelEmaV3, get_state_dict=_ema.get_state_dict)
     mod("timm.loss", SoftTargetCrossEntropy=_loss.SoftTargetCrossEntropy)
     mod("timm.models", create_model=_cn.create_model)

@@ -1,0 +1,363 @@
+"""Round-2 parity closures (VERDICT r01 "Next round" item 3 and ADVICE r01):
+
+  * BASELINE config 2 at its REAL size (ConvNeXt-T, 224^2, batch 256, 1000 classes, bf16 autocast) against the oracle run
+    on the same GPU: logits and the global gradient vector, bar 2e-2 (north_star);
+  * the oracle's step loop (oracle/engine.py <- /root/reference/engine.py:10-143, pinned to the reference's own engine by
+    tests/golden/engine_step.npz) driving THIS PACKAGE's model / criterion / EMA / mixup objects — the drop-in claim;
+  * the CUDA Block directly against the goldens produced by the reference's own Block (tests/golden/block_C*.npz);
+  * bit-exact EMA out of the fused AdamW+EMA kernel, both ATen lerp branches of the EMA kernels (w < 0.5 and w >= 0.5);
+  * the EMA module forwarded across an update (derived-weight caches must follow raw-pointer writes);
+  * gradient norm / clipping kernels and the bf16 loss-scaler object (utils.py:427-468) inside engine.train_one_epoch;
+  * optimizer pointer-table invalidation on load_state_dict; whole-model checkpoint round trip (utils.py:536-615, val.py:14-28).
+"""
+import copy
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import imageclassification_b200 as P
+from cabi import max_rel
+from imageclassification_b200 import engine as PE, optim as PO, utils as PU
+from oracle import convnext as OC, ema as OE, engine as OEng, loss as OL, mixup as OM
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _flat_grads(model):
+    return torch.cat([p.grad.detach().flatten().double() for p in model.parameters()])
+
+
+@pytest.mark.parametrize("gamma", [1e-6, 1.0], ids=["gamma1e-6_default", "gamma1"])
+def test_config2_full_size_against_oracle(gamma):
+    """BASELINE config 2: batch 256 x 3 x 224 x 224, 1000 classes, bf16 autocast, soft targets from mixup(0.8)+smoothing 0.1.
+    Same weights, same mixed batch; no drop-path (mask draws are covered by the Block tests) so both sides are deterministic."""
+    B, K = 256, 1000
+    torch.manual_seed(2)
+    np.random.seed(2)
+    o = OC.create_model("convnext_tiny", num_classes=K, drop_path_rate=0.0, ls_init_value=gamma).to(DEV)
+    p = P.create_model("convnext_tiny", num_classes=K, drop_path_rate=0.0, ls_init_value=gamma).to(DEV)
+    p.load_state_dict(o.state_dict())
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    t = torch.randint(0, K, (B,), generator=g).to(DEV)
+    xs, ts = P.Mixup(mixup_alpha=0.8, label_smoothing=0.1, num_classes=K)(x.clone(), t)
+    res = []
+    for model, crit in ((o, OL.SoftTargetCrossEntropy()), (p, P.SoftTargetCrossEntropy())):
+        model.train()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(xs)
+            loss = crit(logits, ts)
+        loss.backward()
+        res.append((logits.detach().float(), loss.item(), _flat_grads(model)))
+        torch.cuda.synchronize()
+    (lo, losso, go), (lp, lossp, gp) = res
+    assert lp.shape == (B, K)
+    assert max_rel(lp, lo) <= 2e-2, max_rel(lp, lo)
+    assert abs(lossp - losso) <= 2e-2 * abs(losso)
+    # the global gradient vector (28.6 M entries): max-abs-normalised and relative L2
+    assert max_rel(gp, go) <= 2e-2, max_rel(gp, go)
+    rel_l2 = ((gp - go).norm() / go.norm()).item()
+    assert rel_l2 <= 2e-2, rel_l2
+    # per tensor: every parameter's gradient agrees with the oracle's in direction (bf16 noise is not a sign/scale error)
+    off = 0
+    for n, q in p.named_parameters():
+        a, b = gp[off:off + q.numel()], go[off:off + q.numel()]
+        off += q.numel()
+        cos = (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
+        assert cos >= 0.98 or b.norm().item() < 1e-12, (n, cos)
+
+
+CASES = [("fp32", False, 64, 8, 2, 0.0, 1.0, 0.0, 1), ("fp32_accum_cutmix", False, 64, 8, 5, 0.0, 1.0, 1.0, 2),
+         ("bf16_dp", True, 96, 16, 10, 0.05, 1.0, 1.0, 1)]
+
+
+@pytest.mark.parametrize("tag,amp,img,batch,K,dpr,gamma,cutmix,uf", CASES, ids=[c[0] for c in CASES])
+def test_reference_step_loop_drives_product_objects(tag, amp, img, batch, K, dpr, gamma, cutmix, uf):
+    """The drop-in boundary: the REFERENCE's step loop — here its restatement oracle/engine.py, itself pinned
+    to /root/reference/engine.py by tests/golden/engine_step.npz — runs unmodified on this package's objects and gives the
+    numbers it gives on the oracle objects.  (/root/reference's own engine.py cannot be imported on the GPU box.)"""
+    torch.manual_seed(11)
+    o = OC.create_model("convnext_tiny", num_classes=K, drop_path_rate=dpr, ls_init_value=gamma).to(DEV)
+    p = P.create_model("convnext_tiny", num_classes=K, drop_path_rate=dpr, ls_init_value=gamma).to(DEV)
+    p.load_state_dict(o.state_dict())
+    g = torch.Generator().manual_seed(5)
+    data = [(torch.randn(batch, 3, img, img, generator=g), torch.randint(0, K, (batch,), generator=g)) for _ in range(2 * uf)]
+    out = []
+    for model, crit, mixc, emac in ((o, OL.SoftTargetCrossEntropy(), OM.Mixup, OE.ModelEmaV3),
+                                    (p, P.SoftTargetCrossEntropy(), P.Mixup, P.ModelEmaV3)):
+        torch.manual_seed(3)
+        np.random.seed(3)
+        ema = emac(model, decay=0.9995, device=DEV)
+        mix = mixc(mixup_alpha=0.8, cutmix_alpha=cutmix, label_smoothing=0.1, num_classes=K)
+        opt = torch.optim.AdamW([{"params": list(model.parameters()), "weight_decay": 5e-4}], lr=1e-3, weight_decay=0.0)
+        stats = OEng.train_one_epoch(model, crit, [(a.clone(), b.clone()) for a, b in data], opt, DEV, 0, None, None, ema, mix,
+                                     num_training_steps_per_epoch=2, update_freq=uf, use_amp=amp, num_classes=K)
+        out.append((stats, np.array([q.detach().double().norm().item() for q in model.parameters()]),
+                    np.array([q.detach().double().norm().item() for q in ema.module.parameters()])))
+    (so, no, eo), (sp, npar, ep) = out
+    tol = 2e-2 if amp else 1e-4
+    assert abs(sp["loss"] - so["loss"]) <= tol * abs(so["loss"]), (sp["loss"], so["loss"])
+    np.testing.assert_allclose(npar, no, rtol=tol, atol=1e-3 if amp else 1e-6)
+    np.testing.assert_allclose(ep, eo, rtol=tol, atol=1e-6 if amp else 1e-8)
+    if not amp:
+        assert sp["class_acc"] == so["class_acc"]
+        assert sp["true_positives"] == so["true_positives"] and sp["false_negatives"] == so["false_negatives"]
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "block_C*.npz"))), ids=os.path.basename)
+def test_cuda_block_against_reference_block_golden(path):
+    """The libcnx Block against outputs and gradients of the reference's OWN Block
+    (/root/reference/semantic_segmentation/backbone/convnext.py:21-56, generated by tests/golden/make_golden.py), fp32 bar 1e-4."""
+    z = np.load(path)
+    C = z["x"].shape[1]
+    gamma0 = 1.0
+    blk = P.ConvNeXtBlock(C, ls_init_value=gamma0).to(DEV)
+    with torch.no_grad():
+        for n, q in blk.named_parameters():
+            q.copy_(torch.from_numpy(z["p." + n]).reshape(q.shape))
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    y = blk(x)
+    y.backward(torch.from_numpy(z["dout"]).to(DEV))
+    assert max_rel(y.detach().cpu(), torch.from_numpy(z["y"])) <= 1e-4
+    assert max_rel(x.grad.cpu(), torch.from_numpy(z["dx"])) <= 1e-4
+    for n, q in blk.named_parameters():
+        ref = torch.from_numpy(z["g." + n]).reshape(q.shape)
+        assert max_rel(q.grad.cpu(), ref) <= 1e-4, n
+    # ... and the no-grad forward (split-operand tcgen05 path where the shape allows it)
+    with torch.no_grad():
+        y2 = blk.eval()(x.detach())
+    assert max_rel(y2.cpu(), torch.from_numpy(z["y"])) <= 1e-4
+
+
+def _rand_params(n_tensors=7, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(96,), (384, 96), (96, 1, 7, 7), (1000, 768), (8193,), (3, 5), (16384,)][:n_tensors]
+    return [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+
+
+@pytest.mark.parametrize("decay", [0.9995, 0.3, 0.0], ids=["w_small", "w_0.7", "w_1"])
+def test_fused_adamw_ema_bit_exact_ema_and_torch_adamw(decay):
+    """EMA tensors written by cnx_adamw_ema_multi are bit-identical to ATen's lerp(ema, p_new, 1-decay) on BOTH lerp branches,
+    and the parameters / moments follow torch.optim.AdamW (CUDA foreach path) over several steps."""
+    ps = _rand_params()
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+
+    class _M(torch.nn.Module):
+        def __init__(self, params):
+            super().__init__()
+            self.ps = torch.nn.ParameterList(params)
+
+    mp_, mq = _M(ps), _M(qs)
+    ema = P.ModelEmaV3(mp_, decay=decay, device=DEV)
+    ema_ref = [e.detach().clone() for e in ema.module.parameters()]
+    opt = PO.AdamW([{"params": ps, "weight_decay": 5e-2}], lr=1e-2, weight_decay=0.0)
+    opt.fuse_ema(ema, mp_)
+    ref = torch.optim.AdamW([{"params": qs, "weight_decay": 5e-2}], lr=1e-2, weight_decay=0.0, foreach=True)
+    g = torch.Generator().manual_seed(9)
+    exact = True
+    for step in range(4):
+        for p, q in zip(ps, qs):
+            gr = torch.randn(p.shape, generator=g).to(DEV) * (10.0 ** (step - 2))
+            p.grad, q.grad = gr.clone(), gr.clone()
+        opt.step()
+        ema.update(mp_)
+        ref.step()
+        w = 1.0 - decay
+        for e_ref, p in zip(ema_ref, ps):
+            e_ref.copy_(torch.lerp(e_ref, p.detach(), w))
+        for e, e_ref in zip(ema.module.parameters(), ema_ref):
+            assert torch.equal(e.detach(), e_ref), f"EMA not bit-exact at step {step}"
+        for p, q in zip(ps, qs):
+            exact &= torch.equal(p.detach(), q.detach())
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=1e-7)
+    for p, q in zip(ps, qs):
+        torch.testing.assert_close(opt.state[p]["exp_avg"], ref.state[q]["exp_avg"], rtol=2e-6, atol=1e-9)
+        torch.testing.assert_close(opt.state[p]["exp_avg_sq"], ref.state[q]["exp_avg_sq"], rtol=2e-6, atol=1e-12)
+    print("fused AdamW parameters bit-identical to torch.optim.AdamW(foreach):", exact)
+
+
+@pytest.mark.parametrize("decay,step", [(0.9995, None), (0.3, None), (0.9995, 0), (0.9995, 5)])
+def test_ema_update_bit_exact_both_lerp_branches(decay, step):
+    """ModelEmaV3.update (cnx_ema_lerp_multi) vs ATen lerp, incl. w >= 0.5 (decay <= 0.5, or get_decay(step) == 0 -> w = 1)."""
+    m = P.create_model("convnext_tiny", num_classes=8).to(DEV)
+    ema = P.ModelEmaV3(m, decay=decay, device=DEV, update_after_step=2)
+    with torch.no_grad():
+        for q in m.parameters():
+            q.add_(torch.randn_like(q) * 0.1)
+    before = [e.detach().clone() for e in ema.module.state_dict().values()]
+    ema.update(m, step=step)
+    w = 1.0 - ema.get_decay(step)
+    for e, b, q in zip(ema.module.state_dict().values(), before, m.state_dict().values()):
+        assert torch.equal(e, torch.lerp(b, q.detach(), w))
+    if w == 1.0:
+        for e, q in zip(ema.module.state_dict().values(), m.state_dict().values()):
+            assert torch.equal(e, q)
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["ema.update", "fused_in_adamw"])
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16"])
+def test_ema_module_forward_follows_updates(fused, amp):
+    """the EMA weights are written through raw pointers; layouts derived from them (stem / downsample patch
+    weights, split fp32 operands, bf16 copies) are cached per (data_ptr, version) and must be rebuilt after every update.
+    The reference evaluates model_ema.module every epoch (train.py:366-367)."""
+    torch.manual_seed(4)
+    K = 8
+    m = P.create_model("convnext_tiny", num_classes=K, ls_init_value=1.0).to(DEV)
+    ema = P.ModelEmaV3(m, decay=0.5, device=DEV)                  # fast EMA: an update visibly moves the weights
+    opt = PO.AdamW([{"params": list(m.parameters()), "weight_decay": 0.0}], lr=5e-2, weight_decay=0.0)
+    if fused:
+        opt.fuse_ema(ema, m)
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    t = torch.randint(0, K, (4,), device=DEV)
+
+    def fwd(mod):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            return mod(x).float()
+
+    y0 = fwd(ema.module)
+    for _ in range(2):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = torch.nn.functional.cross_entropy(m(x).float(), t)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        ema.update(m)
+        y1 = fwd(ema.module)
+        fresh = P.create_model("convnext_tiny", num_classes=K, ls_init_value=1.0).to(DEV).eval()
+        fresh.load_state_dict(copy.deepcopy(ema.module.state_dict()))
+        y_fresh = fwd(fresh)
+        assert torch.equal(y1, y_fresh), (y1 - y_fresh).abs().max().item()
+        assert not torch.equal(y1, y0)
+        y0 = y1
+
+
+def test_grad_norm_and_clip_match_torch():
+    ps = _rand_params()
+    g = torch.Generator().manual_seed(1)
+    for p in ps:
+        p.grad = torch.randn(p.shape, generator=g).to(DEV) * 3.0
+    ref_norm = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(p.grad) for p in ps]))
+    n = PU.get_grad_norm_(ps)
+    assert n.is_cuda and n.dim() == 0
+    torch.testing.assert_close(n, ref_norm, rtol=1e-6, atol=0)
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    for p, q in zip(ps, qs):
+        q.grad = p.grad.clone()
+    for max_norm in (1e9, 5.0):                                   # no clipping needed / clipping
+        a = PU.clip_grad_norm_(ps, max_norm)
+        b = torch.nn.utils.clip_grad_norm_(qs, max_norm)
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=0)
+        for p, q in zip(ps, qs):
+            torch.testing.assert_close(p.grad, q.grad, rtol=1e-6, atol=0)
+
+
+def test_engine_loss_scaler_object_and_clipping():
+    """engine.py:61-68: with use_amp the step is delegated to the loss_scaler object.  This package's bf16 scaler, torch's
+    GradScaler-based one (the reference's utils.py:427-447, restated here) and no scaler + max_norm give the same parameters;
+    without AMP nothing clips (engine.py:70-77) even when max_norm is set."""
+    class RefScaler:                                              # utils.py:427-447 verbatim in behaviour
+        def __init__(self):
+            self._scaler = torch.amp.GradScaler("cuda")
+
+        def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+            self._scaler.scale(loss).backward(create_graph=create_graph)
+            norm = None
+            if update_grad:
+                self._scaler.unscale_(optimizer)
+                norm = torch.nn.utils.clip_grad_norm_(parameters, clip_grad) if clip_grad is not None else PU.get_grad_norm_(parameters)
+                self._scaler.step(optimizer)
+                self._scaler.update()
+            return norm
+
+    g = torch.Generator().manual_seed(2)
+    data = [(torch.randn(8, 3, 64, 64, generator=g), torch.randint(0, 8, (8,), generator=g)) for _ in range(2)]
+
+    def run(scaler, amp, max_norm):
+        torch.manual_seed(6)
+        np.random.seed(6)
+        m = P.create_model("convnext_tiny", num_classes=8, ls_init_value=1.0).to(DEV)
+        opt = torch.optim.SGD(m.parameters(), lr=0.05)
+        mix = P.Mixup(mixup_alpha=0.8, label_smoothing=0.1, num_classes=8)
+        PE.train_one_epoch(m, P.SoftTargetCrossEntropy(), [(a.clone(), b.clone()) for a, b in data], opt, DEV, 0, scaler, max_norm,
+                           None, mix, use_amp=amp, num_classes=8, verbose=False)
+        return torch.cat([q.detach().flatten() for q in m.parameters()])
+
+    ours = run(P.NativeScaler(), True, 0.5)
+    theirs = run(RefScaler(), True, 0.5)
+    none = run(None, True, 0.5)
+    unclipped = run(None, True, 0)
+    assert torch.equal(ours, none)
+    torch.testing.assert_close(ours, theirs, rtol=1e-3, atol=1e-5)          # 2^16 loss scaling is exact; SGD step order is not
+    assert not torch.equal(ours, unclipped)                                  # max_norm 0.5 really clipped
+    assert torch.equal(run(P.NativeScaler(), False, 0.5), run(None, False, 0))   # fp32 branch: scaler unused, nothing clips
+
+
+def test_adamw_tables_follow_load_state_dict():
+    """the device pointer table caches exp_avg / exp_avg_sq / EMA addresses; load_state_dict replaces the
+    moment tensors, so the table must be rebuilt and the loaded moments used."""
+    ps = _rand_params(4)
+    opt = PO.AdamW([{"params": ps, "weight_decay": 1e-2}], lr=1e-2, weight_decay=0.0)
+    g = torch.Generator().manual_seed(3)
+
+    def grads():
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=g).to(DEV)
+
+    grads()
+    opt.step()
+    sd = copy.deepcopy(opt.state_dict())
+    snap = [p.detach().clone() for p in ps]
+    grads()
+    gsave = [p.grad.clone() for p in ps]
+    opt.step()
+    after = [p.detach().clone() for p in ps]
+    # rewind parameters and optimizer state, replay the same gradients: identical result only if the loaded moments are used
+    with torch.no_grad():
+        for p, s in zip(ps, snap):
+            p.copy_(s)
+    opt.load_state_dict(sd)
+    for p, gg in zip(ps, gsave):
+        p.grad = gg.clone()
+    opt.step()
+    for p, a in zip(ps, after):
+        assert torch.equal(p.detach(), a)
+    assert all(opt.state[p]["step"] == 2 for p in ps)
+
+
+def test_checkpoint_round_trip_on_device(tmp_path):
+    """utils.py:536-615 + val.py:14-28: whole-model pickle written from a CUDA model, resumed into a fresh model / optimizer /
+    EMA, and reloaded for evaluation through a new ModelEmaV3: identical logits."""
+    import types
+    torch.manual_seed(8)
+    m = P.create_model("convnext_tiny", num_classes=8, ls_init_value=1.0).to(DEV)
+    ema = P.ModelEmaV3(m, decay=0.9, device=DEV)
+    opt = PO.AdamW([{"params": list(m.parameters()), "weight_decay": 5e-4}], lr=1e-3, weight_decay=0.0)
+    opt.fuse_ema(ema, m)
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    torch.nn.functional.cross_entropy(m(x), torch.randint(0, 8, (4,), device=DEV)).backward()
+    opt.step()
+    ema.update(m)
+    scaler = P.NativeScaler()
+    args = types.SimpleNamespace(resume="", auto_resume=True, model_ema=True, start_epoch=0, eval=False)
+    path = PU.save_model(args, (64, 64), 3, m, opt, scaler, ema, 8, output_dir=tmp_path)
+    m2 = P.create_model("convnext_tiny", num_classes=8, ls_init_value=1.0).to(DEV)
+    ema2 = P.ModelEmaV3(m2, decay=0.9, device=DEV)
+    opt2 = PO.AdamW([{"params": list(m2.parameters()), "weight_decay": 5e-4}], lr=1e-3, weight_decay=0.0)
+    PU.auto_load_model(args, m2, opt2, scaler, ema2, output_dir=tmp_path)
+    assert args.resume == str(path) and args.start_epoch == 4
+    with torch.no_grad():
+        assert torch.equal(m.eval()(x), m2.eval()(x))
+        assert torch.equal(ema.module(x), ema2.module(x))
+    assert all(int(s["step"]) == 1 for s in opt2.state.values())
+    net, k = PU.initialize_model(str(path), True, DEV)
+    assert k == 8 and not net.training
+    with torch.no_grad():
+        assert torch.equal(net(x), ema.module(x))
+    net2, _ = PU.initialize_model(str(path), False, DEV)
+    with torch.no_grad():
+        assert torch.equal(net2.eval()(x), m.eval()(x))
