@@ -28,6 +28,34 @@ int sm_count();
     }                                           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may start as soon as
+// the CTAs of the previous kernel in the stream have exited (SMs that finished their share of a persistent kernel pick up
+// the next kernel's CTAs, which run their prologue — shared-memory carve-up, mbarrier init, TMEM allocation, tensor-map
+// prefetch — under the previous kernel's tail).  A kernel launched this way MUST execute pdl_wait() in every thread before
+// its first global-memory access: it blocks until the previous grid has completed and its writes are visible (and the
+// kernel's own writes cannot overtake the previous grid's reads).  Without the launch attribute pdl_wait() is a no-op.
+// CNX_PDL=0 in the environment launches everything the ordinary way (for A/B measurements).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KP, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(KP...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KP>(args)...);
+}
+#endif
+
 inline bool dtype_ok(int d) { return d == CNX_F32 || d == CNX_BF16; }
 inline int dtype_size(int d) { return d == CNX_BF16 ? 2 : 4; }
 

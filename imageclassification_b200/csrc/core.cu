@@ -3,6 +3,7 @@
 //   partial-sum reduction, fp32->bf16 cast.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace cnx {
@@ -23,6 +24,15 @@ int check_launch(const char* what) {
     return (int)e;
   }
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int sm_count() {
@@ -62,6 +72,7 @@ __device__ __forceinline__ float lerp_aten(float self, float end, float w, float
 
 __global__ void __launch_bounds__(256) ema_lerp_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
                                                               float w) {
+  pdl_wait();
   __shared__ cnx_ema_entry ent;
   int64_t chunk = blockIdx.x;
   if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
@@ -121,6 +132,7 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(256) adamw_ema_multi_kernel(const cnx_adamw_entry* __restrict__ table, int n_tensors,
                                                                const AdamScalars c) {
+  pdl_wait();
   __shared__ cnx_adamw_entry ent;
   int64_t chunk = blockIdx.x;
   if (threadIdx.x == 0) ent = table[find_tensor(table, n_tensors, chunk)];
@@ -182,6 +194,7 @@ __global__ void __launch_bounds__(256) adamw_ema_multi_kernel(const cnx_adamw_en
 // squares, then ONE CTA sums the partials in a fixed order (deterministic) and forms norm and the clip coefficient.
 __global__ void __launch_bounds__(256) grad_sumsq_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
                                                                 float* __restrict__ partial) {
+  pdl_wait();
   __shared__ cnx_ema_entry ent;
   __shared__ float red[8];
   int64_t chunk = blockIdx.x;
@@ -214,6 +227,7 @@ __global__ void __launch_bounds__(256) grad_sumsq_multi_kernel(const cnx_ema_ent
 
 __global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* __restrict__ partial, int64_t n, float max_norm,
                                                                  float* __restrict__ out) {
+  pdl_wait();
   __shared__ double red[32];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)partial[i];
@@ -231,6 +245,7 @@ __global__ void __launch_bounds__(1024) grad_norm_finish_kernel(const float* __r
 
 __global__ void __launch_bounds__(256) scale_multi_kernel(const cnx_ema_entry* __restrict__ table, int n_tensors,
                                                            const float* __restrict__ coef_p) {
+  pdl_wait();
   __shared__ cnx_ema_entry ent;
   const float coef = __ldg(coef_p);
   if (coef == 1.0f) return;                    // torch multiplies by 1.0 here: same values, no traffic
@@ -265,6 +280,7 @@ __global__ void __launch_bounds__(THREADS) soft_ce_fwd_kernel(const TX* __restri
                                                               int64_t B, int64_t K, float* __restrict__ loss,
                                                               float* __restrict__ lse_out, float* __restrict__ row_loss,
                                                               unsigned int* __restrict__ counter) {
+  pdl_wait();
   __shared__ float red[THREADS / 32];
   __shared__ float bcast;
   __shared__ bool is_last;
@@ -338,6 +354,7 @@ template <typename TX, typename TD>
 __global__ void __launch_bounds__(256) soft_ce_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ t,
                                                           const float* __restrict__ lse, const float* __restrict__ dloss,
                                                           int64_t B, int64_t K, TD* __restrict__ dx) {
+  pdl_wait();
   __shared__ float red[8];
   __shared__ float bcast;
   const int64_t row = blockIdx.x;
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(256) soft_ce_bwd_kernel(const TX* __restrict__
 __global__ void __launch_bounds__(256) mixup_target_kernel(const int64_t* __restrict__ target, int64_t B, int64_t K,
                                                            float on, float off, float lam, float oml,
                                                            float* __restrict__ out) {
+  pdl_wait();
   int64_t total = B * K;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     int64_t b = i / K, k = i - b * K;
@@ -448,6 +466,7 @@ __global__ void __launch_bounds__(256) cutmix_swap_kernel(float* __restrict__ x,
 // deterministic, and a tall narrow partial buffer (P = several hundred CTAs x 2C columns) no longer runs on one warp's latency
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int P, int64_t L,
                                                               float scale, int accumulate, float* __restrict__ out) {
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t j = (int64_t)blockIdx.x * 32 + tx;
@@ -475,6 +494,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 __global__ void __launch_bounds__(256) reduce_partials2_kernel(const float* __restrict__ pa, int64_t La, float* __restrict__ oa,
                                                                const float* __restrict__ pb, int64_t Lb, float* __restrict__ ob,
                                                                int P, int accumulate) {
+  pdl_wait();
   int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= La + Lb) return;
   const float* partial = pa;
@@ -495,6 +515,7 @@ __global__ void __launch_bounds__(256) reduce_partials2_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, int64_t n, bf16* __restrict__ out) {
+  pdl_wait();
   int64_t i4 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   int64_t stride = (int64_t)gridDim.x * 256 * 4;
   bool aligned = ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 7) == 0);
@@ -522,7 +543,7 @@ int cnx_sm_count(void) { return cnx::sm_count(); }
 int cnx_ema_lerp_multi(const void* table_dev, int n_tensors, int64_t total_chunks, float w, void* stream) {
   CNX_REQUIRE(table_dev && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "ema_lerp_multi: empty table");
   CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "ema_lerp_multi: too many chunks");
-  ema_lerp_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_ema_entry*)table_dev,
+  launch_pdl(ema_lerp_multi_kernel, dim3((unsigned)total_chunks), dim3(256), 0, (cudaStream_t)stream, (const cnx_ema_entry*)table_dev,
                                                                                  n_tensors, w);
   return check_launch("ema_lerp_multi");
 }
@@ -546,7 +567,7 @@ int cnx_adamw_ema_multi(const void* table_dev, int n_tensors, int64_t total_chun
   c.ema_w = ema_w;
   c.ema_omw = 1.0f - ema_w;
   c.small_ema_w = fabsf(ema_w) < 0.5f;
-  adamw_ema_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_adamw_entry*)table_dev, n_tensors, c);
+  launch_pdl(adamw_ema_multi_kernel, dim3((unsigned)total_chunks), dim3(256), 0, (cudaStream_t)stream, (const cnx_adamw_entry*)table_dev, n_tensors, c);
   return check_launch("adamw_ema_multi");
 }
 
@@ -555,15 +576,15 @@ int cnx_grad_sumsq_multi(const void* table_dev, int n_tensors, int64_t total_chu
   CNX_REQUIRE(table_dev && partial && out && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "grad_sumsq_multi: bad argument");
   CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "grad_sumsq_multi: too many chunks");
   cudaStream_t s = (cudaStream_t)stream;
-  grad_sumsq_multi_kernel<<<(unsigned)total_chunks, 256, 0, s>>>((const cnx_ema_entry*)table_dev, n_tensors, partial);
-  grad_norm_finish_kernel<<<1, 1024, 0, s>>>(partial, total_chunks, max_norm, out);
+  launch_pdl(grad_sumsq_multi_kernel, dim3((unsigned)total_chunks), dim3(256), 0, s, (const cnx_ema_entry*)table_dev, n_tensors, partial);
+  launch_pdl(grad_norm_finish_kernel, dim3(1), dim3(1024), 0, s, partial, total_chunks, max_norm, out);
   return check_launch("grad_sumsq_multi");
 }
 
 int cnx_scale_multi(const void* table_dev, int n_tensors, int64_t total_chunks, const float* coef, void* stream) {
   CNX_REQUIRE(table_dev && coef && n_tensors > 0 && total_chunks > 0, CNX_E_BADARG, "scale_multi: bad argument");
   CNX_REQUIRE(total_chunks < (1ll << 31), CNX_E_SHAPE, "scale_multi: too many chunks");
-  scale_multi_kernel<<<(unsigned)total_chunks, 256, 0, (cudaStream_t)stream>>>((const cnx_ema_entry*)table_dev, n_tensors, coef);
+  launch_pdl(scale_multi_kernel, dim3((unsigned)total_chunks), dim3(256), 0, (cudaStream_t)stream, (const cnx_ema_entry*)table_dev, n_tensors, coef);
   return check_launch("scale_multi");
 }
 
@@ -573,11 +594,11 @@ int cnx_soft_target_ce_fwd(const void* x, int x_dtype, const float* t, int64_t B
   CNX_REQUIRE(B > 0 && K > 0 && dtype_ok(x_dtype), CNX_E_BADARG, "soft_target_ce_fwd: bad shape/dtype");
   cudaStream_t s = (cudaStream_t)stream;
   if (K <= 64) {
-    if (x_dtype == CNX_F32) soft_ce_fwd_kernel<float, 32><<<(unsigned)B, 32, 0, s>>>((const float*)x, t, B, K, loss, lse, row_loss, counter);
-    else soft_ce_fwd_kernel<bf16, 32><<<(unsigned)B, 32, 0, s>>>((const bf16*)x, t, B, K, loss, lse, row_loss, counter);
+    if (x_dtype == CNX_F32) launch_pdl(soft_ce_fwd_kernel<float, 32>, dim3((unsigned)B), dim3(32), 0, s, (const float*)x, t, B, K, loss, lse, row_loss, counter);
+    else launch_pdl(soft_ce_fwd_kernel<bf16, 32>, dim3((unsigned)B), dim3(32), 0, s, (const bf16*)x, t, B, K, loss, lse, row_loss, counter);
   } else {
-    if (x_dtype == CNX_F32) soft_ce_fwd_kernel<float, 256><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, B, K, loss, lse, row_loss, counter);
-    else soft_ce_fwd_kernel<bf16, 256><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, B, K, loss, lse, row_loss, counter);
+    if (x_dtype == CNX_F32) launch_pdl(soft_ce_fwd_kernel<float, 256>, dim3((unsigned)B), dim3(256), 0, s, (const float*)x, t, B, K, loss, lse, row_loss, counter);
+    else launch_pdl(soft_ce_fwd_kernel<bf16, 256>, dim3((unsigned)B), dim3(256), 0, s, (const bf16*)x, t, B, K, loss, lse, row_loss, counter);
   }
   return check_launch("soft_target_ce_fwd");
 }
@@ -587,10 +608,10 @@ int cnx_soft_target_ce_bwd(const void* x, int x_dtype, const float* t, const flo
   CNX_REQUIRE(x && t && lse && dloss && dx, CNX_E_BADARG, "soft_target_ce_bwd: null pointer");
   CNX_REQUIRE(B > 0 && K > 0 && dtype_ok(x_dtype) && dtype_ok(dx_dtype), CNX_E_BADARG, "soft_target_ce_bwd: bad shape/dtype");
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == CNX_F32 && dx_dtype == CNX_F32) soft_ce_bwd_kernel<float, float><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, lse, dloss, B, K, (float*)dx);
-  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_BF16) soft_ce_bwd_kernel<bf16, bf16><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, lse, dloss, B, K, (bf16*)dx);
-  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_F32) soft_ce_bwd_kernel<bf16, float><<<(unsigned)B, 256, 0, s>>>((const bf16*)x, t, lse, dloss, B, K, (float*)dx);
-  else soft_ce_bwd_kernel<float, bf16><<<(unsigned)B, 256, 0, s>>>((const float*)x, t, lse, dloss, B, K, (bf16*)dx);
+  if (x_dtype == CNX_F32 && dx_dtype == CNX_F32) launch_pdl(soft_ce_bwd_kernel<float, float>, dim3((unsigned)B), dim3(256), 0, s, (const float*)x, t, lse, dloss, B, K, (float*)dx);
+  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_BF16) launch_pdl(soft_ce_bwd_kernel<bf16, bf16>, dim3((unsigned)B), dim3(256), 0, s, (const bf16*)x, t, lse, dloss, B, K, (bf16*)dx);
+  else if (x_dtype == CNX_BF16 && dx_dtype == CNX_F32) launch_pdl(soft_ce_bwd_kernel<bf16, float>, dim3((unsigned)B), dim3(256), 0, s, (const bf16*)x, t, lse, dloss, B, K, (float*)dx);
+  else launch_pdl(soft_ce_bwd_kernel<float, bf16>, dim3((unsigned)B), dim3(256), 0, s, (const float*)x, t, lse, dloss, B, K, (bf16*)dx);
   return check_launch("soft_target_ce_bwd");
 }
 
@@ -604,7 +625,7 @@ int cnx_mixup_target(const int64_t* target, int64_t B, int64_t K, double lam, do
   int64_t total = B * K;
   unsigned grid = (unsigned)((total + 255) / 256);
   if (grid > 148u * 16u) grid = 148u * 16u;
-  mixup_target_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(target, B, K, (float)on, (float)off, (float)lam,
+  launch_pdl(mixup_target_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, target, B, K, (float)on, (float)off, (float)lam,
                                                                (float)oml, out);
   return check_launch("mixup_target");
 }
@@ -646,7 +667,7 @@ int cnx_mixup_batch(float* x, float* orig, int64_t B, int64_t C, int64_t H, int6
 int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream) {
   CNX_REQUIRE(partial && out && P > 0 && L > 0, CNX_E_BADARG, "reduce_partials: bad argument");
-  reduce_partials_kernel<<<(unsigned)((L + 31) / 32), 256, 0, (cudaStream_t)stream>>>(partial, P, L, scale,
+  launch_pdl(reduce_partials_kernel, dim3((unsigned)((L + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, partial, P, L, scale,
                                                                                        accumulate, out);
   return check_launch("reduce_partials");
 }
@@ -656,7 +677,7 @@ int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int
 namespace cnx {
 int reduce_partials2(const float* pa, int64_t La, float* oa, const float* pb, int64_t Lb, float* ob, int P, int accumulate,
                      cudaStream_t s) {
-  reduce_partials2_kernel<<<(unsigned)((La + Lb + 255) / 256), 256, 0, s>>>(pa, La, oa, pb, Lb, ob, P, accumulate);
+  launch_pdl(reduce_partials2_kernel, dim3((unsigned)((La + Lb + 255) / 256)), dim3(256), 0, s, pa, La, oa, pb, Lb, ob, P, accumulate);
   return check_launch("reduce_partials2");
 }
 }  // namespace cnx
@@ -667,7 +688,7 @@ int cnx_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
   CNX_REQUIRE(in && out && n > 0, CNX_E_BADARG, "cast_f32_to_bf16: bad argument");
   int64_t blocks = (n / 4 + 255) / 256 + 1;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, n, (bf16*)out);
+  launch_pdl(cast_f32_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, in, n, (bf16*)out);
   return check_launch("cast_f32_to_bf16");
 }
 

@@ -182,6 +182,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();                                  // everything above overlapped the previous kernel's tail (common.cuh)
 
   if (warp == 0) {
     // ===== producer =====
@@ -411,8 +412,8 @@ static int launch_conv(const void* x, int x_dtype, const float* wt, const float*
   CNX_REQUIRE(nt < (1ll << 30), CNX_E_SHAPE, "dwconv: too many tiles");
   int grid = sm_count();
   if (grid > nt) grid = (int)nt;
-  k<<<grid, Cfg::NT, Cfg::SMEM, s>>>(tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias, (const TOUT*)dres,
-                                     (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd, (bf16*)xn3);
+  launch_pdl(k, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, s, tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias,
+             (const TOUT*)dres, (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd, (bf16*)xn3);
   return check_launch(MODE == MODE_FWD ? "dwconv7_ln_fwd" : "dwconv7_dgrad");
 }
 
@@ -480,6 +481,7 @@ dwconv7_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -573,7 +575,7 @@ static int launch_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype
   const int64_t nt = num_tiles<G>(N, H, W, &tiles_x, &tiles_y);
   CNX_REQUIRE(nt < (1ll << 30), CNX_E_SHAPE, "dwconv wgrad: too many tiles");
   const int nchunks = (int)(C / CH);
-  k<<<(unsigned)(P * nchunks), Cfg::NT, Cfg::SMEM, s>>>(tmX, tmDY, (int)C, tiles_x, tiles_y, (int)nt, P, partial);
+  launch_pdl(k, dim3((unsigned)(P * nchunks)), dim3(Cfg::NT), Cfg::SMEM, s, tmX, tmDY, (int)C, tiles_x, tiles_y, (int)nt, P, partial);
   return check_launch("dwconv7_wgrad");
 }
 

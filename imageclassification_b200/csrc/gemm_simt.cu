@@ -188,6 +188,7 @@ template <typename TS, typename TA>
 __global__ void __launch_bounds__(256) grad_prep_kernel(const TS* __restrict__ dout, const float* __restrict__ dp,
                                                         int64_t rows_per_sample, int64_t M, int64_t C,
                                                         TA* __restrict__ dz) {
+  pdl_wait();
   const int64_t vec_per_row = C >> 3;
   const int64_t total = M * vec_per_row;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const TS* __restrict__ d
 
 // fp32 [M, C] -> bf16 [M, 3C] = [hi | mid | hi]: the A-side split operand (x ~ hi + mid to 2^-17 relative); 8 elements per thread
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int64_t M, int64_t C, bf16* __restrict__ out) {
+  pdl_wait();
   const int64_t vpr = C >> 3, total = M * vpr;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
     const int64_t m = i / vpr, v = i - m * vpr;
@@ -227,6 +229,7 @@ template <typename TO>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, int64_t R, int64_t Cc,
                                                           const float* __restrict__ row_scale, int mode,
                                                           TO* __restrict__ out) {
+  pdl_wait();
   // 32x32 shared-memory transpose tiles; mode 0 is a straight cast
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
@@ -280,6 +283,7 @@ struct WeightPrepEntry {
 };
 
 __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const WeightPrepEntry* __restrict__ table, int n) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int64_t b = blockIdx.x;
   int lo = 0, hi = n - 1;
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(256) layerscale_finalize_kernel(const float* _
                                                                   const float* __restrict__ gamma, int64_t C, int64_t K4,
                                                                   int accumulate, float* __restrict__ dW2,
                                                                   float* __restrict__ db2, float* __restrict__ dgamma) {
+  pdl_wait();
   __shared__ float red[8];
   const int64_t c = blockIdx.x;
   const float gm = gamma ? gamma[c] : 1.0f;
@@ -368,9 +373,9 @@ int cnx_grad_prep(const void* dout, int stream_dtype, const float* dp, int64_t r
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t s = (cudaStream_t)stream;
-  if (stream_dtype == CNX_F32 && act_dtype == CNX_F32) grad_prep_kernel<float, float><<<(unsigned)blocks, 256, 0, s>>>((const float*)dout, dp, rows_per_sample, M, C, (float*)dz);
-  else if (stream_dtype == CNX_F32 && act_dtype == CNX_BF16) grad_prep_kernel<float, bf16><<<(unsigned)blocks, 256, 0, s>>>((const float*)dout, dp, rows_per_sample, M, C, (bf16*)dz);
-  else if (stream_dtype == CNX_BF16 && act_dtype == CNX_BF16) grad_prep_kernel<bf16, bf16><<<(unsigned)blocks, 256, 0, s>>>((const bf16*)dout, dp, rows_per_sample, M, C, (bf16*)dz);
+  if (stream_dtype == CNX_F32 && act_dtype == CNX_F32) launch_pdl(grad_prep_kernel<float, float>, dim3((unsigned)blocks), dim3(256), 0, s, (const float*)dout, dp, rows_per_sample, M, C, (float*)dz);
+  else if (stream_dtype == CNX_F32 && act_dtype == CNX_BF16) launch_pdl(grad_prep_kernel<float, bf16>, dim3((unsigned)blocks), dim3(256), 0, s, (const float*)dout, dp, rows_per_sample, M, C, (bf16*)dz);
+  else if (stream_dtype == CNX_BF16 && act_dtype == CNX_BF16) launch_pdl(grad_prep_kernel<bf16, bf16>, dim3((unsigned)blocks), dim3(256), 0, s, (const bf16*)dout, dp, rows_per_sample, M, C, (bf16*)dz);
   else { set_error("grad_prep: unsupported dtype combination"); return CNX_E_BADARG; }
   return check_launch("grad_prep");
 }
@@ -382,8 +387,8 @@ int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_s
   CNX_REQUIRE(mode != 3 || out_dtype == CNX_BF16, CNX_E_BADARG, "weight_prep: mode 3 (split operand) writes bf16");
   dim3 grid((unsigned)((Ccols + 31) / 32), (unsigned)((R + 31) / 32));
   cudaStream_t s = (cudaStream_t)stream;
-  if (out_dtype == CNX_F32) weight_prep_kernel<float><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (float*)out);
-  else weight_prep_kernel<bf16><<<grid, 256, 0, s>>>(W, R, Ccols, row_scale, mode, (bf16*)out);
+  if (out_dtype == CNX_F32) launch_pdl(weight_prep_kernel<float>, dim3(grid), dim3(256), 0, s, W, R, Ccols, row_scale, mode, (float*)out);
+  else launch_pdl(weight_prep_kernel<bf16>, dim3(grid), dim3(256), 0, s, W, R, Ccols, row_scale, mode, (bf16*)out);
   return check_launch("weight_prep");
 }
 
@@ -394,14 +399,14 @@ int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream) {
   const int64_t total = M * (C / 8);
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  split3_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, M, C, (bf16*)out);
+  launch_pdl(split3_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, x, M, C, (bf16*)out);
   return check_launch("split3");
 }
 
 int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_tiles, void* stream) {
   CNX_REQUIRE(table_dev && n_entries > 0 && total_tiles > 0 && total_tiles < (1ll << 31), CNX_E_BADARG,
               "weight_prep_multi: bad argument");
-  weight_prep_multi_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const WeightPrepEntry*)table_dev, n_entries);
+  launch_pdl(weight_prep_multi_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)stream, (const WeightPrepEntry*)table_dev, n_entries);
   return check_launch("weight_prep_multi");
 }
 
@@ -409,7 +414,7 @@ int cnx_layerscale_finalize(const float* G2, const float* s, const float* W2, co
                             int64_t C, int64_t K4, int accumulate, float* dW2, float* db2, float* dgamma,
                             void* stream) {
   CNX_REQUIRE(G2 && s && W2 && b2 && dW2 && db2 && C > 0 && K4 > 0, CNX_E_BADARG, "layerscale_finalize: bad argument");
-  layerscale_finalize_kernel<<<(unsigned)C, 256, 0, (cudaStream_t)stream>>>(G2, s, W2, b2, gamma, C, K4, accumulate,
+  launch_pdl(layerscale_finalize_kernel, dim3((unsigned)C), dim3(256), 0, (cudaStream_t)stream, G2, s, W2, b2, gamma, C, K4, accumulate,
                                                                            dW2, db2, dgamma);
   return check_launch("layerscale_finalize");
 }

@@ -382,6 +382,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                        // barrier init / TMEM allocation above ran under the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -733,6 +734,7 @@ gemm_tn_tc_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -952,6 +954,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1120,6 +1123,7 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_cons
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1376,6 +1380,7 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1587,13 +1592,15 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, M, N, K, ep);
   if (e != cudaSuccess) {
     set_error("gemm_tn_tc launch: %s", cudaGetErrorString(e));
@@ -1641,7 +1648,7 @@ static int launch_tn_staged(const void* A, const void* B, int64_t M, int64_t N, 
   int64_t tiles = ((M + BM - 1) / BM) * (N / kStBN);
   int64_t grid = sm_count();
   if (grid > tiles) grid = tiles;
-  k<<<(unsigned)grid, kStThreads, kStSmem, s>>>(tmA, tmB, tmO0, tmO1, M, N, K, ep.bias, ep.out0 != nullptr ? 1 : 0);
+  launch_pdl(k, dim3((unsigned)grid), dim3(kStThreads), kStSmem, s, tmA, tmB, tmO0, tmO1, M, N, K, ep.bias, ep.out0 != nullptr ? 1 : 0);
   return check_launch("gemm_tn_tc_staged");
 }
 
@@ -1662,7 +1669,7 @@ static int launch_mlp_fused(const void* xn, const void* W1, const float* b1, con
   int64_t grid = sm_count();
   const int64_t tiles = (M + BM - 1) / BM;
   if (grid > tiles) grid = tiles;
-  k<<<(unsigned)grid, kFuThreads, Cfg::SMEM, s>>>(tmXn, tmW1, tmW2, tmRes, tmOut, M, b1, b2, gamma, dp, rows_per_sample);
+  launch_pdl(k, dim3((unsigned)grid), dim3(kFuThreads), Cfg::SMEM, s, tmXn, tmW1, tmW2, tmRes, tmOut, M, b1, b2, gamma, dp, rows_per_sample);
   return check_launch("mlp_fused_fwd");
 }
 
@@ -1748,13 +1755,15 @@ static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int
   cfg.blockDim = dim3(tc::kThreads);
   cfg.dynamicSmemBytes = tc::WgPairCfg<BN>::SMEM;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmX, tmY, M, N1, N2, kb_per_split, part, cs_part);
   if (e != cudaSuccess) {
     set_error("gemm_wgrad_pair launch: %s", cudaGetErrorString(e));
@@ -1787,11 +1796,11 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
     if (pl.bn == 128) {
       auto k = tc::gemm_wgrad_tc_kernel<128>;
       if (int rc = tc::set_smem(k, tc::WgCfg<128>::SMEM)) return rc;
-      k<<<grid, tc::kThreads, tc::WgCfg<128>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<128>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
     } else {
       auto k = tc::gemm_wgrad_tc_kernel<96>;
       if (int rc = tc::set_smem(k, tc::WgCfg<96>::SMEM)) return rc;
-      k<<<grid, tc::kThreads, tc::WgCfg<96>::SMEM, s>>>(tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<96>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
     }
     if (int rc = check_launch("gemm_wgrad_tc")) return rc;
   }

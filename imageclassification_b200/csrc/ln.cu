@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const TX* __restr
                                                                const float* __restrict__ ln_b, float eps, int64_t M,
                                                                int C, TO* __restrict__ out, float* __restrict__ mean_out,
                                                                float* __restrict__ rstd_out, int pH, int pW) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
   float lw[NJ][4], lb[NJ][4];
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, (NJ >= 3 ? 2 : 3)) ln_fwd_v2_ke
                                                                      const float* __restrict__ ln_b, float eps, int64_t M, int C,
                                                                      TO* __restrict__ out, float* __restrict__ mean_out,
                                                                      float* __restrict__ rstd_out, int pH, int pW) {
+  pdl_wait();
   constexpr int PPW = 32 / LPP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPP, l = lane % LPP;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const TG* __restr
                                                                const float* __restrict__ ln_w, int64_t M, int C,
                                                                TD* __restrict__ dy, float* __restrict__ partial, int pH,
                                                                int pW) {
+  pdl_wait();
   extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = C >> 2;
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, CNX_LNB_MINB) ln_bwd_v2_kernel(
                                                                   const float* __restrict__ ln_w, int64_t M, int C,
                                                                   TD* __restrict__ dy, float* __restrict__ partial, int pH,
                                                                   int pW) {
+  pdl_wait();
   extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C]
   constexpr int PPW = 32 / LPP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,6 +392,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2) ln_bwd_v3_kernel(const bf16*
                                                                      const float* __restrict__ ln_w, int64_t M, int C,
                                                                      bf16* __restrict__ dy, float* __restrict__ partial, int pH,
                                                                      int pW) {
+  pdl_wait();
   extern __shared__ __align__(16) float colacc[];        // [LN_WARPS][2][C], then ln_w [C] when it does not fit in registers
   constexpr int PPW = 32 / LPP;
   constexpr bool LW_SMEM = NJ >= 3;                      // 16 accumulators per vector already: keep ln_w in shared memory
@@ -553,7 +558,7 @@ static int launch_ln_bwd_v3(const bf16* dxn, const bf16* y, const float* mean, c
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
       if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }          \
     }                                                                                                             \
-    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>(dxn, y, mean, rstd, ln_w, M, (int)C, dy, partial, pH, pW);         \
+    launch_pdl(k, dim3((unsigned)P), dim3(LN_WARPS * 32), smem, s, dxn, y, mean, rstd, ln_w, M, (int)C, dy, partial, pH, pW); \
     return check_launch("ln_bwd");                                                                                \
   } while (0)
 #define CNX_LNB3_NJ(LPP)                     \
@@ -600,7 +605,7 @@ static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, fl
     const int lpp = (int)(C / 24);
     int64_t b3 = (int64_t)sm_count() * 2;
 #define CNX_LNF3(LPP)                                                                                                              \
-    ln_fwd_v2_kernel<TX, TO, 3, LPP, 2><<<(unsigned)b3, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, \
+    launch_pdl(ln_fwd_v2_kernel<TX, TO, 3, LPP, 2>, dim3((unsigned)b3), dim3(LN_WARPS * 32), 0, s, (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, \
                                                                                 mean, rstd, pH, pW)
     if (lpp == 4) { CNX_LNF3(4); return check_launch("ln_fwd"); }
     if (lpp == 8) { CNX_LNF3(8); return check_launch("ln_fwd"); }
@@ -610,14 +615,14 @@ static int launch_ln_fwd(const void* x, const float* ln_w, const float* ln_b, fl
   if (C % 8 == 0 && C <= 256 && M >= 4096 && !ln_v1()) {
     int64_t b2 = (int64_t)sm_count() * 3;
     if (C <= 128)
-      ln_fwd_v2_kernel<TX, TO, 1, 16, 4><<<(unsigned)b2, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
+      launch_pdl(ln_fwd_v2_kernel<TX, TO, 1, 16, 4>, dim3((unsigned)b2), dim3(LN_WARPS * 32), 0, s, (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
                                                                                 mean, rstd, pH, pW);
     else
-      ln_fwd_v2_kernel<TX, TO, 1, 32, 4><<<(unsigned)b2, LN_WARPS * 32, 0, s>>>((const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
+      launch_pdl(ln_fwd_v2_kernel<TX, TO, 1, 32, 4>, dim3((unsigned)b2), dim3(LN_WARPS * 32), 0, s, (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out,
                                                                                 mean, rstd, pH, pW);
     return check_launch("ln_fwd");
   }
-  CNX_NJ_SWITCH(nj_for(C), (ln_fwd_kernel<TX, TO, NJ><<<(unsigned)blocks, LN_WARPS * 32, 0, s>>>(
+  CNX_NJ_SWITCH(nj_for(C), (launch_pdl(ln_fwd_kernel<TX, TO, NJ>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), 0, s, 
                                (const TX*)x, ln_w, ln_b, eps, M, (int)C, (TO*)out, mean, rstd, pH, pW)));
   return check_launch("ln_fwd");
 }
@@ -636,8 +641,8 @@ static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, cons
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
       if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }             \
     }                                                                                                                \
-    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,   \
-                                               partial, pH, pW);                                                     \
+    launch_pdl(k, dim3((unsigned)P), dim3(LN_WARPS * 32), smem, s, (const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C,  \
+               (TD*)dy, partial, pH, pW);                                                                            \
     return check_launch("ln_bwd");                                                                                   \
   } while (0)
     const int64_t vpr = C / 8;
@@ -651,8 +656,8 @@ static int launch_ln_bwd(const void* dxn, const void* y, const float* mean, cons
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("ln_bwd smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    k<<<(unsigned)P, LN_WARPS * 32, smem, s>>>((const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,
-                                               partial, pH, pW);
+    launch_pdl(k, dim3((unsigned)P), dim3(LN_WARPS * 32), smem, s, (const TG*)dxn, (const TY*)y, mean, rstd, ln_w, M, (int)C, (TD*)dy,
+               partial, pH, pW);
   });
   return check_launch("ln_bwd");
 }

@@ -11,6 +11,7 @@ namespace cnx {
 template <typename TOUT>
 __global__ void __launch_bounds__(256) patchify4_kernel(const float* __restrict__ x, int N, int Cin, int H, int W,
                                                         TOUT* __restrict__ out) {
+  pdl_wait();
   const int OW = W >> 2, OH = H >> 2;
   const int64_t total = (int64_t)N * OH * OW * Cin * 4;        // one float4 (4 kx) per work item
   const int K = Cin * 16;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) patchify4_kernel(const float* __restrict_
 // in [N,H,W,C] -> out [N,H/2,W/2,(2,2,C)]  (GATHER = true)   or the inverse (GATHER = false); VEC-byte elements moved as 16 B
 __global__ void __launch_bounds__(256) patch2_kernel(const uint4* __restrict__ in, int N, int H, int W, int vpc /*16B vectors per pixel*/,
                                                      uint4* __restrict__ out, int gather) {
+  pdl_wait();
   const int64_t total = (int64_t)N * H * W * vpc;
   const int OW = W >> 1, OH = H >> 1;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(256) patch2_kernel(const uint4* __restrict__ i
 // ------------------------------------------------------------------------------------------------
 template <typename TX>
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const TX* __restrict__ x, int64_t N, int HW, int C, float* __restrict__ out) {
+  pdl_wait();
   const int c4 = C >> 2;
   const int64_t total = N * c4;
   const float inv = 1.0f / (float)HW;
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const TX* __restrict__
 }
 template <typename TX>
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dout, int64_t N, int HW, int C, TX* __restrict__ dx) {
+  pdl_wait();
   const int c4 = C >> 2;
   const int64_t total = N * HW * c4;
   const float inv = 1.0f / (float)HW;
@@ -101,8 +105,8 @@ int cnx_patchify4_nchw(const float* x, int64_t N, int64_t Cin, int64_t H, int64_
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t s = (cudaStream_t)stream;
-  if (out_dtype == CNX_F32) patchify4_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(x, (int)N, (int)Cin, (int)H, (int)W, (float*)out);
-  else patchify4_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(x, (int)N, (int)Cin, (int)H, (int)W, (bf16*)out);
+  if (out_dtype == CNX_F32) launch_pdl(patchify4_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, s, x, (int)N, (int)Cin, (int)H, (int)W, (float*)out);
+  else launch_pdl(patchify4_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, s, x, (int)N, (int)Cin, (int)H, (int)W, (bf16*)out);
   return check_launch("patchify4");
 }
 
@@ -118,7 +122,7 @@ int cnx_patch2(const void* in, int dtype, int64_t N, int64_t H, int64_t W, int64
   int64_t blocks = (items + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  patch2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (int)N, (int)H, (int)W, vpc, (uint4*)out,
+  launch_pdl(patch2_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const uint4*)in, (int)N, (int)H, (int)W, vpc, (uint4*)out,
                                                                      gather);
   return check_launch("patch2");
 }
@@ -128,8 +132,8 @@ int cnx_avgpool_nhwc_fwd(const void* x, int x_dtype, int64_t N, int64_t HW, int6
   CNX_REQUIRE(C % 4 == 0, CNX_E_SHAPE, "avgpool_fwd: C=%lld must be a multiple of 4", (long long)C);
   int64_t blocks = (N * (C / 4) + 255) / 256;
   cudaStream_t s = (cudaStream_t)stream;
-  if (x_dtype == CNX_F32) avgpool_fwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)x, N, (int)HW, (int)C, out);
-  else avgpool_fwd_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>((const bf16*)x, N, (int)HW, (int)C, out);
+  if (x_dtype == CNX_F32) launch_pdl(avgpool_fwd_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, s, (const float*)x, N, (int)HW, (int)C, out);
+  else launch_pdl(avgpool_fwd_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, s, (const bf16*)x, N, (int)HW, (int)C, out);
   return check_launch("avgpool_fwd");
 }
 
@@ -140,8 +144,8 @@ int cnx_avgpool_nhwc_bwd(const float* dout, int64_t N, int64_t HW, int64_t C, vo
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dx_dtype == CNX_F32) avgpool_bwd_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(dout, N, (int)HW, (int)C, (float*)dx);
-  else avgpool_bwd_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(dout, N, (int)HW, (int)C, (bf16*)dx);
+  if (dx_dtype == CNX_F32) launch_pdl(avgpool_bwd_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, s, dout, N, (int)HW, (int)C, (float*)dx);
+  else launch_pdl(avgpool_bwd_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, s, dout, N, (int)HW, (int)C, (bf16*)dx);
   return check_launch("avgpool_bwd");
 }
 

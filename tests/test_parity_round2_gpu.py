@@ -361,3 +361,38 @@ def test_checkpoint_round_trip_on_device(tmp_path):
     net2, _ = PU.initialize_model(str(path), False, DEV)
     with torch.no_grad():
         assert torch.equal(net2.eval()(x), m.eval()(x))
+
+
+def test_non_finite_loss_skips_the_step_like_the_reference():
+    """engine.py:54-59: a non-finite loss leaves parameters, optimizer state and EMA untouched, drops the accumulated
+    gradients and the step's metrics.  (This package reads the loss after enqueuing backward; the outcome is the same.)"""
+    g = torch.Generator().manual_seed(12)
+    good = (torch.randn(8, 3, 64, 64, generator=g), torch.randint(0, 8, (8,), generator=g))
+    bad = (torch.full((8, 3, 64, 64), float("nan")), torch.randint(0, 8, (8,), generator=g))
+
+    def run(eng, mods, data, uf):
+        torch.manual_seed(6)
+        np.random.seed(6)
+        create, crit, mixc, emac = mods
+        m = create("convnext_tiny", num_classes=8, ls_init_value=1.0).to(DEV)
+        ema = emac(m, decay=0.9, device=DEV)
+        opt = torch.optim.SGD(m.parameters(), lr=0.05)
+        mix = mixc(mixup_alpha=0.8, label_smoothing=0.1, num_classes=8)
+        kw = {"verbose": False} if eng is PE else {}
+        st = eng.train_one_epoch(m, crit, [(a.clone(), b.clone()) for a, b in data], opt, DEV, 0, None, 0, ema, mix, update_freq=uf,
+                                 use_amp=False, num_classes=8, **kw)
+        return st, torch.cat([q.detach().flatten() for q in m.parameters()]), torch.cat([q.detach().flatten() for q in ema.module.parameters()])
+
+    ours = (P.create_model, P.SoftTargetCrossEntropy(), P.Mixup, P.ModelEmaV3)
+    orac = (OC.create_model, OL.SoftTargetCrossEntropy(), OM.Mixup, OE.ModelEmaV3)
+    # only bad batches: nothing may move
+    st, p1, e1 = run(PE, ours, [bad, bad], 1)
+    st0, p0, e0 = run(PE, ours, [], 1)
+    assert torch.equal(p1, p0) and torch.equal(e1, e0) and st["loss"] == 0.0
+    # good, bad, good with accumulation over 2 micro-steps: the bad micro-step discards the first one's gradients (zero_grad),
+    # exactly as the reference's loop does — compare with the oracle loop on the oracle objects
+    for uf in (1, 2):
+        sp, pp, ep = run(PE, ours, [good, bad, good, good], uf)
+        so, po, eo = run(OEng, orac, [good, bad, good, good], uf)
+        assert abs(sp["loss"] - so["loss"]) <= 1e-4 * abs(so["loss"])
+        assert max_rel(pp, po) <= 1e-4 and max_rel(ep, eo) <= 1e-4
