@@ -464,8 +464,10 @@ __global__ void __launch_bounds__(256) cutmix_swap_kernel(float* __restrict__ x,
 // ================================================================================================
 // 32 columns per CTA; the 8 warps split the P rows (fixed assignment), then meet in shared memory in a fixed order:
 // deterministic, and a tall narrow partial buffer (P = several hundred CTAs x 2C columns) no longer runs on one warp's latency
+// (columns [0, La) go to out, columns [La, L) to out_b: the two halves of a [P, 2C] LayerNorm partial land in two tensors)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int P, int64_t L,
-                                                              float scale, int accumulate, float* __restrict__ out) {
+                                                              float scale, int accumulate, float* __restrict__ out,
+                                                              int64_t La, float* __restrict__ out_b) {
   pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -486,7 +488,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][tx];
     s *= scale;
-    out[j] = accumulate ? out[j] + s : s;
+    float* o = (j < La) ? out + j : out_b + (j - La);
+    *o = accumulate ? *o + s : s;
   }
 }
 
@@ -668,8 +671,16 @@ int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int
                         void* stream) {
   CNX_REQUIRE(partial && out && P > 0 && L > 0, CNX_E_BADARG, "reduce_partials: bad argument");
   launch_pdl(reduce_partials_kernel, dim3((unsigned)((L + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, partial, P, L, scale,
-                                                                                       accumulate, out);
+             accumulate, out, L, (float*)nullptr);
   return check_launch("reduce_partials");
+}
+
+int cnx_reduce_partials_split(const float* partial, int P, int64_t La, int64_t Lb, int accumulate, float* out_a, float* out_b,
+                              void* stream) {
+  CNX_REQUIRE(partial && out_a && out_b && P > 0 && La > 0 && Lb > 0, CNX_E_BADARG, "reduce_partials_split: bad argument");
+  launch_pdl(reduce_partials_kernel, dim3((unsigned)((La + Lb + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, partial, P, La + Lb,
+             1.0f, accumulate, out_a, La, out_b);
+  return check_launch("reduce_partials_split");
 }
 
 }  // extern "C"

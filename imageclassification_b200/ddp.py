@@ -8,19 +8,67 @@ in ~`bucket_cap_mb` buckets formed in reverse registration order, overlapped wit
 
 Design: one contiguous fp32 arena holds every gradient; `param.grad` is a view into it, so a bucket is a slice of
 the arena and the collective needs no flatten/unflatten copies (NCCL all-reduces the slice in place over
-NVLink/NVSwitch; with NVLS the reduction happens in the switch).  A post-accumulate-grad hook per parameter counts
-the bucket down; the last arrival launches `all_reduce(AVG)` asynchronously (NCCL's own stream), and an autograd
-engine callback queued by the first hook waits for all buckets at the end of backward.  If an optimizer sets grads
-to None (`zero_grad()` default), the next backward hands fresh tensors to the hook, which copies them into the
-arena (one multi-tensor copy per bucket) and re-points `param.grad`.
+NVLink/NVSwitch; with NVLS the reduction happens in the switch).
+
+How gradients reach the arena:
+  * the libcnx autograd Functions (ops.py: Block, stem, head) find a `_GradSink` on their parameters and have their weight-
+    gradient kernels write — or, under gradient accumulation, accumulate — STRAIGHT into the parameter's arena slot (the
+    kernels' `out` / `accumulate` arguments); they return no gradient for those parameters, so autograd allocates nothing
+    and copies nothing, and they report the parameter ready themselves;
+  * every other parameter goes through a post-accumulate-grad hook: if `zero_grad()` had set the gradient to None, autograd
+    hands the hook a fresh tensor, which is copied into the arena (one multi-tensor copy per bucket) and `param.grad`
+    re-pointed.
+When a bucket's last parameter is ready its `all_reduce(AVG)` is launched asynchronously (NCCL's own stream, overlapped with
+the rest of backward); an autograd-engine callback queued by the first arrival waits for all buckets at the end of backward.
+`overlap=False` (or CNX_DDP_OVERLAP=0) instead issues ONE all-reduce of the whole arena at the end of backward: on
+NVLink 5 / NVSwitch the exposed transfer is a few hundred microseconds, and no NCCL CTA competes for SMs with the persistent
+one-CTA-per-SM compute kernels of backward.
 
 On a CPU process group (gloo; used by the CPU tests) AVG is not available, so SUM + in-place divide is used.
 """
 from __future__ import annotations
 
+import os
+import weakref
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+
+
+from . import ops
+
+
+def _padded(numel: int) -> int:
+    """arena slots start on 16-byte boundaries (the kernels' 128-bit paths); the padding words stay zero"""
+    return (numel + 3) // 4 * 4
+
+
+class _GradSink:
+    """What ops.py finds for a parameter (ops.register_grad_sink): where to write its gradient, and whom to tell."""
+
+    def __init__(self, ddp):
+        self._ddp = weakref.ref(ddp)
+
+    def claim(self, p):
+        """-> (arena view shaped like p, accumulate flag) or None when this backward must go through autograd's own
+        accumulation (reducer gone, or `p.grad` is a tensor that is not this parameter's arena slot)."""
+        ddp = self._ddp()
+        if ddp is None or not ddp._sinks_enabled:
+            return None
+        view = ddp._slot[p][1]
+        g = p.grad
+        if g is None:
+            return view, 0
+        if g.data_ptr() == view.data_ptr():
+            return view, 1
+        return None
+
+    def ready(self, p):
+        ddp = self._ddp()
+        if p.grad is None:
+            p.grad = ddp._slot[p][1]
+        ddp._ready(p)
 
 
 class _Bucket:
@@ -33,8 +81,13 @@ class _Bucket:
 
 class DistributedDataParallel(nn.Module):
     def __init__(self, module: nn.Module, device_ids=None, output_device=None, find_unused_parameters: bool = False,
-                 bucket_cap_mb: float = 25.0, process_group=None, broadcast_buffers: bool = True):
+                 bucket_cap_mb: float = 25.0, process_group=None, broadcast_buffers: bool = True, overlap=None,
+                 direct_grads: bool = True):
         super().__init__()
+        if overlap is None:
+            overlap = os.environ.get("CNX_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
+        self._sinks_enabled = bool(direct_grads) and os.environ.get("CNX_DDP_DIRECT", "1") != "0"
         if find_unused_parameters:
             raise NotImplementedError("find_unused_parameters=True is not supported (the reference passes False, "
                                       "train.py:220: every parameter receives a gradient every step)")
@@ -61,23 +114,25 @@ class DistributedDataParallel(nn.Module):
         cur, off = _Bucket(), 0
         for p in reversed(params):
             limit = first_cap if not self.buckets else cap
-            if cur.params and cur.numel + p.numel() > limit:
+            if cur.params and cur.numel + _padded(p.numel()) > limit:
                 self.buckets.append(cur)
                 cur = _Bucket()
                 cur.offset = off
             cur.params.append(p)
-            cur.numel += p.numel()
-            off += p.numel()
+            cur.numel += _padded(p.numel())
+            off += _padded(p.numel())
         self.buckets.append(cur)
         self.arena = torch.zeros(off, dtype=dt, device=dev)
         self._slot = {}
+        sink = _GradSink(self)
         for bi, b in enumerate(self.buckets):
             b.flat = self.arena[b.offset:b.offset + b.numel]
             o = b.offset
             for p in b.params:
                 self._slot[p] = (bi, self.arena[o:o + p.numel()].view_as(p))
-                o += p.numel()
+                o += _padded(p.numel())
                 p.register_post_accumulate_grad_hook(self._hook)
+                ops.register_grad_sink(p, sink)
         self._armed = False
         self.comm_bytes_per_step = self.arena.numel() * self.arena.element_size()
 
@@ -98,18 +153,24 @@ class DistributedDataParallel(nn.Module):
 
     def _hook(self, p):
         if not self._armed:
-            self._arm()
+            self._arm()                      # (resets the buckets' stale lists: must precede the append below)
         bi, view = self._slot[p]
-        b = self.buckets[bi]
         if p.grad.data_ptr() != view.data_ptr():
-            b.stale.append((view, p.grad))
+            self.buckets[bi].stale.append((view, p.grad))
             p.grad = view
+        self._ready(p)
+
+    def _ready(self, p):
+        """`p.grad` is this backward's gradient (in the arena, or queued for the copy into it): count its bucket down."""
+        if not self._armed:
+            self._arm()
+        b = self.buckets[self._slot[p][0]]
         b.pending -= 1
         if b.pending == 0:
             if b.stale:
                 torch._foreach_copy_([v for v, _ in b.stale], [g for _, g in b.stale])
                 b.stale = []
-            if self.world_size > 1:
+            if self.world_size > 1 and self.overlap:
                 op = dist.ReduceOp.AVG if self._avg_native else dist.ReduceOp.SUM
                 b.handle = dist.all_reduce(b.flat, op=op, group=self.process_group, async_op=True)
 
@@ -119,6 +180,13 @@ class DistributedDataParallel(nn.Module):
             if b.pending != 0:
                 raise RuntimeError("DistributedDataParallel: a parameter received no gradient in this backward "
                                    "(find_unused_parameters is not supported)")
+        if self.world_size > 1 and not self.overlap:
+            op = dist.ReduceOp.AVG if self._avg_native else dist.ReduceOp.SUM
+            dist.all_reduce(self.arena, op=op, group=self.process_group)
+            if not self._avg_native:
+                self.arena.div_(self.world_size)
+            return
+        for b in self.buckets:
             if b.handle is not None:
                 b.handle.wait()
                 b.handle = None

@@ -169,14 +169,56 @@ def _conv_weight_tap_major(conv_w: torch.Tensor) -> torch.Tensor:
     return _derived((conv_w,), ("tapmajor",), build)
 
 
-def _wgrad(X, Y, M, N1, N2, want_colsum: bool):
+# Gradient sinks: a data-parallel reducer (ddp.DistributedDataParallel) registers, per parameter, an object that names the
+# buffer this parameter's gradient should be written into (a slot of its flat arena).  The backward functions below then point
+# their weight-gradient kernels' `out` / `accumulate` arguments at that slot, return None for the parameter (autograd neither
+# allocates nor copies anything) and report the parameter ready.  Kept out of the parameters' __dict__ on purpose: whole-model
+# pickling (utils.py:542) serialises parameter attributes.
+_GRAD_SINKS = weakref.WeakKeyDictionary()
+
+
+def register_grad_sink(param: torch.Tensor, sink) -> None:
+    _GRAD_SINKS[param] = sink
+
+
+class _Dest:
+    """Destination of one kernel's group of parameter gradients (e.g. fc1 weight + bias): either every parameter's arena slot
+    (`sunk`), or fresh tensors that are returned to autograd.  One accumulate flag per group, as the kernels have."""
+    __slots__ = ("bufs", "acc", "sink", "params")
+
+    def __init__(self, params, shapes):
+        self.params = params
+        self.sink, self.acc = None, 0
+        sinks = [_GRAD_SINKS.get(p) if (p is not None and p.requires_grad) else None for p in params]
+        if sinks[0] is not None and all(s is sinks[0] for s in sinks):
+            claims = [sinks[0].claim(p) for p in params]
+            if all(c is not None for c in claims) and len({c[1] for c in claims}) == 1:
+                self.bufs = [c[0] for c in claims]
+                self.acc = claims[0][1]
+                self.sink = sinks[0]
+                return
+        dev = next(p for p in params if p is not None).device
+        self.bufs = [torch.empty(sh, dtype=torch.float32, device=dev) if p is not None else None for p, sh in zip(params, shapes)]
+
+    def results(self):
+        """after the kernels were enqueued: what backward returns for these parameters"""
+        if self.sink is None:
+            return self.bufs
+        for p in self.params:
+            self.sink.ready(p)
+        return [None] * len(self.bufs)
+
+
+def _wgrad(X, Y, M, N1, N2, want_colsum: bool, out=None, cs=None, accumulate: int = 0):
     lib = L.load()
     d = L.dt(X)
     ws_bytes = lib.cnx_gemm_wgrad_workspace_bytes(M, N1, N2, d, GEMM_FLAGS)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=X.device)
-    out = torch.empty((N1, N2), dtype=torch.float32, device=X.device)
-    cs = torch.empty((N1,), dtype=torch.float32, device=X.device) if want_colsum else None
-    L.check(lib.cnx_gemm_wgrad(L.ptr(X), L.ptr(Y), M, N1, N2, 0, L.ptr(out), L.ptr(cs), L.ptr(ws), ws_bytes, d,
+    if out is None:
+        out = torch.empty((N1, N2), dtype=torch.float32, device=X.device)
+    if cs is None and want_colsum:
+        cs = torch.empty((N1,), dtype=torch.float32, device=X.device)
+    L.check(lib.cnx_gemm_wgrad(L.ptr(X), L.ptr(Y), M, N1, N2, int(accumulate), L.ptr(out), L.ptr(cs), L.ptr(ws), ws_bytes, d,
                                GEMM_FLAGS, L.stream()), "gemm_wgrad")
     return out, cs
 
@@ -250,6 +292,7 @@ class _BlockFn(torch.autograd.Function):
             ctx.save_for_backward(xl, y, xn, mean, rstd, h, g, conv_w, ln_w, w1, w2, b2, gamma, dp)
             ctx.shape = (N, C, H, W)
             ctx.act_dtype = act_dtype
+            ctx.params = (conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma)     # the leaves themselves (gradient sinks)
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -277,35 +320,40 @@ class _BlockFn(torch.autograd.Function):
         L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
                 "gemm_dgrad_gelu_bwd")
         # 3. fc2 wgrad on the UNSCALED gradient; layer-scale identities give dW2, db2, dgamma without saving z
+        p_conv_w, p_conv_b, p_ln_w, p_ln_b, p_w1, p_b1, p_w2, p_b2, p_gamma = ctx.params
         G2, s = _wgrad(dz, g, M, C, C4, True)
-        dW2 = torch.empty_like(w2)
-        db2 = torch.empty_like(b2)
-        dgamma = torch.empty_like(gamma) if gamma is not None else None
-        L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, 0,
+        d_fc2 = _Dest((p_w2, p_b2, p_gamma), (w2.shape, b2.shape, (C,)))
+        dW2, db2, dgamma = d_fc2.bufs
+        L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, d_fc2.acc,
                                             L.ptr(dW2), L.ptr(db2), L.ptr(dgamma), st), "layerscale_finalize")
+        dW2, db2, dgamma = d_fc2.results()
         # 4. dxn = dh . W1
         w1t = _weight_prep(w1, 1, None, act_dtype)              # [C, 4C]
         dxn = torch.empty((M, C), dtype=act_dtype, device=dev)
         L.check(lib.cnx_gemm_plain(L.ptr(dh), L.ptr(w1t), None, L.ptr(dxn), ad, M, C, C4, ad, GEMM_FLAGS, st), "gemm_plain")
         # 5. fc1 wgrad + bias grad
-        dW1, db1 = _wgrad(dh, xn, M, C4, C, True)
+        d_fc1 = _Dest((p_w1, p_b1), (w1.shape, (C4,)))
+        _wgrad(dh, xn, M, C4, C, True, out=d_fc1.bufs[0], cs=d_fc1.bufs[1], accumulate=d_fc1.acc)
+        dW1, db1 = d_fc1.results()
         # 6. LayerNorm backward
         P = _num_partials(C)
         dy = torch.empty((M, C), dtype=act_dtype, device=dev)
         part = torch.empty((P, 2 * C), dtype=torch.float32, device=dev)
         L.check(lib.cnx_ln_bwd(L.ptr(dxn), ad, L.ptr(y), ad, L.ptr(mean), L.ptr(rstd), L.ptr(ln_w), M, C, L.ptr(dy), ad,
                                L.ptr(part), P, st), "ln_bwd")
-        dln = torch.empty((2 * C,), dtype=torch.float32, device=dev)
-        L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dln), st), "reduce_partials")
+        d_ln = _Dest((p_ln_w, p_ln_b), ((C,), (C,)))
+        L.check(lib.cnx_reduce_partials_split(L.ptr(part), P, C, C, d_ln.acc, L.ptr(d_ln.bufs[0]), L.ptr(d_ln.bufs[1]), st),
+                "reduce_partials_split")
+        dln_w, dln_b = d_ln.results()
         # 7. dwconv wgrad (+bias)
         # one persistent CTA per SM: (C/32 channel chunks) x Pw partial rows ~= SM count, every CTA sweeps many tiles
         Pw = max(1, min(L.load().cnx_sm_count() // max(C // 32, 1), (N * ((H + 7) // 8) * ((W + 31) // 32))))
         wpart = torch.empty((Pw, 50, C), dtype=torch.float32, device=dev)
         L.check(lib.cnx_dwconv7_wgrad(L.ptr(dy), ad, L.ptr(xl), sd, N, H, W, C, L.ptr(wpart), Pw, st), "dwconv7_wgrad")
-        dconv_w = torch.empty_like(conv_w)
-        dconv_b = torch.empty((C,), dtype=torch.float32, device=dev)
-        L.check(lib.cnx_dwconv7_wgrad_finalize(L.ptr(wpart), Pw, C, 0, L.ptr(dconv_w), L.ptr(dconv_b), st),
+        d_cv = _Dest((p_conv_w, p_conv_b), (conv_w.shape, (C,)))
+        L.check(lib.cnx_dwconv7_wgrad_finalize(L.ptr(wpart), Pw, C, d_cv.acc, L.ptr(d_cv.bufs[0]), L.ptr(d_cv.bufs[1]), st),
                 "dwconv7_wgrad_finalize")
+        dconv_w, dconv_b = d_cv.results()
         # 8. dx = dout + dwconv_dgrad(dy)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -313,7 +361,7 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
                     "dwconv7_dgrad")
             dx = dxl.permute(0, 3, 1, 2)
-        return (dx, dconv_w, dconv_b, dln[:C], dln[C:], dW1, db1, dW2, db2, dgamma, None, None, None, None)
+        return (dx, dconv_w, dconv_b, dln_w, dln_b, dW1, db1, dW2, db2, dgamma, None, None, None, None)
 
 
 def block_forward(x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps: float):
@@ -415,8 +463,8 @@ def _ln_fwd(x2, w, b, eps, out_dtype):
     return out, mean, rstd
 
 
-def _ln_bwd(dxn, y, mean, rstd, w, dy_dtype):
-    """-> dy [M,C], d ln_w [C], d ln_b [C]"""
+def _ln_bwd(dxn, y, mean, rstd, w, dy_dtype, params=None):
+    """-> dy [M,C], d ln_w [C], d ln_b [C] (None, None when `params` = (ln_w, ln_b) leaves have a gradient sink)"""
     lib = L.load()
     M, C = y.shape
     P = max(1, min(_num_partials(C), (M + 7) // 8))
@@ -424,9 +472,15 @@ def _ln_bwd(dxn, y, mean, rstd, w, dy_dtype):
     part = torch.empty((P, 2 * C), dtype=torch.float32, device=y.device)
     L.check(lib.cnx_ln_bwd(L.ptr(dxn), L.dt(dxn), L.ptr(y), L.dt(y), L.ptr(mean), L.ptr(rstd), L.ptr(w), M, C, L.ptr(dy),
                            L.dt(dy_dtype), L.ptr(part), P, L.stream()), "ln_bwd")
-    dwb = torch.empty((2 * C,), dtype=torch.float32, device=y.device)
-    L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
-    return dy, dwb[:C], dwb[C:]
+    d = _Dest(params if params is not None else (w, w), ((C,), (C,))) if params is not None else None
+    if d is None:
+        dwb = torch.empty((2 * C,), dtype=torch.float32, device=y.device)
+        L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
+        return dy, dwb[:C], dwb[C:]
+    L.check(lib.cnx_reduce_partials_split(L.ptr(part), P, C, C, d.acc, L.ptr(d.bufs[0]), L.ptr(d.bufs[1]), L.stream()),
+            "reduce_partials_split")
+    dlw, dlb = d.results()
+    return dy, dlw, dlb
 
 
 def _patch_weight(conv_w: torch.Tensor, act_dtype, channels_last_taps: bool) -> torch.Tensor:
@@ -461,16 +515,23 @@ class _StemFn(torch.autograd.Function):
         if track and any(ctx.needs_input_grad[1:5]):
             ctx.save_for_backward(A, y, mean, rstd, conv_w, ln_w)
             ctx.act_dtype = act_dtype
+            ctx.params = (conv_w, conv_b, ln_w, ln_b)
         return out.view(N, H // 4, W // 4, Cout).permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dout):
         A, y, mean, rstd, conv_w, ln_w = ctx.saved_tensors
+        p_conv_w, p_conv_b, p_ln_w, p_ln_b = ctx.params
         M, Cout = y.shape
         d2 = _nhwc(dout).reshape(M, Cout)
-        dy, dlw, dlb = _ln_bwd(d2, y, mean, rstd, ln_w, ctx.act_dtype)
-        dW, db = _wgrad(dy, A, M, Cout, A.shape[1], True)
-        return None, dW.view_as(conv_w), db, dlw, dlb, None, None, None
+        dy, dlw, dlb = _ln_bwd(d2, y, mean, rstd, ln_w, ctx.act_dtype, params=(p_ln_w, p_ln_b))
+        d = _Dest((p_conv_w, p_conv_b), (conv_w.shape, (Cout,))) if p_conv_w.is_contiguous() else None
+        if d is None:
+            dW, db = _wgrad(dy, A, M, Cout, A.shape[1], True)
+            return None, dW.view_as(conv_w), db, dlw, dlb, None, None, None
+        _wgrad(dy, A, M, Cout, A.shape[1], True, out=d.bufs[0], cs=d.bufs[1], accumulate=d.acc)   # [Cout, Cin*16] IS the conv weight's layout
+        dW, db = d.results()
+        return None, dW, db, dlw, dlb, None, None, None
 
 
 class _DownsampleFn(torch.autograd.Function):
@@ -566,6 +627,7 @@ class _HeadFn(torch.autograd.Function):
         if track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5])):
             ctx.save_for_backward(pooled, xn, mean, rstd, ln_w, fc_w)
             ctx.meta = (N, C, H, W, xl.dtype, act_dtype)
+            ctx.params = (ln_w, ln_b, fc_w, fc_b)
         return logits
 
     @staticmethod
@@ -581,8 +643,11 @@ class _HeadFn(torch.autograd.Function):
         wt = _weight_prep(fc_w, 1, None, act_dtype) if act_dtype != torch.float32 else _derived(
             (fc_w,), ("fcT",), lambda: fc_w.detach().t().contiguous())
         dxn = _gemm_plain(d, wt, None, act_dtype)
-        dW, db = _wgrad(d, xn, N, K, C, True)
-        dpooled, dlw, dlb = _ln_bwd(dxn, pooled, mean, rstd, ln_w, torch.float32)
+        p_ln_w, p_ln_b, p_fc_w, p_fc_b = ctx.params
+        dfc = _Dest((p_fc_w, p_fc_b), ((K, C), (K,)))
+        _wgrad(d, xn, N, K, C, True, out=dfc.bufs[0], cs=dfc.bufs[1], accumulate=dfc.acc)
+        dW, db = dfc.results()
+        dpooled, dlw, dlb = _ln_bwd(dxn, pooled, mean, rstd, ln_w, torch.float32, params=(p_ln_w, p_ln_b))
         dx = None
         if ctx.needs_input_grad[0]:
             dxl = torch.empty((N, H, W, C), dtype=sdt, device=d.device)

@@ -153,6 +153,10 @@ CNX_API int cnx_ln_bwd_patch2(const void* dxn, int dxn_dtype, const void* y, int
 /* out[j] = (accumulate ? out[j] : 0) + scale * sum_p partial[p, j], fixed order (deterministic). */
 CNX_API int cnx_reduce_partials(const float* partial, int P, int64_t L, float scale, int accumulate, float* out,
                         void* stream);
+/* The same over a [P, La + Lb] partial whose column halves belong to two tensors (LayerNorm: d ln_w | d ln_b), so that each
+ * half can be written — or accumulated — straight into its own gradient buffer (e.g. a slot of the data-parallel arena). */
+CNX_API int cnx_reduce_partials_split(const float* partial, int P, int64_t La, int64_t Lb, int accumulate, float* out_a,
+                              float* out_b, void* stream);
 
 /* dwconv backward-data (+ residual-gradient add): dx = dres + dwconv7x7_flipped(dy).  dres may be NULL.  wt tap-major.
  * dy [M,C] act dtype; dres, dx [M,C] stream dtype. */

@@ -1,0 +1,8 @@
+# round 2, session d: arena-direct gradients (single-rank test), full GPU suite, bench
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r02d_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 12 gpurun_out/r02d_pytest.log
+python bench.py --no-cpu-baseline --no-variants --kernels-out gpurun_out/r02d_kernels.json > gpurun_out/r02d_bench.json 2> gpurun_out/r02d_bench.err; echo "bench rc=$?"
+python -c "
+import json
+d=json.loads(open('gpurun_out/r02d_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['roofline']['cnx_kernels_ms_per_step'], d['gpu_launches'])"

@@ -33,7 +33,9 @@ def _worker(rank, world, port, ret):
         ref = _model(100)
         for p, q in zip(model.parameters(), ref.parameters()):
             assert torch.equal(p, q)
-        assert sum(b.numel for b in ddp.buckets) == sum(p.numel() for p in model.parameters()) == ddp.arena.numel()
+        # every parameter has its own slot; slots start on 16-byte boundaries, so the arena may be a few words larger
+        assert sum(b.numel for b in ddp.buckets) == ddp.arena.numel() >= sum(p.numel() for p in model.parameters())
+        assert ddp.arena.numel() - sum(p.numel() for p in model.parameters()) < 4 * len(list(model.parameters()))
         assert len(ddp.buckets) > 2
         g = torch.Generator().manual_seed(7)
         X = torch.randn(2 * world, 3, 6, 6, generator=g)

@@ -87,3 +87,61 @@ def test_ddp_world2_nccl_matches_single_process(amp):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, amp, ret), nprocs=2, join=True)
     assert all(str(ret.get(r, "")).startswith("ok") for r in (0, 1)), dict(ret)
+
+
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16"])
+def test_direct_arena_gradients_single_rank(amp):
+    """One-rank process group on one GPU: the libcnx backward functions write the Block / stem / head parameter gradients
+    straight into the reducer's arena (no autograd accumulation, no copy) — same values as the unwrapped model, with
+    zero_grad(set_to_none) between steps, gradient accumulation over two micro-steps, and `direct_grads=False` as the control."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import imageclassification_b200 as P
+    from cabi import max_rel
+    from imageclassification_b200.ddp import DistributedDataParallel
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("gloo", store=dist.HashStore(), rank=0, world_size=1)
+    try:
+        _direct_arena_body(amp, P, DistributedDataParallel, max_rel)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
+def _direct_arena_body(amp, P, DistributedDataParallel, max_rel):
+    dev = torch.device("cuda")
+    K = 8
+    x, t = _data(1, 4, K)
+    x, t = x.to(dev), t.to(dev)
+    crit = P.SoftTargetCrossEntropy()
+
+    def make():
+        torch.manual_seed(5)
+        return P.create_model("convnext_tiny", num_classes=K, ls_init_value=1.0, drop_path_rate=0.05).to(dev)
+
+    def run(model, net, accum):
+        opt = torch.optim.SGD(model.parameters(), lr=0.05)
+        torch.manual_seed(9)                                    # drop-path masks
+        for it in range(2):
+            opt.zero_grad()
+            for _ in range(accum):
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    loss = crit(net(x), t) / accum
+                loss.backward()
+            grads = [p.grad.detach().clone() for p in model.parameters()]
+            opt.step()
+        return grads
+
+    for accum in (1, 2):
+        ref = make()
+        g_ref = run(ref, ref, accum)
+        for direct in (True, False):
+            m = make()
+            ddp = DistributedDataParallel(m, device_ids=[0], bucket_cap_mb=4.0, direct_grads=direct)
+            g = run(m, ddp, accum)
+            for (n, p), a, b, q in zip(m.named_parameters(), g, g_ref, ref.parameters()):
+                assert p.grad.untyped_storage().data_ptr() == ddp.arena.untyped_storage().data_ptr(), n
+                assert p.grad.data_ptr() == ddp._slot[p][1].data_ptr(), n
+                assert torch.equal(a, b), (n, accum, direct, max_rel(a, b))
+                assert torch.equal(p.detach(), q.detach()), n
