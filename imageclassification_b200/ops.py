@@ -174,11 +174,20 @@ def _conv_weight_tap_major(conv_w: torch.Tensor) -> torch.Tensor:
 # their weight-gradient kernels' `out` / `accumulate` arguments at that slot, return None for the parameter (autograd neither
 # allocates nor copies anything) and report the parameter ready.  Kept out of the parameters' __dict__ on purpose: whole-model
 # pickling (utils.py:542) serialises parameter attributes.
-_GRAD_SINKS = weakref.WeakKeyDictionary()
+_GRAD_SINKS: dict = {}          # id(param) -> (weakref to param, sink); tensors cannot key a WeakKeyDictionary (== is elementwise)
 
 
 def register_grad_sink(param: torch.Tensor, sink) -> None:
-    _GRAD_SINKS[param] = sink
+    key = id(param)
+    _GRAD_SINKS[key] = (weakref.ref(param), sink)
+    weakref.finalize(param, _GRAD_SINKS.pop, key, None)
+
+
+def _sink_of(param):
+    if param is None or not param.requires_grad:
+        return None
+    e = _GRAD_SINKS.get(id(param))
+    return e[1] if (e is not None and e[0]() is param) else None
 
 
 class _Dest:
@@ -189,7 +198,7 @@ class _Dest:
     def __init__(self, params, shapes):
         self.params = params
         self.sink, self.acc = None, 0
-        sinks = [_GRAD_SINKS.get(p) if (p is not None and p.requires_grad) else None for p in params]
+        sinks = [_sink_of(p) for p in params]
         if sinks[0] is not None and all(s is sinks[0] for s in sinks):
             claims = [sinks[0].claim(p) for p in params]
             if all(c is not None for c in claims) and len({c[1] for c in claims}) == 1:
