@@ -134,6 +134,7 @@ class DistributedDataParallel(nn.Module):
                 p.register_post_accumulate_grad_hook(self._hook)
                 ops.register_grad_sink(p, sink)
         self._armed = False
+        self._seen = set()
         self.comm_bytes_per_step = self.arena.numel() * self.arena.element_size()
 
     def _broadcast(self, tensors):
@@ -148,6 +149,7 @@ class DistributedDataParallel(nn.Module):
     def _arm(self):
         for b in self.buckets:
             b.pending, b.handle, b.stale = len(b.params), None, []
+        self._seen = set()
         self._armed = True
         torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
 
@@ -164,6 +166,9 @@ class DistributedDataParallel(nn.Module):
         """`p.grad` is this backward's gradient (in the arena, or queued for the copy into it): count its bucket down."""
         if not self._armed:
             self._arm()
+        if id(p) in self._seen:              # a sunk parameter whose (undefined-gradient) accumulation node still ran its hook
+            return
+        self._seen.add(id(p))
         b = self.buckets[self._slot[p][0]]
         b.pending -= 1
         if b.pending == 0:
