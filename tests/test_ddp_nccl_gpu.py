@@ -143,5 +143,9 @@ def _direct_arena_body(amp, P, DistributedDataParallel, max_rel):
             for (n, p), a, b, q in zip(m.named_parameters(), g, g_ref, ref.parameters()):
                 assert p.grad.untyped_storage().data_ptr() == ddp.arena.untyped_storage().data_ptr(), n
                 assert p.grad.data_ptr() == ddp._slot[p][1].data_ptr(), n
-                assert torch.equal(a, b), (n, accum, direct, max_rel(a, b))
-                assert torch.equal(p.detach(), q.detach()), n
+                if accum == 1:
+                    assert torch.equal(a, b), (n, direct, max_rel(a, b))
+                    assert torch.equal(p.detach(), q.detach()), n
+                else:                       # accumulating kernels add with one fused rounding where autograd adds two tensors
+                    assert max_rel(a, b) <= 1e-6, (n, direct, max_rel(a, b))
+                    assert max_rel(p.detach(), q.detach()) <= 1e-6, n
