@@ -52,6 +52,10 @@ def parse():
                     help="fp32 everywhere (the reference's --use_amp false default) instead of the headline's bf16 autocast")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra timed region of the `variants` key")
     ap.add_argument("--no-acc-forward", action="store_true", help="skip the reference's accuracy forward (not the default)")
+    ap.add_argument("--update-freq", type=int, default=1,
+                    help="gradient-accumulation micro-steps per optimizer step (the reference's --update_freq, engine.py:29,63-75); "
+                         "one bench step = one optimizer step = this many micro-batches of --batch images per GPU")
+    ap.add_argument("--cutmix", type=float, default=0.0, help="cutmix alpha (train.py:72-76; BASELINE config 3 uses 1.0)")
     ap.add_argument("--kernels-out", default=None,
                     help="side file for the per-shape kernel table / family table / launch timeline "
                          "(default gpurun_out/bench_kernels_N<gpus>.json)")
@@ -59,7 +63,9 @@ def parse():
 
 
 def workload_name(a):
-    return (f"{a.model} {a.img}x{a.img} {'fp32 (no autocast)' if getattr(a, 'no_amp', False) else 'bf16 autocast'}, batch {a.batch}/GPU, {a.classes} classes, mixup 0.8 + smoothing 0.1 + "
+    uf = getattr(a, "update_freq", 1)
+    return (f"{a.model} {a.img}x{a.img} {'fp32 (no autocast)' if getattr(a, 'no_amp', False) else 'bf16 autocast'}, batch {a.batch}/GPU"
+            f"{f' x update_freq {uf}' if uf > 1 else ''}, {a.classes} classes, mixup 0.8{f' + cutmix {a.cutmix:g}' if getattr(a, 'cutmix', 0) else ''} + smoothing 0.1 + "
             f"SoftTargetCE + AdamW + ModelEmaV3(0.9995) + accuracy forward "
             f"{'under the same bf16 autocast' if getattr(a, 'acc_autocast', False) else 'in fp32 outside autocast as the reference places it'}"
             f" (engine.py:27-97)")
@@ -199,14 +205,14 @@ def kernel_work(name, a):
         # fp32-accurate GEMM on split bf16 operands: ALGORITHMIC flops are those of the fp32 product (2MNK); the kernel
         # executes 3x that on the tensor pipe by design (include/cnx.h "x3")
         M, N, K3 = a[3:6]
-        return (M * K3 + N * K3 + M * 2 * N) * 2, 2 * M * N * (K3 // 3), f"fc1_gelu_x3 K{K3 // 3}"
+        return (M * (K3 // 3) * a[7] + N * K3 + M * 2 * N) * 2, 2 * M * N * (K3 // 3), f"fc1_gelu_x3 K{K3 // 3}"
     if name == "cnx_dwconv7_ln_fwd_x3":
         N, H, W, C = a[6:10]
         MC = N * H * W * C
-        return MC * (4 + 4 + 6) + 8 * N * H * W + 52 * C * 4, 106 * MC, f"dwconv7_ln_fwd_x3 C{C} H{H}"
+        return MC * (4 + 4 + 2 * a[14]) + 8 * N * H * W + 52 * C * 4, 106 * MC, f"dwconv7_ln_fwd_x3 C{C} H{H}"
     if name == "cnx_split3":
         M, C = a[1:3]
-        return M * C * (4 + 6), 0, f"split3 C{C}"
+        return M * C * (4 + 2 * a[4]), 0, f"split3 C{C}"
     if name == "cnx_avgpool_nhwc_fwd":
         N, HW, C = a[2:5]
         return N * HW * C * es(a[1]) + N * C * 4, 0, f"avgpool_fwd C{C}"
@@ -276,7 +282,7 @@ def run_ours(a):
     else:
         opt = poptim.AdamW(groups, lr=1e-3, weight_decay=0.0)
         opt.fuse_ema(ema, model)
-    mix = P.Mixup(mixup_alpha=0.8, cutmix_alpha=0.0, label_smoothing=0.1, num_classes=a.classes)     # train.py:176-185
+    mix = P.Mixup(mixup_alpha=0.8, cutmix_alpha=a.cutmix, label_smoothing=0.1, num_classes=a.classes)     # train.py:176-185
     crit = P.SoftTargetCrossEntropy()
 
     B = a.batch
@@ -291,7 +297,7 @@ def run_ours(a):
     def epoch(batches):
         if a.no_acc_forward:
             return _fast_epoch(batches)
-        return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=1, use_amp=not a.no_amp,
+        return pengine.train_one_epoch(net, crit, batches, opt, dev, 0, None, 0, ema, mix, update_freq=a.update_freq, use_amp=not a.no_amp,
                                        num_classes=a.classes, verbose=False, prefetch=not a.no_prefetch,
                                        acc_forward_fp32=acc_fp32[0], tune_gc=os.environ.get("CNX_ENGINE_TUNE_GC", "1") != "0")
 
@@ -332,7 +338,7 @@ def run_ours(a):
     last_batches = [None]
 
     def timed(batches_src, steps):
-        batches = _Stamped(batches_src[i % len(batches_src)] for i in range(steps))
+        batches = _Stamped(batches_src[i % len(batches_src)] for i in range(steps * a.update_freq))
         last_batches[0] = batches
         # Python's cyclic garbage collector is switched off inside a timed region, as `timeit` does: a generation-2 pass was
         # measured to stop the launching thread for 40-190 ms at a fixed step of the run (one long host interval, always the
@@ -411,7 +417,7 @@ def run_ours(a):
             ms_v, _ = timed(devb, a.steps)
             acc_fp32[0] = not acc_fp32[0]
             variants = {("accuracy_forward_fp32_outside_autocast" if a.acc_autocast else "accuracy_forward_under_bf16_autocast"):
-                        {"value": round(B * world * a.steps / (ms_v * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_v / a.steps, 3)}}
+                        {"value": round(B * world * a.steps * a.update_freq / (ms_v * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_v / a.steps, 3)}}
     clocks = clk.summary()
 
     # per-kernel breakdown pass (untimed for the headline): every C-ABI call bracketed by CUDA events
@@ -428,14 +434,14 @@ def run_ours(a):
         table, families, roof = roofline_tables(recs, bsteps, peaks, ms_b)
         timeline = timeline_summary(tl, bsteps)
 
-    imgs = B * world * a.steps
+    imgs = B * world * a.steps * a.update_freq
     out = {
         "metric": METRIC, "value": round(imgs / (ms_dev * 1e-3), 1), "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms_dev / a.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if a.no_amp else "bf16", "data": "synthetic (randn images, random labels; random-init weights)",
         "config": config_dict(a, world),
         "e2e": {"value": round(imgs / (ms_e2e * 1e-3), 1), "unit": UNIT,
-                "h2d_bytes_per_step": B * 3 * a.img * a.img * 4 + B * 8, "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": (B * 3 * a.img * a.img * 4 + B * 8) * a.update_freq, "d2h_bytes_per_step": 4 * a.update_freq,
                 "ms_per_step": round(ms_e2e / a.steps, 3), "host_buffers_pinned": pinned, "h2d_link_GBps": h2d_gbps,
                 "api": "engine.train_one_epoch on pinned host batches"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "families": families,
@@ -473,7 +479,7 @@ def run_ours(a):
 
 def config_dict(a, world):
     """`config` of the JSON line: identical for this arm and for `--impl reference` (the driver compares them)."""
-    return {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": f"dp{world}",
+    return {"workload": workload_name(a), "global_batch": a.batch * world * getattr(a, "update_freq", 1), "parallelism": f"dp{world}",
             "l2": "per-step activation footprint >> 126 MB L2 (inputs larger than L2, no explicit flush)"}
 
 

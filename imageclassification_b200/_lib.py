@@ -63,9 +63,9 @@ SIGNATURES = {
     "cnx_dwconv7_wgrad_finalize": (c_int, [_P, _I, _L, _I, _P, _P, _P]),
     "cnx_gemm_bias_gelu_fwd": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P, _I, _I, _P]),
     "cnx_gemm_bias_scale_residual_fwd": (c_int, [_P, _P, _P, _P, _P, _L, _P, _P, _I, _L, _L, _L, _I, _I, _P]),
-    "cnx_split3": (c_int, [_P, _L, _L, _P, _P]),
-    "cnx_dwconv7_ln_fwd_x3": (c_int, [_P, _P, _P, _P, _P, _F, _L, _L, _L, _L, _P, _P, _P, _P, _P]),
-    "cnx_gemm_bias_gelu_fwd_x3": (c_int, [_P, _P, _P, _L, _L, _L, _P, _P]),
+    "cnx_split3": (c_int, [_P, _L, _L, _P, _I, _P]),
+    "cnx_dwconv7_ln_fwd_x3": (c_int, [_P, _P, _P, _P, _P, _F, _L, _L, _L, _L, _P, _P, _P, _P, _I, _P]),
+    "cnx_gemm_bias_gelu_fwd_x3": (c_int, [_P, _P, _P, _L, _L, _L, _P, _I, _P]),
     "cnx_mlp_fused_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _L, _P]),
     "cnx_gemm_dgrad_gelu_bwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _P]),
     "cnx_gemm_plain": (c_int, [_P, _P, _P, _P, _I, _L, _L, _L, _I, _I, _P]),

@@ -50,7 +50,8 @@ int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* 
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
                      int64_t H, int64_t W, int64_t C, cudaStream_t s);
 int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
-                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, float* mean, float* rstd, cudaStream_t s);
+                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, int segments, float* mean, float* rstd,
+                         cudaStream_t s);
 int dwconv7_wgrad_v2(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W, int64_t C,
                      float* partial, int P, cudaStream_t s);
 }  // namespace cnx
@@ -77,11 +78,12 @@ int cnx_dwconv7_ln_fwd(const void* x, int x_dtype, const float* wt, const float*
 
 int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
                           int64_t N, int64_t H, int64_t W, int64_t C, float* y_scratch, void* xn3, float* mean, float* rstd,
-                          void* stream) {
+                          int segments, void* stream) {
   CNX_REQUIRE(x && wt && bias && ln_w && ln_b && y_scratch && xn3 && mean && rstd, CNX_E_BADARG, "dwconv7_ln_fwd_x3: null pointer");
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_ln_fwd_x3: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_ln_fwd_x3: C=%lld must be a multiple of 32", (long long)C);
-  return dwconv7_ln_fwd_x3_v2(x, wt, bias, ln_w, ln_b, eps, N, H, W, C, y_scratch, xn3, mean, rstd, (cudaStream_t)stream);
+  CNX_REQUIRE(segments == 2 || segments == 3, CNX_E_BADARG, "dwconv7_ln_fwd_x3: segments must be 2 ([hi | mid]) or 3 ([hi | mid | hi])");
+  return dwconv7_ln_fwd_x3_v2(x, wt, bias, ln_w, ln_b, eps, N, H, W, C, y_scratch, xn3, segments, mean, rstd, (cudaStream_t)stream);
 }
 
 int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype,

@@ -123,7 +123,7 @@ __device__ __forceinline__ uint4 pack16(const float (&v)[4], float*) {
 
 // fp32-accurate forward ("x3", include/cnx.h): the normalised row leaves as the A-side split operand [hi | mid | hi] (bf16,
 // row stride 3C) instead of fp32 xn — 4 values per lane, three 8-byte stores
-__device__ __forceinline__ void store_split3(bf16* row3, int C, int col, const float (&x)[4]) {
+__device__ __forceinline__ void store_split3(bf16* row3, int C, int col, const float (&x)[4], bool third) {
   uint2 hi, mid;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(x[1]), "f"(x[0]));
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(x[3]), "f"(x[2]));
@@ -133,9 +133,9 @@ __device__ __forceinline__ void store_split3(bf16* row3, int C, int col, const f
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.y) : "f"(r3), "f"(r2));
   *reinterpret_cast<uint2*>(row3 + col) = hi;
   *reinterpret_cast<uint2*>(row3 + C + col) = mid;
-  *reinterpret_cast<uint2*>(row3 + 2 * C + col) = hi;
+  if (third) *reinterpret_cast<uint2*>(row3 + 2 * C + col) = hi;      // 2-segment form: the consuming GEMM's K loop wraps instead
 }
-__device__ __forceinline__ void store_split3(bf16*, int, int, const float (&)[8]) {}   // bf16 activations: never taken
+__device__ __forceinline__ void store_split3(bf16*, int, int, const float (&)[8], bool) {}   // bf16 activations: never taken
 
 // tile pixel slot p (row-major over [NB][ROWS][TW]) -> global pixel index, or -1 outside the tensor
 template <class G, bool EXACT>
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(ConvCfg<G, MODE, TIN, TOUT>::NT, 1)
 dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, int N, int H, int W, int C,
                   int tiles_x, int tiles_y, int ntiles, const float* __restrict__ bias, const TOUT* __restrict__ dres,
                   TOUT* out, const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, TOUT* __restrict__ xn,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ xn3) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, bf16* __restrict__ xn3, int xseg) {
   typedef ConvCfg<G, MODE, TIN, TOUT> Cfg;
   constexpr int STAGES = Cfg::STAGES, NWC = Cfg::NWC, NLN = Cfg::NLN;
   constexpr int NPIX = G::CPW * G::TH;
@@ -335,7 +335,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               unpack16(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
               for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-              if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mm[u] * 3 * C, C, v * VEC, x);
+              if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mm[u] * xseg * C, C, v * VEC, x, xseg == 3);
               else *reinterpret_cast<uint4*>(xn + off[u]) = pack16(x, (TOUT*)nullptr);
             }
           }
@@ -382,7 +382,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   unpack16(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
                   for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-                  if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mrow[u] * 3 * C, C, v * VEC, x);
+                  if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mrow[u] * xseg * C, C, v * VEC, x, xseg == 3);
                   else *reinterpret_cast<uint4*>(xn + mrow[u] * C + v * VEC) = pack16(x, (TOUT*)nullptr);
                 }
               }
@@ -399,7 +399,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 template <class G, int MODE, typename TIN, typename TOUT, bool EXACT>
 static int launch_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                        const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
-                       int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr) {
+                       int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr, int xseg = 3) {
   typedef ConvCfg<G, MODE, TIN, TOUT> Cfg;
   CUtensorMap tmX, tmW;
   if (int rc = make_map_nhwc(&tmX, x, x_dtype, N, H, W, C, G::HW, G::HH, G::NB)) return rc;
@@ -413,20 +413,20 @@ static int launch_conv(const void* x, int x_dtype, const float* wt, const float*
   int grid = sm_count();
   if (grid > nt) grid = (int)nt;
   launch_pdl(k, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, s, tmX, tmW, (int)N, (int)H, (int)W, (int)C, tiles_x, tiles_y, (int)nt, bias,
-             (const TOUT*)dres, (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd, (bf16*)xn3);
+             (const TOUT*)dres, (TOUT*)out, ln_w, ln_b, eps, (TOUT*)xn, mean, rstd, (bf16*)xn3, xseg);
   return check_launch(MODE == MODE_FWD ? "dwconv7_ln_fwd" : "dwconv7_dgrad");
 }
 
 template <int MODE, typename TIN, typename TOUT>
 static int pick_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                      const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
-                     int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr) {
+                     int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr, int xseg = 3) {
   const int gid = pick_geo(N, H, W);
   CNX_GEO_SWITCH(gid, {
     const bool exact = (W % G::TW == 0) && (H % G::ROWS == 0) && (N % G::NB == 0);
     if (exact)
-      return launch_conv<G, MODE, TIN, TOUT, true>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3);
-    return launch_conv<G, MODE, TIN, TOUT, false>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3);
+      return launch_conv<G, MODE, TIN, TOUT, true>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3, xseg);
+    return launch_conv<G, MODE, TIN, TOUT, false>(x, x_dtype, wt, bias, dres, out, ln_w, ln_b, eps, xn, mean, rstd, N, H, W, C, s, xn3, xseg);
   });
   return CNX_E_BADARG;
 }
@@ -612,9 +612,11 @@ int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* 
 
 // fp32 stream, fp32 conv + LayerNorm; the normalised rows leave as the split operand xn3 bf16 [M, 3C]; y is fp32 scratch
 int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
-                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, float* mean, float* rstd, cudaStream_t s) {
+                         int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, int segments, float* mean, float* rstd,
+                         cudaStream_t s) {
   using namespace dw2;
-  return pick_conv<MODE_FWD, float, float>(x, CNX_F32, wt, bias, nullptr, y, ln_w, ln_b, eps, y, mean, rstd, N, H, W, C, s, xn3);
+  return pick_conv<MODE_FWD, float, float>(x, CNX_F32, wt, bias, nullptr, y, ln_w, ln_b, eps, y, mean, rstd, N, H, W, C, s, xn3,
+                                           segments);
 }
 
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,

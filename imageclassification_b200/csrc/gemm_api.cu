@@ -41,11 +41,14 @@ int cnx_gemm_bias_gelu_fwd(const void* A, const void* W1, const float* b1, int64
 }
 
 int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3, void* g3,
-                              void* stream) {
+                              int a_segments, void* stream) {
   CNX_REQUIRE(A3 && W3 && b1 && g3, CNX_E_BADARG, "gemm_bias_gelu_fwd_x3: null pointer");
   CNX_REQUIRE(M > 0 && N > 0 && K3 > 0 && K3 % 24 == 0, CNX_E_BADARG, "gemm_bias_gelu_fwd_x3: bad shape (K3 = 3K, K %% 8 == 0)");
   CNX_REQUIRE(N % 32 == 0, CNX_E_SHAPE, "gemm_bias_gelu_fwd_x3: N=%lld must be a multiple of 32", (long long)N);
+  CNX_REQUIRE(a_segments == 3 || (a_segments == 2 && (K3 / 3) % 32 == 0), CNX_E_SHAPE,
+              "gemm_bias_gelu_fwd_x3: a_segments must be 3, or 2 with K3/3 a multiple of 32 (K3=%lld)", (long long)K3);
   EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, nullptr, g3, N};
+  if (a_segments == 2) ep.a_wrap = (int32_t)(2 * (K3 / 3));      // the K loop's third segment re-reads A's hi columns
   return gemm_tn_tc<EPI_BIAS_GELU3, bf16>(A3, W3, M, N, K3, ep, (cudaStream_t)stream);
 }
 
@@ -102,6 +105,11 @@ int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, i
   CNX_REQUIRE(dtype_ok(out_dtype), CNX_E_BADARG, "gemm_plain: bad out dtype");
   EpiParams ep = {bias, nullptr, nullptr, 1, nullptr, out, nullptr, N};
   cudaStream_t s = (cudaStream_t)stream;
+  if (flags & CNX_GEMM_A_SPLIT2) {
+    CNX_REQUIRE(dtype == CNX_BF16 && !(flags & CNX_GEMM_FORCE_SIMT) && K % 3 == 0 && (K / 3) % 32 == 0, CNX_E_SHAPE,
+                "gemm_plain: CNX_GEMM_A_SPLIT2 needs bf16 operands and K/3 a multiple of 32 (K=%lld)", (long long)K);
+    ep.a_wrap = (int32_t)(2 * (K / 3));
+  }
   if (dtype == CNX_F32) {
     CNX_REQUIRE(out_dtype == CNX_F32, CNX_E_BADARG, "gemm_plain: fp32 operands need an fp32 output");
     return gemm_tn_simt<float, float, EPI_PLAIN>(A, B, M, N, K, ep, s);

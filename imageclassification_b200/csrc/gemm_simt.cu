@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(256) grad_prep_kernel(const TS* __restrict__ d
 }
 
 // fp32 [M, C] -> bf16 [M, 3C] = [hi | mid | hi]: the A-side split operand (x ~ hi + mid to 2^-17 relative); 8 elements per thread
-__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int64_t M, int64_t C, bf16* __restrict__ out) {
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int64_t M, int64_t C, bf16* __restrict__ out,
+                                                     int seg) {
   pdl_wait();
   const int64_t vpr = C >> 3, total = M * vpr;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
@@ -218,10 +219,10 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
       r[2 * k] = a[2 * k] - __low2float(h2[k]);
       r[2 * k + 1] = a[2 * k + 1] - __high2float(h2[k]);
     }
-    bf16* o = out + m * 3 * C + v * 8;
+    bf16* o = out + m * seg * C + v * 8;
     *reinterpret_cast<uint4*>(o) = hi;
     store8(o + C, r);
-    *reinterpret_cast<uint4*>(o + 2 * C) = hi;
+    if (seg == 3) *reinterpret_cast<uint4*>(o + 2 * C) = hi;
   }
 }
 
@@ -392,14 +393,14 @@ int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const float* row_s
   return check_launch("weight_prep");
 }
 
-int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream) {
-  CNX_REQUIRE(x && out && M > 0 && C > 0, CNX_E_BADARG, "split3: bad argument");
+int cnx_split3(const float* x, int64_t M, int64_t C, void* out, int segments, void* stream) {
+  CNX_REQUIRE(x && out && M > 0 && C > 0 && (segments == 2 || segments == 3), CNX_E_BADARG, "split3: bad argument");
   CNX_REQUIRE(C % 8 == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0, CNX_E_SHAPE,
               "split3: C=%lld must be a multiple of 8 and the pointers 16-byte aligned", (long long)C);
   const int64_t total = M * (C / 8);
   int64_t grid = (total + 255) / 256;
   if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-  launch_pdl(split3_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, x, M, C, (bf16*)out);
+  launch_pdl(split3_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, x, M, C, (bf16*)out, segments);
   return check_launch("split3");
 }
 

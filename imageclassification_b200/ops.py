@@ -259,12 +259,12 @@ class _BlockFn(torch.autograd.Function):
             # fp32 no-grad pass on the tensor cores: split operands [hi | mid | hi] x [hi | hi | mid], K' = 3K; the LayerNorm half
             # of the dwconv kernel writes the split operand itself
             bf = torch.bfloat16
-            a3 = torch.empty((M, 3 * C), dtype=bf, device=dev)
+            a3 = torch.empty((M, 2 * C), dtype=bf, device=dev)             # [hi | mid] of xn: fc1's K loop wraps for the third segment
             L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(xl), L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C,
-                                              L.ptr(y), L.ptr(a3), L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd_x3")
+                                              L.ptr(y), L.ptr(a3), L.ptr(mean), L.ptr(rstd), 2, st), "dwconv7_ln_fwd_x3")
             g2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)            # [hi | mid] of g
             L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), M, C4, 3 * C,
-                                                  L.ptr(g2), st), "gemm_bias_gelu_fwd_x3")
+                                                  L.ptr(g2), 2, st), "gemm_bias_gelu_fwd_x3")
             del a3
             out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
             # (running fc1 -> fc2 over L2-sized row blocks so that g never reaches HBM was measured SLOWER: 36.9-41.1 ms/step
@@ -452,12 +452,13 @@ def _gemm_plain_x3(A, conv_w, channels_last_taps: bool, bias):
         L.check(lib.cnx_weight_prep(L.ptr(w2), w2.shape[0], w2.shape[1], None, 3, L.ptr(out), L.dt(bf), L.stream()), "weight_prep(x3)")
         return out
     B3 = _derived((conv_w,), ("patchw_x3", channels_last_taps), build)
-    a3 = torch.empty((M, 3 * K), dtype=bf, device=A.device)
-    L.check(lib.cnx_split3(L.ptr(A), M, K, L.ptr(a3), L.stream()), "split3")
+    seg2 = K % 32 == 0                                         # two segments + a wrapping K loop where the segment is whole 16-column MMA slices
+    a3 = torch.empty((M, (2 if seg2 else 3) * K), dtype=bf, device=A.device)
+    L.check(lib.cnx_split3(L.ptr(A), M, K, L.ptr(a3), 2 if seg2 else 3, L.stream()), "split3")
     Nn = B3.shape[0]
     out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
-    L.check(lib.cnx_gemm_plain(L.ptr(a3), L.ptr(B3), L.ptr(bias), L.ptr(out), L.dt(torch.float32), M, Nn, 3 * K, L.dt(bf), 0,
-                               L.stream()), "gemm_plain(x3)")
+    L.check(lib.cnx_gemm_plain(L.ptr(a3), L.ptr(B3), L.ptr(bias), L.ptr(out), L.dt(torch.float32), M, Nn, 3 * K, L.dt(bf),
+                               L.CNX_GEMM_A_SPLIT2 if seg2 else 0, L.stream()), "gemm_plain(x3)")
     return out
 
 

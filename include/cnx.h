@@ -178,8 +178,9 @@ CNX_API int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, i
  * kernel (test-only cross-check of the tensor-core path).
  * ---------------------------------------------------------------------------------------------- */
 #define CNX_GEMM_FORCE_SIMT 1
-/* cnx_gemm_bias_scale_residual_fwd only: A is a two-segment split operand [hi | mid] with 2K/3 columns (written by
- * cnx_gemm_bias_gelu_fwd_x3); the K loop covers three segments and the third re-reads the first ([hi | mid | hi]). */
+/* cnx_gemm_bias_scale_residual_fwd / cnx_gemm_plain: A is a two-segment split operand [hi | mid] with 2K/3 columns (written by
+ * cnx_gemm_bias_gelu_fwd_x3, or by cnx_split3 / cnx_dwconv7_ln_fwd_x3 with segments = 2); the K loop covers three segments and
+ * the third re-reads the first ([hi | mid | hi]) — the operand crosses HBM as 2 pieces instead of 3. */
 #define CNX_GEMM_A_SPLIT2 2
 
 /* fc1: h = round_dtype(A.W1^T + b1) ; g_out = GELU_erf(h) ; gprime_out = GELU_erf'(h) (what backward needs of h:
@@ -205,14 +206,17 @@ CNX_API int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, cons
  *   fc2: cnx_gemm_bias_scale_residual_fwd(A = g2, W2 = mode-3 weight, K = 3*4C, dtype = CNX_BF16, stream_dtype = CNX_F32,
  *        flags = CNX_GEMM_A_SPLIT2: the third K segment re-reads g2's hi columns, so g leaves and re-enters HBM as 2 pieces)
  *   plain: cnx_gemm_plain(A3, B3, ..., out fp32, K = 3K, dtype = CNX_BF16) */
-CNX_API int cnx_split3(const float* x, int64_t M, int64_t C, void* out, void* stream);
+/* `segments` = 3: out [M,3C] = [hi | mid | hi];  `segments` = 2: out [M,2C] = [hi | mid] for a consumer that wraps its K loop
+ * (CNX_GEMM_A_SPLIT2 / a_segments = 2). */
+CNX_API int cnx_split3(const float* x, int64_t M, int64_t C, void* out, int segments, void* stream);
 /* cnx_dwconv7_ln_fwd on an fp32 stream whose LayerNorm rows leave directly as the A-side split operand xn3 bf16 [M,3C]
  * (no fp32 xn, no separate cnx_split3 pass).  y_scratch fp32 [M,C] holds the conv output between the two halves of the kernel. */
 CNX_API int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
                           float eps, int64_t N, int64_t H, int64_t W, int64_t C, float* y_scratch, void* xn3, float* mean,
-                          float* rstd, void* stream);
+                          float* rstd, int segments, void* stream);
+/* a_segments = 3: A3 is [M, K3]; a_segments = 2: A3 is [M, 2*K3/3] = [hi | mid] and the K loop wraps (K3/3 a multiple of 32). */
 CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
-                              void* g3, void* stream);
+                              void* g3, int a_segments, void* stream);
 
 /* Fused no-grad MLP forward for the HBM-bound stages (C in {96, 128, 192}; bf16 operands, fp32 residual stream):
  *   out[m,:] = shortcut[m,:] + dp[m / rows_per_sample] * gamma * (GELU_erf(xn[m,:].W1^T + b1).W2^T + b2)

@@ -76,7 +76,7 @@ for si in [int(s) for s in args.stages.split(",")]:
     tag = f"C{C}_H{H}"
     if only is None or "dwconv" in only:
         timeit(f"dwconv7_ln_fwd {tag}", lambda: cabi.dwconv7_ln_fwd(x, w, b, lw, lb, 1e-6, bf))
-        timeit(f"dwconv7_ln_fwd_x3 {tag}", lambda: cabi.dwconv7_ln_fwd_x3(x, w, b, lw, lb, 1e-6))
+        timeit(f"dwconv7_ln_fwd_x3 {tag}", lambda: cabi.dwconv7_ln_fwd_x3(x, w, b, lw, lb, 1e-6, 2))
         dy = torch.randn(M, C, device=dev, generator=g).to(bf)
         timeit(f"dwconv7_dgrad {tag}", lambda: cabi.dwconv7_dgrad(dy, w, x, (N, H, H, C), f32))
         timeit(f"dwconv7_wgrad {tag}", lambda: cabi.dwconv7_wgrad(dy, x, P=max(1, L.load().cnx_sm_count() // (C // 32))))
@@ -116,7 +116,7 @@ for si in [int(s) for s in args.stages.split(",")]:
         o32 = torch.empty(M, C, device=dev)
         st = L.stream()
         timeit(f"fc1_gelu_x3 {tag}", lambda: L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C,
-                                                                                     L.ptr(g2), st)))
+                                                                                     L.ptr(g2), 2, st)))
         timeit(f"fc2_scale_res_x3 {tag}", lambda: L.check(lib.cnx_gemm_bias_scale_residual_fwd(
             L.ptr(g2), L.ptr(w23), L.ptr(b2), L.ptr(gam), None, H * H, L.ptr(xs), L.ptr(o32), L.dt(f32), M, C, 12 * C, L.dt(bf),
             L.CNX_GEMM_A_SPLIT2, st)))

@@ -30,18 +30,18 @@ def dwconv7_ln_fwd(x_nhwc, w, b, ln_w, ln_b, eps, act_dtype):
     return y, xn, mean, rstd
 
 
-def dwconv7_ln_fwd_x3(x_nhwc, w, b, ln_w, ln_b, eps):
+def dwconv7_ln_fwd_x3(x_nhwc, w, b, ln_w, ln_b, eps, segments=3):
     """fp32 stream -> split operand [hi | mid | hi] bf16 [M, 3C] (+ the fp32 conv output used as scratch, mean, rstd)"""
     lib = L.load()
     w = tap_major(w)
     N, H, W, C = x_nhwc.shape
     M = N * H * W
     y = torch.empty((M, C), dtype=torch.float32, device=x_nhwc.device)
-    a3 = torch.empty((M, 3 * C), dtype=torch.bfloat16, device=x_nhwc.device)
+    a3 = torch.empty((M, segments * C), dtype=torch.bfloat16, device=x_nhwc.device)
     mean = torch.empty((M,), dtype=torch.float32, device=x_nhwc.device)
     rstd = torch.empty_like(mean)
     L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(x_nhwc), L.ptr(w), L.ptr(b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C, L.ptr(y),
-                                      L.ptr(a3), L.ptr(mean), L.ptr(rstd), _st()), "dwconv7_ln_fwd_x3")
+                                      L.ptr(a3), L.ptr(mean), L.ptr(rstd), segments, _st()), "dwconv7_ln_fwd_x3")
     return y, a3, mean, rstd
 
 

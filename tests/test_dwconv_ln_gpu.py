@@ -110,3 +110,6 @@ def test_dwconv_ln_fwd_split_operand(shape):
     hi, mid = a3[:, :C], a3[:, C:2 * C]
     assert torch.equal(hi, xn.to(torch.bfloat16)) and torch.equal(a3[:, 2 * C:], hi)
     assert torch.equal(mid, (xn - hi.float()).to(torch.bfloat16))
+    # two-segment form [hi | mid] (row stride 2C) for a consumer whose K loop wraps
+    y2, a2, mean2, rstd2 = dwconv7_ln_fwd_x3(x, w, b, lw, lb, 1e-6, 2)
+    assert torch.equal(y2, y3) and torch.equal(a2, a3[:, :2 * C]) and torch.equal(mean2, mean3)

@@ -142,9 +142,12 @@ def test_split_operands_reconstruct_fp32(M, C):
     g = torch.Generator(device=DEV).manual_seed(M + C)
     x = torch.randn(M, C, device=DEV, generator=g) * 3
     a3 = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=DEV)
-    L.check(lib.cnx_split3(L.ptr(x), M, C, L.ptr(a3), L.stream()), "split3")
+    L.check(lib.cnx_split3(L.ptr(x), M, C, L.ptr(a3), 3, L.stream()), "split3")
     hi, mid, hi2 = a3[:, :C].float(), a3[:, C:2 * C].float(), a3[:, 2 * C:].float()
     assert torch.equal(hi, hi2) and torch.equal(hi, x.to(torch.bfloat16).float())
+    a2 = torch.empty(M, 2 * C, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.cnx_split3(L.ptr(x), M, C, L.ptr(a2), 2, L.stream()), "split3(2 segments)")
+    assert torch.equal(a2, a3[:, :2 * C])
     assert ((hi + mid - x).abs() <= x.abs() * 2 ** -16 + 1e-30).all()
     b3 = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=DEV)
     L.check(lib.cnx_weight_prep(L.ptr(x), M, C, None, 3, L.ptr(b3), L.dt(torch.bfloat16), L.stream()), "weight_prep")
@@ -165,10 +168,22 @@ def test_x3_mlp_forward_is_fp32_accurate(M, C):
     g2 = torch.empty(M, 8 * C, dtype=bf, device=DEV)
     out = torch.empty(M, C, device=DEV)
     st = L.stream()
-    L.check(lib.cnx_split3(L.ptr(A), M, C, L.ptr(a3), st))
+    L.check(lib.cnx_split3(L.ptr(A), M, C, L.ptr(a3), 3, st))
     L.check(lib.cnx_weight_prep(L.ptr(W1), 4 * C, C, None, 3, L.ptr(w13), L.dt(bf), st))
     L.check(lib.cnx_weight_prep(L.ptr(W2), C, 4 * C, None, 3, L.ptr(w23), L.dt(bf), st))
-    L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C, L.ptr(g2), st))
+    L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C, L.ptr(g2), 3, st))
+    # the two-segment A operand [hi | mid] with a wrapping K loop: identical MMAs, identical result
+    a2 = a3[:, :2 * C].contiguous()
+    g2w = torch.empty_like(g2)
+    L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a2), L.ptr(w13), L.ptr(b1), M, 4 * C, 3 * C, L.ptr(g2w), 2, st))
+    assert torch.equal(g2w, g2)
+    o3 = torch.empty(M, 4 * C, device=DEV)
+    o2 = torch.empty_like(o3)
+    L.check(lib.cnx_gemm_plain(L.ptr(a3), L.ptr(w13), L.ptr(b1), L.ptr(o3), L.dt(torch.float32), M, 4 * C, 3 * C, L.dt(bf), 0, st))
+    L.check(lib.cnx_gemm_plain(L.ptr(a2), L.ptr(w13), L.ptr(b1), L.ptr(o2), L.dt(torch.float32), M, 4 * C, 3 * C, L.dt(bf),
+                               L.CNX_GEMM_A_SPLIT2, st))
+    assert torch.equal(o2, o3)
+    assert max_rel(o3.double(), A.double() @ W1.double().t() + b1.double()) <= 2e-5
     gd = F.gelu(A.double() @ W1.double().t() + b1.double())
     ghat = g2[:, :4 * C].double() + g2[:, 4 * C:].double()
     assert max_rel(ghat, gd) <= 2e-5

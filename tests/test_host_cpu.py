@@ -42,11 +42,14 @@ def test_argument_validation_needs_no_device():
     assert lib.cnx_mixup_batch(None, None, 4, 3, 8, 8, 0.5, 0, 0, 0, 0, 0, None) == -1
     assert lib.cnx_mixup_batch(fake, None, 4, 3, 8, 8, 0.5, 1, 0, 9, 0, 1, None) == -1 and b"cutmix box" in lib.cnx_last_error_string()
     assert lib.cnx_mixup_batch(fake + 4, None, 4, 3, 8, 8, 0.5, 0, 0, 0, 0, 0, None) == -1 and b"aligned" in lib.cnx_last_error_string()
-    assert lib.cnx_split3(fake, 16, 12, fake, None) == -2 and b"multiple of 8" in lib.cnx_last_error_string()
-    assert lib.cnx_gemm_bias_gelu_fwd_x3(fake, fake, fake, 128, 48, 72, fake, None) == -2 and b"multiple of 32" in lib.cnx_last_error_string()
-    assert lib.cnx_gemm_bias_gelu_fwd_x3(fake, fake, fake, 128, 64, 70, fake, None) == -1
+    assert lib.cnx_split3(fake, 16, 12, fake, 3, None) == -2 and b"multiple of 8" in lib.cnx_last_error_string()
+    assert lib.cnx_split3(fake, 16, 16, fake, 4, None) == -1
+    assert lib.cnx_gemm_bias_gelu_fwd_x3(fake, fake, fake, 128, 48, 72, fake, 3, None) == -2 and b"multiple of 32" in lib.cnx_last_error_string()
+    assert lib.cnx_gemm_bias_gelu_fwd_x3(fake, fake, fake, 128, 64, 70, fake, 3, None) == -1
+    assert lib.cnx_gemm_bias_gelu_fwd_x3(fake, fake, fake, 128, 64, 72, fake, 2, None) == -2 and b"a_segments" in lib.cnx_last_error_string()
     assert lib.cnx_gemm_bias_scale_residual_fwd(fake, fake, None, None, None, 49, fake, fake, 0, 128, 96, 300, 1, L.CNX_GEMM_A_SPLIT2, None) == -2
-    assert lib.cnx_dwconv7_ln_fwd_x3(fake, fake, fake, fake, fake, 1e-6, 1, 7, 7, 40, fake, fake, fake, fake, None) == -2
+    assert lib.cnx_dwconv7_ln_fwd_x3(fake, fake, fake, fake, fake, 1e-6, 1, 7, 7, 40, fake, fake, fake, fake, 3, None) == -2
+    assert lib.cnx_dwconv7_ln_fwd_x3(fake, fake, fake, fake, fake, 1e-6, 1, 7, 7, 64, fake, fake, fake, fake, 1, None) == -1
     assert lib.cnx_avgpool_nhwc_fwd(fake, 0, 2, 49, 6, fake, None) == -2 and lib.cnx_avgpool_nhwc_bwd(None, 2, 49, 8, fake, 0, None) == -1
     assert lib.cnx_weight_prep(fake, 8, 8, None, 3, fake, 0, None) == -1 and b"mode 3" in lib.cnx_last_error_string()
 
