@@ -51,7 +51,7 @@ def cutmix_bbox_and_lam(img_shape, lam, ratio_minmax=None, correct_lam=True, cou
 
 
 def mixup_target(target, num_classes, lam=1.0, smoothing=0.0):
-    return ops.mixup_target(target, num_classes, lam, smoothing)
+    return torch.ops.cnx.mixup_target(target, num_classes, float(lam), float(smoothing))
 
 
 class Mixup:
@@ -103,14 +103,14 @@ class Mixup:
             (yl, yh, xl, xh), lam = cutmix_bbox_and_lam(x.shape, lam, ratio_minmax=self.cutmix_minmax,
                                                         correct_lam=self.correct_lam)
             if fused:
-                ops.mixup_batch(x, lam, box=(yl, yh, xl, xh), original_out=original_out)
+                torch.ops.cnx.mixup_batch(x, float(lam), [int(yl), int(yh), int(xl), int(xh)], original_out)
                 return lam
             if original_out is not None:
                 original_out.copy_(x)
             x[:, :, yl:yh, xl:xh] = x.flip(0)[:, :, yl:yh, xl:xh]
         else:
             if fused:
-                ops.mixup_batch(x, lam, original_out=original_out)       # one pass instead of flip / mul_ / mul_ / add_
+                torch.ops.cnx.mixup_batch(x, float(lam), None, original_out)    # one pass instead of flip / mul_ / mul_ / add_
                 return lam
             if original_out is not None:
                 original_out.copy_(x)

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops  # noqa: F401  (registers the torch.ops.cnx.* custom ops the modules below call)
 
 
 def _trunc_normal_(t: torch.Tensor, std: float = 0.02) -> torch.Tensor:
@@ -54,7 +54,7 @@ class LayerNorm(nn.LayerNorm):
         super().__init__(num_channels, eps=eps, elementwise_affine=affine)
 
     def forward(self, x):
-        return ops.layer_norm_cl(x, self.weight, self.bias, self.eps)
+        return torch.ops.cnx.layer_norm_cl(x, self.weight, self.bias, self.eps)
 
 
 class LayerNorm2d(nn.LayerNorm):
@@ -65,7 +65,7 @@ class LayerNorm2d(nn.LayerNorm):
 
     def forward(self, x):
         x = x.permute(0, 2, 3, 1)
-        x = ops.layer_norm_cl(x, self.weight, self.bias, self.eps)
+        x = torch.ops.cnx.layer_norm_cl(x, self.weight, self.bias, self.eps)
         return x.permute(0, 3, 1, 2)
 
 
@@ -101,9 +101,9 @@ class ConvNeXtBlock(nn.Module):
 
     def forward(self, x):
         dp = self.drop_path.sample_scale(x.shape[0], x.device) if isinstance(self.drop_path, DropPath) else None
-        return ops.block_forward(x, self.conv_dw.weight, self.conv_dw.bias, self.norm.weight, self.norm.bias,
-                                 self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
-                                 self.gamma, dp, self.norm.eps)
+        return torch.ops.cnx.block_forward(x, self.conv_dw.weight, self.conv_dw.bias, self.norm.weight, self.norm.bias,
+                                           self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
+                                           self.gamma, dp, self.norm.eps)
 
 
 class ConvNeXtStage(nn.Module):
@@ -122,7 +122,7 @@ class ConvNeXtStage(nn.Module):
         if isinstance(ds, nn.Sequential):
             conv = ds[1]
             if conv.kernel_size == (2, 2) and conv.stride == (2, 2) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-                x = ops.downsample_forward(x, ds[0].weight, ds[0].bias, conv.weight, conv.bias, ds[0].eps)
+                x = torch.ops.cnx.downsample_forward(x, ds[0].weight, ds[0].bias, conv.weight, conv.bias, ds[0].eps)
             else:
                 x = ds(x)
         return self.blocks(x)
@@ -146,7 +146,7 @@ class NormMlpClassifierHead(nn.Module):
         if (not pre_logits and isinstance(self.fc, nn.Linear) and self.fc.bias is not None and ops.head_supported(x, self.fc.weight)
                 and not (self.training and self.drop.p > 0)):
             # pool -> LayerNorm -> fc on the libcnx kernels; other shapes (e.g. 2 classes) use the ATen modules
-            return ops.head_forward(x, self.norm.weight, self.norm.bias, self.fc.weight, self.fc.bias, self.norm.eps)
+            return torch.ops.cnx.head_forward(x, self.norm.weight, self.norm.bias, self.fc.weight, self.fc.bias, self.norm.eps)
         x = self.global_pool(x)
         x = self.norm(x)
         x = self.flatten(x)
@@ -197,7 +197,7 @@ class ConvNeXt(nn.Module):
         # row-major matrix the Block kernels consume (no permute copies anywhere in the network)
         conv, norm = self.stem[0], self.stem[1]
         if conv.kernel_size == (4, 4) and conv.stride == (4, 4) and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0:
-            x = ops.stem_forward(x, conv.weight, conv.bias, norm.weight, norm.bias, norm.eps)
+            x = torch.ops.cnx.stem_forward(x, conv.weight, conv.bias, norm.weight, norm.bias, norm.eps)
         else:
             x = self.stem(x.contiguous(memory_format=torch.channels_last))
         x = self.stages(x)

@@ -741,3 +741,26 @@ def mixup_target(target: torch.Tensor, num_classes: int, lam: float = 1.0, smoot
     L.check(lib.cnx_mixup_target(L.ptr(t), B, num_classes, float(lam), float(smoothing), L.ptr(out), L.stream()),
             "mixup_target")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# torch.library registration: the entry points above are also torch custom ops, `torch.ops.cnx.*` (what the nn.Module mirror in
+# modules.py / loss.py / mixup.py calls).  They are registered CompositeImplicitAutograd: the dispatcher hands the call to the
+# Python function above, whose torch.autograd.Function records the backward — so autograd, autocast state and grad mode are
+# exactly what a direct call sees.  Schemas are the contract a maintainer would bind against.
+# ------------------------------------------------------------------------------------------------------------------------
+_LIB = torch.library.Library("cnx", "DEF")
+_SCHEMAS = {
+    "block_forward": ("(Tensor x, Tensor conv_w, Tensor conv_b, Tensor ln_w, Tensor ln_b, Tensor w1, Tensor b1, Tensor w2, Tensor b2, "
+                      "Tensor? gamma, Tensor? dp, float eps) -> Tensor", block_forward),
+    "layer_norm_cl": ("(Tensor x, Tensor w, Tensor b, float eps) -> Tensor", layer_norm_cl),
+    "stem_forward": ("(Tensor x, Tensor conv_w, Tensor conv_b, Tensor ln_w, Tensor ln_b, float eps) -> Tensor", stem_forward),
+    "downsample_forward": ("(Tensor x, Tensor ln_w, Tensor ln_b, Tensor conv_w, Tensor conv_b, float eps) -> Tensor", downsample_forward),
+    "head_forward": ("(Tensor x, Tensor ln_w, Tensor ln_b, Tensor fc_w, Tensor fc_b, float eps) -> Tensor", head_forward),
+    "soft_target_cross_entropy": ("(Tensor x, Tensor target) -> Tensor", soft_target_cross_entropy),
+    "mixup_target": ("(Tensor target, int num_classes, float lam=1.0, float smoothing=0.0) -> Tensor", mixup_target),
+    "mixup_batch": ("(Tensor(a!) x, float lam, int[]? box=None, Tensor(b!)? original_out=None) -> Tensor(a!)", mixup_batch),
+}
+for _name, (_schema, _fn) in _SCHEMAS.items():
+    _LIB.define(_name + _schema)
+    _LIB.impl(_name, _fn, "CompositeImplicitAutograd")

@@ -115,3 +115,21 @@ def test_mixup_host_rng_sequence_matches_oracle():
         assert r1 == r2
     with pytest.raises(NotImplementedError):
         P.Mixup(mode="elem")
+
+
+def test_torch_library_registration():
+    """BASELINE north_star: "the Python host code calls the kernels as torch custom ops": every entry point of the hot path is
+    registered with torch.library under torch.ops.cnx and is what the nn.Module mirror calls."""
+    import inspect
+    from imageclassification_b200 import loss, mixup, modules, ops
+    for name in ("block_forward", "layer_norm_cl", "stem_forward", "downsample_forward", "head_forward",
+                 "soft_target_cross_entropy", "mixup_target", "mixup_batch"):
+        op = getattr(torch.ops.cnx, name)
+        assert "cnx::" + name in str(op.default._schema)
+        assert name in ops._SCHEMAS
+    assert "Tensor? dp" in str(torch.ops.cnx.block_forward.default._schema)
+    assert "Tensor(a!) x" in str(torch.ops.cnx.mixup_batch.default._schema)
+    for mod in (modules, loss, mixup):
+        assert "torch.ops.cnx." in inspect.getsource(mod)
+    with pytest.raises(RuntimeError, match="CUDA"):                       # dispatched, then refused: no CPU fallback behind the op
+        torch.ops.cnx.mixup_target(torch.zeros(2, dtype=torch.long), 3, 0.5, 0.1)
