@@ -318,8 +318,14 @@ template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
   static constexpr int RING_BUDGET = 224 * 1024 - SLAB_BYTES;
   static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
   static constexpr int NCHUNK = BN / 32;                               // 32-column epilogue chunks per tile
+  // BN <= 256: TWO accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1).  BN = 384 (CTA pairs only): ONE
+  // 384-column accumulator — a CTA then stages 40 KB per k-block for 128 x 384 x 64 MACs (79 MAC/B) where the 256 x 192 tile
+  // stages 28 KB for half the MACs (55 MAC/B): the long-K GEMMs with N = 384 were bound by the bytes an SM can take in per
+  // clock, not by the tensor pipe (profiles/r02h_*), and their epilogue is a small fraction of a K >= 1024 tile.
+  static constexpr int NACC = (BN <= 256) ? 2 : 1;
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int TMEM_COLS = (BN <= 256) ? 2 * ACC_STRIDE : 512;
+  static_assert(BN <= 256 || (BN == 384 && NCTA == 2 && SLAB), "BN = 384 is a CTA-pair slab-epilogue configuration");
   static constexpr int EPI_COLS = BN / 2;                              // columns per epilogue warp
   static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
   static constexpr int SMEM = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align*/ + 512 /*barriers*/;
@@ -399,7 +405,15 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (NCTA == 2) {
             if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
             tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), acol, arow);
-            tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+            if constexpr (BN == 384) {
+              // this CTA's half of the N = 256 MMA's B rows (two 64-row boxes), then its half of the N = 128 MMA's (one box)
+              const int32_t b0 = (int32_t)(nt * BN + rank * 128), b1 = (int32_t)(nt * BN + 256 + rank * 64);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, b0);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 8192, &tmB, full_bar(s), kb * BK, b0 + 64);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 16384, &tmB, full_bar(s), kb * BK, b1);
+            } else {
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+            }
           } else {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
             tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), acol, arow);
@@ -413,7 +427,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ===== MMA issuer (the leader CTA's elected thread issues for the pair) =====
-      constexpr uint32_t idesc = make_idesc(TM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc(TM, BN == 384 ? 256 : BN, 0, 0);
+      constexpr uint32_t idesc_b = make_idesc(TM, 128, 0, 0);          // BN = 384: the second MMA of a k-step (columns 256..383)
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
       for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
@@ -430,6 +445,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < kmma; ++k) {
             if (NCTA == 2) umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
             else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if constexpr (BN == 384) {
+              const uint64_t bdesc2 = make_smem_desc(sB + s * Cfg::B_BYTES + 16384, 16, 1024);
+              umma_f16_pair(d_tmem + 256, adesc + (uint64_t)(k * 2), bdesc2 + (uint64_t)(k * 2), idesc_b, (kb | k) != 0);
+            }
           }
           if (NCTA == 2) umma_commit_pair(empty_bar(s));   // slot s is free in BOTH CTAs once these MMAs retire
           else umma_commit(empty_bar(s));
@@ -437,7 +456,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (NCTA == 2) umma_commit_pair(tfull_bar(as));    // accumulator complete -> both epilogues
         else umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == Cfg::NACC) { as = 0; aph ^= 1; }
       }
     }
     __syncwarp();
@@ -472,7 +491,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (NCTA == 2) mbar_arrive_cluster(tempty_bar(as), 0);     // the leader's MMA issuer waits for both CTAs
         else mbar_arrive(tempty_bar(as));
       }
-      if (++as == 2) { as = 0; aph ^= 1; }
+      if (++as == Cfg::NACC) { as = 0; aph ^= 1; }
     }
   } else if (warp >= kFirstEpiWarp && SLAB) {
     // ===== slab epilogue: every epilogue warp is autonomous.  It owns TMEM lanes [32q, 32q+32) and every other 32-column
@@ -532,7 +551,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (NCTA == 2) mbar_arrive_cluster(tempty_bar(as), 0);
           else mbar_arrive(tempty_bar(as));
         }
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++as == Cfg::NACC) { as = 0; aph ^= 1; }
       }
       const int64_t n0 = (t_cur % n_tiles) * BN + c_cur * 32;
       const int64_t m = (t_cur / n_tiles) * TM + rank * BM + quarter * 32 + lane;
@@ -1555,6 +1574,14 @@ static bool staged_enabled(int kind, bool dflt) {
   if (v == 8) return dflt;
   return kind == EPI_BIAS_GELU ? (v & 1) != 0 : (v & 2) != 0;
 }
+static bool bn384_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_GEMM_BN384");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 static bool slab_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1569,7 +1596,7 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   typedef TnCfg<BN, NCTA, SLAB, NEPI> Cfg;
   CUtensorMap tmA, tmB, tmOut, tmIn;
   if (int rc = make_map(&tmA, A, M, ep.a_wrap > 0 ? (int64_t)ep.a_wrap : K, BM)) return rc;
-  if (int rc = make_map(&tmB, B, N, K, Cfg::B_ROWS)) return rc;
+  if (int rc = make_map(&tmB, B, N, K, BN == 384 ? 64 : Cfg::B_ROWS)) return rc;
   if (SLAB) {
     constexpr bool kGelu = (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3);
     void* o = kGelu ? ep.out1 : ep.out0;
@@ -1585,6 +1612,13 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   if (int rc = set_smem(k, Cfg::SMEM)) return rc;
   const int64_t tiles = ((M + BM * NCTA - 1) / (BM * NCTA)) * ((N + BN - 1) / BN);
   int64_t grid = sm_count() / NCTA;
+  {
+    // experiments (profiles/kbench.py): CNX_GEMM_MAXSMS caps the number of SMs the persistent grid occupies — if throughput
+    // per launch barely drops with fewer SMs, the kernel is bound by what the SMs share (L2 -> SM bandwidth), not by the SMs
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("CNX_GEMM_MAXSMS"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && grid > cap / NCTA) grid = cap / NCTA;
+  }
   if (grid > tiles) grid = tiles;
   grid *= NCTA;
   cudaLaunchConfig_t cfg = {};
@@ -1698,6 +1732,20 @@ int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, co
   }
   // CTA-pair tiles (256 x BN) wherever a whole tile fits; CNX_GEMM_NCTA=1 in the environment selects the single-CTA kernel
   if (tc::pair_enabled() && M >= 256) {
+    if constexpr (KIND == EPI_PLAIN || KIND == EPI_SCALE_RES) {
+      // long-K GEMMs onto N = 384 * j columns (fc2 and the fc1 data gradient at C = 384 / 768, and their split-operand
+      // forms): 256 x 384 single-accumulator tiles when they fill the machine's waves about as well as the alternative
+      if (N % 384 == 0 && K >= 1024 && tc::bn384_enabled()) {
+        const int64_t pairs = sm_count() / 2, mt = (M + 255) / 256;
+        auto eff = [&](int64_t tiles) { return (double)tiles / (double)(((tiles + pairs - 1) / pairs) * pairs); };
+        const int alt = (N % 256 == 0) ? 256 : 192;
+        if (eff(mt * (N / 384)) + 0.05 >= eff(mt * (N / alt))) {
+          const bool need_in = (KIND == EPI_SCALE_RES);
+          if (N % 32 == 0 && (!need_in || ep.aux != nullptr) && ep.out0 != nullptr && tc::slab_enabled())
+            return tc::launch_tn_impl<384, KIND, TOUT, 2, true>(A, B, M, N, K, ep, s);
+        }
+      }
+    }
     if (N % 256 == 0) return tc::launch_tn<256, KIND, TOUT, 2>(A, B, M, N, K, ep, s);
     if (N % 192 == 0) return tc::launch_tn<192, KIND, TOUT, 2>(A, B, M, N, K, ep, s);
   }

@@ -109,6 +109,12 @@ class _PrepRegistry:
             self.entries[k] = e
             self.table = None
             weakref.finalize(w, self._drop, k)
+            # a NEW layout is built on its own (one small launch); rebuilding every registered layout here made the first
+            # forward of a model quadratic in its number of weights (128 multi-launches in the first step of ConvNeXt-T)
+            L.check(L.load().cnx_weight_prep(L.ptr(w), R, Cc, L.ptr(scale), mode, L.ptr(out), L.dt(out_dtype), L.stream()),
+                    "weight_prep")
+            e["key"] = self._key(w, scale)
+            return out
         if e["key"] != self._key(w, scale):
             self.refresh()
         return e["out"]
