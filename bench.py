@@ -508,13 +508,17 @@ def roofline_tables(recs, bsteps, peaks, ms_b):
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["bytes"] else None
         tfs = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["flops"] else None
         is_gemm = d["name"].startswith("cnx_gemm") or d["name"].startswith("cnx_mlp")
+        # the fp32-accurate split-operand GEMMs execute 3 MMAs per algorithmic product by design (include/cnx.h "x3"): their
+        # tensor roof is set by the EXECUTED flops; the algorithmic fraction (SURVEY 8d flops) is reported beside it
+        xf = 3 if (is_gemm and "_x3" in label) else 1
         # time the launch would take at the roof that bounds it (max of the HBM time and, for GEMMs, the tensor time)
-        roof_ms = max(d["bytes"] / (peaks["hbm"] * 1e9), (d["flops"] / (peaks["tensor"] * 1e12)) if is_gemm else 0.0) * 1e3
+        roof_ms = max(d["bytes"] / (peaks["hbm"] * 1e9), (xf * d["flops"] / (peaks["tensor"] * 1e12)) if is_gemm else 0.0) * 1e3
         table.append({"kernel": label, "family": _family(label), "calls_per_step": d["n"] / bsteps,
                       "ms_per_step": round(d["ms"] / bsteps, 4), "share_of_cnx": round(d["ms"] / tot, 4),
                       "bytes_per_launch": d["bytes"] // max(d["n"], 1), "flops_per_launch": d["flops"] // max(d["n"], 1),
                       "GBps": gbs and round(gbs, 1), "hbm_frac": gbs and round(gbs / peaks["hbm"], 4),
                       "TFLOPs": tfs and round(tfs, 2), "tensor_frac": (tfs and round(tfs / peaks["tensor"], 4)) if is_gemm else None,
+                      "executed_flops_factor": xf,
                       "roof_ms_per_step": round(roof_ms / bsteps, 4), "gemm": is_gemm})
     fams = families_all(table)
     try:
@@ -558,26 +562,29 @@ def families_all(table):
     fam = {}
     tot = sum(r["ms_per_step"] for r in table) or 1.0
     for r in table:
-        f = fam.setdefault(r["family"], {"ms": 0.0, "n": 0.0, "bytes": 0.0, "flops": 0.0, "roof_ms": 0.0, "gemm": r["gemm"],
-                                         "t_hbm": 0.0, "t_tensor": 0.0})
+        f = fam.setdefault(r["family"], {"ms": 0.0, "n": 0.0, "bytes": 0.0, "flops": 0.0, "xflops": 0.0, "roof_ms": 0.0,
+                                         "gemm": r["gemm"]})
         f["ms"] += r["ms_per_step"]
         f["n"] += r["calls_per_step"]
         f["bytes"] += r["bytes_per_launch"] * r["calls_per_step"]
         f["flops"] += r["flops_per_launch"] * r["calls_per_step"]
+        f["xflops"] += r["flops_per_launch"] * r["calls_per_step"] * r.get("executed_flops_factor", 1)
         f["roof_ms"] += r["roof_ms_per_step"]
     peaks = _peaks()
     out = []
     for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
         hb = f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peaks["hbm"] if f["bytes"] and f["ms"] else None
         tf = f["flops"] / (f["ms"] * 1e-3) / 1e12 / peaks["tensor"] if (f["flops"] and f["gemm"] and f["ms"]) else None
-        if hb is None and tf is None:
+        tfx = f["xflops"] / (f["ms"] * 1e-3) / 1e12 / peaks["tensor"] if (f["xflops"] and f["gemm"] and f["ms"]) else None
+        if hb is None and tfx is None:
             bound, frac = None, None
-        elif tf is not None and tf > (hb or 0):
-            bound, frac = "tensor", round(tf, 4)
+        elif tfx is not None and tfx > (hb or 0):
+            bound, frac = "tensor", round(tfx, 4)        # executed flops (= algorithmic except for the x3 split-operand GEMMs)
         else:
             bound, frac = "hbm", round(hb, 4)
         out.append({"family": name, "ms": round(f["ms"], 3), "launches": f["n"], "share": round(f["ms"] / tot, 4), "bound": bound,
                     "frac": frac, "hbm_frac": hb and round(hb, 4), "tensor_frac": tf and round(tf, 4),
+                    "tensor_frac_executed": tfx and round(tfx, 4),
                     "roof_time_frac": round(f["roof_ms"] / f["ms"], 4) if f["ms"] and f["roof_ms"] else None})
     return out
 

@@ -8,7 +8,10 @@
  *   - plain pointers + sizes only; all pointers are DEVICE pointers unless a name ends in _host;
  *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); no function
  *     synchronises, allocates device memory, or keeps a reference to a caller buffer after it returns
- *     (tensor-map descriptors are cached by (pointer, shape) only);
+ *     (TMA tensor-map descriptors are encoded on the host at every call — cuTensorMapEncodeTiled, no device work — and passed
+ *     to the kernel by value as __grid_constant__ parameters; nothing is cached between calls);
+ *   - kernels are launched with programmatic stream serialization (their prologue may overlap the previous kernel's tail;
+ *     every kernel waits for its predecessors' memory before its first global access), CNX_PDL=0 in the environment disables it;
  *   - return 0 on success; a negative value for argument errors (CNX_E_*), a positive cudaError_t for a
  *     failed launch.  cnx_last_error_string() describes the last failure on the calling thread;
  *   - no exceptions and no torch types cross this boundary.
