@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace cnx {
 namespace dw2 {
@@ -45,6 +46,9 @@ struct Geo {
   static_assert(NWORK % 2 == 0, "workers come in pairs (one warp = two half-warps)");
 };
 
+typedef Geo<7, 2, 4, 4, 1> GeoT28;    // 28 x 8          H % 28 == 0, W % 8 == 0 (56, 112, 224): 16 workers = 8 compute warps, two
+                                      //                 per scheduler — the 14-worker geometries leave one scheduler with a single
+                                      //                 compute warp (FMA pipe capped at 7/8)
 typedef Geo<8, 2, 16, 1, 1> GeoW32;   //  8 x 32         generic wide maps
 typedef Geo<8, 2, 14, 1, 1> GeoW28;   //  8 x 28         W % 28 == 0, H % 8 == 0  (56, 112, 224)
 typedef Geo<7, 2, 14, 1, 1> GeoS28;   //  7 x 28         28 x 28
@@ -53,16 +57,18 @@ typedef Geo<7, 2, 7, 2, 1> GeoS14;    // 14 x 14         14 x 14
 typedef Geo<8, 1, 8, 1, 2> GeoW8;     //  8 x 8 x 2 img  generic small maps
 typedef Geo<7, 1, 7, 1, 2> GeoS7;     //  7 x 7 x 2 img  7 x 7
 
-enum GeoId { GEO_W32 = 0, GEO_W28, GEO_S28, GEO_W16, GEO_S14, GEO_W8, GEO_S7, GEO_COUNT };
+enum GeoId { GEO_T28 = 0, GEO_W32, GEO_W28, GEO_S28, GEO_W16, GEO_S14, GEO_W8, GEO_S7, GEO_COUNT };
 
 // least padded work; ties go to the earlier (larger-tile) entry
 inline int pick_geo(int64_t N, int64_t H, int64_t W) {
-  static const int tw[GEO_COUNT] = {32, 28, 28, 16, 14, 8, 7};
-  static const int rows[GEO_COUNT] = {8, 8, 7, 16, 14, 8, 7};
-  static const int nb[GEO_COUNT] = {1, 1, 1, 1, 1, 2, 2};
+  static const int tw[GEO_COUNT] = {8, 32, 28, 28, 16, 14, 8, 7};
+  static const int rows[GEO_COUNT] = {28, 8, 8, 7, 16, 14, 8, 7};
+  static const int nb[GEO_COUNT] = {1, 1, 1, 1, 1, 1, 2, 2};
+  static int t28 = -1;                          // CNX_DW_T28=0: without the 16-worker 28 x 8 geometry (A/B measurements)
+  if (t28 < 0) { const char* e = getenv("CNX_DW_T28"); t28 = (e && e[0] == '0') ? 0 : 1; }
   int best = 0;
   double bw = 1e30;
-  for (int g = 0; g < GEO_COUNT; ++g) {
+  for (int g = t28 ? 0 : 1; g < GEO_COUNT; ++g) {
     double work = (double)((W + tw[g] - 1) / tw[g] * tw[g]) * (double)((H + rows[g] - 1) / rows[g] * rows[g]) *
                   (double)((N + nb[g] - 1) / nb[g] * nb[g]);
     if (work < bw * 0.999) { bw = work; best = g; }
@@ -72,6 +78,7 @@ inline int pick_geo(int64_t N, int64_t H, int64_t W) {
 
 #define CNX_GEO_SWITCH(gid, ...)                                                 \
   switch (gid) {                                                                 \
+    case cnx::dw2::GEO_T28: { typedef cnx::dw2::GeoT28 G; __VA_ARGS__; } break;    \
     case cnx::dw2::GEO_W32: { typedef cnx::dw2::GeoW32 G; __VA_ARGS__; } break;    \
     case cnx::dw2::GEO_W28: { typedef cnx::dw2::GeoW28 G; __VA_ARGS__; } break;    \
     case cnx::dw2::GEO_S28: { typedef cnx::dw2::GeoS28 G; __VA_ARGS__; } break;    \
