@@ -421,7 +421,9 @@ template <int MODE, typename TIN, typename TOUT>
 static int pick_conv(const void* x, int x_dtype, const float* wt, const float* bias, const void* dres, void* out,
                      const float* ln_w, const float* ln_b, float eps, void* xn, float* mean, float* rstd, int64_t N,
                      int64_t H, int64_t W, int64_t C, cudaStream_t s, void* xn3 = nullptr, int xseg = 3) {
-  const int gid = pick_geo(N, H, W);
+  // forward with fp32 activations (the x3 / fp32 paths): the LayerNorm half sets the kernel time and needs its 8 warps, which
+  // only fit beside 7 compute warps (measured: 28 x 8 with 4 LayerNorm warps 0.455 ms against 0.337 ms at C96, 56^2)
+  const int gid = pick_geo(N, H, W, !(MODE == MODE_FWD && sizeof(TOUT) == 4));
   CNX_GEO_SWITCH(gid, {
     const bool exact = (W % G::TW == 0) && (H % G::ROWS == 0) && (N % G::NB == 0);
     if (exact)

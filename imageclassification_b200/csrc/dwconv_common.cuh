@@ -60,7 +60,7 @@ typedef Geo<7, 1, 7, 1, 2> GeoS7;     //  7 x 7 x 2 img  7 x 7
 enum GeoId { GEO_T28 = 0, GEO_W32, GEO_W28, GEO_S28, GEO_W16, GEO_S14, GEO_W8, GEO_S7, GEO_COUNT };
 
 // least padded work; ties go to the earlier (larger-tile) entry
-inline int pick_geo(int64_t N, int64_t H, int64_t W) {
+inline int pick_geo(int64_t N, int64_t H, int64_t W, bool allow_t28 = true) {
   static const int tw[GEO_COUNT] = {8, 32, 28, 28, 16, 14, 8, 7};
   static const int rows[GEO_COUNT] = {28, 8, 8, 7, 16, 14, 8, 7};
   static const int nb[GEO_COUNT] = {1, 1, 1, 1, 1, 1, 2, 2};
@@ -68,7 +68,7 @@ inline int pick_geo(int64_t N, int64_t H, int64_t W) {
   if (t28 < 0) { const char* e = getenv("CNX_DW_T28"); t28 = (e && e[0] == '0') ? 0 : 1; }
   int best = 0;
   double bw = 1e30;
-  for (int g = t28 ? 0 : 1; g < GEO_COUNT; ++g) {
+  for (int g = (t28 && allow_t28) ? 0 : 1; g < GEO_COUNT; ++g) {
     double work = (double)((W + tw[g] - 1) / tw[g] * tw[g]) * (double)((H + rows[g] - 1) / rows[g] * rows[g]) *
                   (double)((N + nb[g] - 1) / nb[g] * nb[g]);
     if (work < bw * 0.999) { bw = work; best = g; }
