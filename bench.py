@@ -235,6 +235,9 @@ def kernel_work(name, a):
         M, N, K = a[4:7]
         e = es(a[7])
         return (M * K + N * K + 2 * M * N) * e, 2 * M * N * K, f"dgrad_fc2_gelu K{K}"
+    if name == "cnx_gemm_dgrad_gelu_recompute_bwd":
+        M, N, K = a[6:9]
+        return (2 * M * K + 2 * N * K + M * N) * 2, 2 * M * N * K, f"dgrad_fc2_gelu_rc K{K}"     # algorithmic flops: the data gradient only
     if name == "cnx_gemm_plain":
         M, N, K = a[5:8]
         e = es(a[8])

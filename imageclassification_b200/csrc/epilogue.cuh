@@ -12,8 +12,10 @@ enum {
   EPI_BIAS_GELU = 1,    // h = round(acc + b1); GELU'(h) -> out0 (optional, saved for backward), g = GELU(h) -> out1 [act dtype]
   EPI_SCALE_RES = 2,    // out0 = shortcut + dp[row/rps] * gamma[n] * (acc + b2[n])  [stream dtype]
   EPI_DGELU = 3,        // out0 = acc * gp[m,n]                                 [act dtype], aux = gp = GELU'(h) saved by BIAS_GELU
-  EPI_BIAS_GELU3 = 4    // fp32-accurate forward: g = GELU_erf(acc + b1) in fp32 -> out1 bf16 [M, 2N] = [hi(g) | mid(g)]
+  EPI_BIAS_GELU3 = 4,   // fp32-accurate forward: g = GELU_erf(acc + b1) in fp32 -> out1 bf16 [M, 2N] = [hi(g) | mid(g)]
                         // (split operand of the next GEMM, read with a_wrap = 2N; tcgen05 slab epilogue only)
+  EPI_DGELU_RC = 5      // out0 = acc * GELU'(round(acc2 + b1)), acc2 = A2.B2^T RECOMPUTED in the same kernel (A2 = xn, B2 = W1): the
+                        // forward then stores g only, not GELU'(h) (tcgen05 CTA-pair slab kernel only; HBM-bound stages)
 };
 
 struct EpiParams {
@@ -25,6 +27,8 @@ struct EpiParams {
   void* out0;
   void* out1;
   int64_t ld;               // row stride of out0/out1/aux (= N)
+  const void* a2;           // EPI_DGELU_RC: second operand pair A2 [M,K], B2 [N,K] of the recomputed pre-activation
+  const void* b2;
   int32_t a_wrap;           // tcgen05 kernels: A is stored with only this many columns and the K loop wraps around it (0 = off):
                             // the split operand [hi | mid | hi] kept as [hi | mid], its third segment re-reads the first
 };

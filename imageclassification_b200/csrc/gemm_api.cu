@@ -16,6 +16,7 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
 int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
                      cudaStream_t s);
+int gemm_dgelu_recompute_tc(const void* dz, const void* Bt, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s);
 int64_t wgrad_workspace_bytes_simt(int64_t M, int64_t N1, int64_t N2);
 int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2);
 }  // namespace cnx
@@ -96,6 +97,17 @@ int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, 
   if (dtype == CNX_F32) return gemm_tn_simt<float, float, EPI_DGELU>(dz, Bt, M, N, K, ep, s);
   if (flags & CNX_GEMM_FORCE_SIMT) return gemm_tn_simt<bf16, bf16, EPI_DGELU>(dz, Bt, M, N, K, ep, s);
   return gemm_tn_tc<EPI_DGELU, bf16>(dz, Bt, M, N, K, ep, s);
+}
+
+int cnx_gemm_dgrad_gelu_recompute_bwd(const void* dz, const void* Bt, const void* xn, const void* W1, const float* b1, void* dh,
+                                      int64_t M, int64_t N, int64_t K, int dtype, void* stream) {
+  CNX_REQUIRE(dz && Bt && xn && W1 && b1 && dh, CNX_E_BADARG, "gemm_dgrad_gelu_recompute_bwd: null pointer");
+  CNX_REQUIRE(M > 0 && N > 0 && K > 0, CNX_E_BADARG, "gemm_dgrad_gelu_recompute_bwd: bad shape");
+  CNX_REQUIRE(dtype == CNX_BF16, CNX_E_BADARG, "gemm_dgrad_gelu_recompute_bwd: bf16 operands only (tcgen05 kernel)");
+  EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, dh, nullptr, N};
+  ep.a2 = xn;
+  ep.b2 = W1;
+  return gemm_dgelu_recompute_tc(dz, Bt, M, N, K, ep, (cudaStream_t)stream);
 }
 
 int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,

@@ -308,7 +308,7 @@ __device__ __forceinline__ float2 gelu_as2(float2 h) {
 }
 
 constexpr int kSlabBytes = 4096;                 // one epilogue slab: [32 rows][32 columns] of <= 4-byte elements
-template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
+template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps, bool DUAL = false> struct TnCfg {
   static constexpr int THREADS = (kFirstEpiWarp + NEPI) * 32;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = BN / NCTA;                             // B rows staged by one CTA
@@ -323,8 +323,10 @@ template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
   // stages 28 KB for half the MACs (55 MAC/B): the long-K GEMMs with N = 384 were bound by the bytes an SM can take in per
   // clock, not by the tensor pipe (profiles/r02h_*), and their epilogue is a small fraction of a K >= 1024 tile.
   static constexpr int NACC = (BN <= 256) ? 2 : 1;
-  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  // DUAL (EPI_DGELU_RC): two accumulators per tile, [acc | recomputed pre-activation], BN = 128 columns each
+  static constexpr int ACC_STRIDE = (BN <= 128 && !DUAL) ? 128 : 256;
   static constexpr int TMEM_COLS = (BN <= 256) ? 2 * ACC_STRIDE : 512;
+  static_assert(!DUAL || (BN == 128 && SLAB), "the recompute epilogue is a 128-column slab configuration");
   static_assert(BN <= 256 || (BN == 384 && NCTA == 2 && SLAB), "BN = 384 is a CTA-pair slab-epilogue configuration");
   static constexpr int EPI_COLS = BN / 2;                              // columns per epilogue warp
   static constexpr int CHUNK = (EPI_COLS % 32 == 0) ? 32 : 16;
@@ -339,9 +341,10 @@ template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps> struct TnCfg {
 template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB, int NEPI>
 __global__ void __launch_bounds__((kFirstEpiWarp + NEPI) * 32, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmIn, int64_t M, int64_t N,
-                  int64_t K, EpiParams ep) {
-  typedef TnCfg<BN, NCTA, SLAB, NEPI> Cfg;
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmIn,
+                  const __grid_constant__ CUtensorMap tmB2, int64_t M, int64_t N, int64_t K, EpiParams ep) {
+  constexpr bool DUAL = (KIND == EPI_DGELU_RC);        // second operand pair: A2 through tmIn, B2 through tmB2
+  typedef TnCfg<BN, NCTA, SLAB, NEPI, DUAL> Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TM = BM * NCTA;
   constexpr int NGRP = NEPI / 4;                     // epilogue warps per TMEM lane quarter = column groups
@@ -398,26 +401,29 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int32_t arow = (int32_t)(mt * TM + rank * BM);
         const int32_t brow = (int32_t)(nt * BN + rank * Cfg::B_ROWS);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kk = 0; kk < (DUAL ? 2 : 1) * nkb; ++kk) {
+          const int kb = (DUAL && kk >= nkb) ? kk - nkb : kk;
+          const CUtensorMap* mA = (DUAL && kk >= nkb) ? &tmIn : &tmA;
+          const CUtensorMap* mB = (DUAL && kk >= nkb) ? &tmB2 : &tmB;
           mbar_wait(empty_bar(s), ph ^ 1);
           int32_t acol = kb * BK;
           if (ep.a_wrap > 0 && acol >= ep.a_wrap) acol -= ep.a_wrap;      // third segment of a split operand = its first
           if (NCTA == 2) {
             if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-            tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), acol, arow);
+            tma_load_2d_pair(sA + s * Cfg::A_BYTES, mA, full_bar(s), acol, arow);
             if constexpr (BN == 384) {
               // this CTA's half of the N = 256 MMA's B rows (two 64-row boxes), then its half of the N = 128 MMA's (one box)
               const int32_t b0 = (int32_t)(nt * BN + rank * 128), b1 = (int32_t)(nt * BN + 256 + rank * 64);
-              tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, b0);
-              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 8192, &tmB, full_bar(s), kb * BK, b0 + 64);
-              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 16384, &tmB, full_bar(s), kb * BK, b1);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES, mB, full_bar(s), kb * BK, b0);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 8192, mB, full_bar(s), kb * BK, b0 + 64);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES + 16384, mB, full_bar(s), kb * BK, b1);
             } else {
-              tma_load_2d_pair(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+              tma_load_2d_pair(sB + s * Cfg::B_BYTES, mB, full_bar(s), kb * BK, brow);
             }
           } else {
             mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-            tma_load_2d(sA + s * Cfg::A_BYTES, &tmA, full_bar(s), acol, arow);
-            tma_load_2d(sB + s * Cfg::B_BYTES, &tmB, full_bar(s), kb * BK, brow);
+            tma_load_2d(sA + s * Cfg::A_BYTES, mA, full_bar(s), acol, arow);
+            tma_load_2d(sB + s * Cfg::B_BYTES, mB, full_bar(s), kb * BK, brow);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -434,8 +440,10 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int64_t tile = first_tile; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue(s) have drained this accumulator buffer
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kk = 0; kk < (DUAL ? 2 : 1) * nkb; ++kk) {
+          const int kb = (DUAL && kk >= nkb) ? kk - nkb : kk;
+          // DUAL: the second pass accumulates the recomputed pre-activation in the upper 128 columns of the buffer
+          const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE + ((DUAL && kk >= nkb) ? 128u : 0u);
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(sA + s * Cfg::A_BYTES, 16, 1024);
@@ -542,7 +550,11 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
       }
       float v[32];
+      float u[DUAL ? 32 : 1];       // DUAL: the recomputed pre-activation chunk (upper 128 columns of the accumulator buffer)
       tmem_ld32(tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + c_cur * 32, v);
+      if constexpr (DUAL)
+        tmem_ld32(tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + 128 + c_cur * 32,
+                  *reinterpret_cast<float(*)[32]>(u));
       tmem_ld_wait();
       if (t_nxt != t_cur) {         // last chunk of this tile for this warp: hand the accumulator back
         tc_fence_before();
@@ -576,6 +588,22 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           v[i + 1] = sc * (g4.y * (v[i + 1] + b4.y));
           v[i + 2] = sc * (g4.z * (v[i + 2] + b4.z));
           v[i + 3] = sc * (g4.w * (v[i + 3] + b4.w));
+        }
+      }
+      if constexpr (DUAL) {
+        // dh = acc * GELU'(h), h = round_bf16(xn.W1^T + b1) exactly as the forward's fc1 epilogue rounded it
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
+          const float2 ha = __fadd2_rn(make_float2(u[i], u[i + 1]), make_float2(b4.x, b4.y));
+          const float2 hb = __fadd2_rn(make_float2(u[i + 2], u[i + 3]), make_float2(b4.z, b4.w));
+          const uint32_t ua = pack_bf16(ha.x, ha.y), ub = pack_bf16(hb.x, hb.y);
+          float2 ga, gb, da, db;
+          gelu_pair<true>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
+          gelu_pair<true>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
+          // GELU'(h) rounded to bf16 as the stored tensor of the other path is, then the same multiply
+          const uint32_t pa = pack_bf16(da.x, da.y), pb = pack_bf16(db.x, db.y);
+          v[i] *= bf16_lo(pa); v[i + 1] *= bf16_hi(pa); v[i + 2] *= bf16_lo(pb); v[i + 3] *= bf16_hi(pb);
         }
       }
       uint32_t pg[16], pd[16];
@@ -1593,8 +1621,8 @@ static bool slab_enabled() {
 
 template <int BN, int KIND, typename TOUT, int NCTA, bool SLAB, int NEPI = kEpiWarps>
 static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  typedef TnCfg<BN, NCTA, SLAB, NEPI> Cfg;
-  CUtensorMap tmA, tmB, tmOut, tmIn;
+  typedef TnCfg<BN, NCTA, SLAB, NEPI, KIND == EPI_DGELU_RC> Cfg;
+  CUtensorMap tmA, tmB, tmOut, tmIn, tmB2;
   if (int rc = make_map(&tmA, A, M, ep.a_wrap > 0 ? (int64_t)ep.a_wrap : K, BM)) return rc;
   if (int rc = make_map(&tmB, B, N, K, BN == 384 ? 64 : Cfg::B_ROWS)) return rc;
   if (SLAB) {
@@ -1603,11 +1631,16 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
     const void* in = kGelu ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
     if (int rc = make_slab_map(&tmOut, o, M, (KIND == EPI_BIAS_GELU3) ? 2 * N : N, (int)sizeof(TOUT))) return rc;
     if (KIND == EPI_BIAS_GELU3) tmIn = tmOut;
-    else if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
+    else if (KIND == EPI_DGELU_RC) {
+      if (int rc = make_map(&tmIn, ep.a2, M, K, BM)) return rc;               // A2 = xn
+    } else if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
   } else {
     tmOut = tmA;
     tmIn = tmA;
   }
+  tmB2 = tmB;
+  if (KIND == EPI_DGELU_RC)
+    if (int rc = make_map(&tmB2, ep.b2, N, K, Cfg::B_ROWS)) return rc;        // B2 = W1
   auto k = gemm_tn_tc_kernel<BN, KIND, TOUT, NCTA, SLAB, NEPI>;
   if (int rc = set_smem(k, Cfg::SMEM)) return rc;
   const int64_t tiles = ((M + BM * NCTA - 1) / (BM * NCTA)) * ((N + BN - 1) / BN);
@@ -1635,7 +1668,7 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, M, N, K, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, tmB2, M, N, K, ep);
   if (e != cudaSuccess) {
     set_error("gemm_tn_tc launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -1753,6 +1786,14 @@ int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, co
   if (N % 96 == 0) return tc::launch_tn<96, KIND, TOUT, 1>(A, B, M, N, K, ep, s);
   if (N % 64 == 0) return tc::launch_tn<64, KIND, TOUT, 1>(A, B, M, N, K, ep, s);
   return tc::launch_tn<128, KIND, TOUT, 1>(A, B, M, N, K, ep, s);   // ragged N: TMA zero-fills, epilogue guards
+}
+
+// dh = (dz . Bt^T) * GELU'(round(xn . W1^T + b1)): CTA-pair 256 x 128 tiles, two accumulators, 16 epilogue warps
+int gemm_dgelu_recompute_tc(const void* dz, const void* Bt, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
+  CNX_REQUIRE(N % 128 == 0 && K % 8 == 0 && M >= 256, CNX_E_SHAPE,
+              "gemm_dgrad_gelu_recompute: needs N %% 128 == 0, K %% 8 == 0, M >= 256 (N=%lld K=%lld M=%lld)", (long long)N,
+              (long long)K, (long long)M);
+  return tc::launch_tn_impl<128, EPI_DGELU_RC, bf16, 2, true, 16>(dz, Bt, M, N, K, ep, s);
 }
 
 #define CNX_INST(KIND, TOUT) \

@@ -30,6 +30,10 @@ KEEP_BF16_STREAM = os.environ.get("CNX_BF16_STREAM", "0") == "1"
 # with split bf16 operands (include/cnx.h "x3"): fp32-accurate (~2^-16 per product), 3 MMAs per product instead of CUDA-core
 # FMAs.  CNX_X3_FWD=0 selects the CUDA-core fp32 GEMMs for comparison.
 X3_FWD = os.environ.get("CNX_X3_FWD", "1") != "0"
+# Training forward at the HBM-bound stages (C <= RECOMPUTE_MAX_C, bf16): fc1 stores g only and the backward kernel recomputes
+# the pre-activation for GELU' (one [M,4C] tensor per Block instead of two; the tensor pipe idles there).  CNX_RECOMPUTE_C=0
+# turns it off (saved GELU'(h) everywhere).
+RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "192"))
 
 
 def _act_dtype() -> torch.dtype:
@@ -295,7 +299,9 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.cnx_mlp_fused_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), L.ptr(w2a), L.ptr(b2), L.ptr(gamma), L.ptr(dp), H * W,
                                           L.ptr(xl), L.ptr(out), M, C, st), "mlp_fused_fwd")
             return out.permute(0, 3, 1, 2)
-        h = torch.empty((M, C4), dtype=act_dtype, device=dev) if need_grad else None
+        recompute = (need_grad and act_dtype == torch.bfloat16 and C <= RECOMPUTE_MAX_C and C4 % 128 == 0 and M >= 256
+                     and GEMM_FLAGS == 0)
+        h = torch.empty((M, C4), dtype=act_dtype, device=dev) if (need_grad and not recompute) else None     # holds GELU'(h)
         g = torch.empty((M, C4), dtype=act_dtype, device=dev)
         L.check(lib.cnx_gemm_bias_gelu_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), M, C4, C, L.ptr(h), L.ptr(g), ad,
                                            GEMM_FLAGS, st), "gemm_bias_gelu_fwd")
@@ -332,8 +338,14 @@ class _BlockFn(torch.autograd.Function):
         # 2. dh = (dz . (gamma*W2)) * GELU'(h)
         w2gt = _weight_prep(w2, 2, gamma, act_dtype)            # [4C, C]
         dh = torch.empty((M, C4), dtype=act_dtype, device=dev)
-        L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
-                "gemm_dgrad_gelu_bwd")
+        if h is None:
+            # GELU'(h) was not saved: the kernel recomputes h = xn . W1^T + b1 beside the data gradient
+            L.check(lib.cnx_gemm_dgrad_gelu_recompute_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(xn), L.ptr(_weight_prep(w1, 0, None, act_dtype)),
+                                                          L.ptr(ctx.params[5]), L.ptr(dh), M, C4, C, ad, st),
+                    "gemm_dgrad_gelu_recompute_bwd")
+        else:
+            L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
+                    "gemm_dgrad_gelu_bwd")
         # 3. fc2 wgrad on the UNSCALED gradient; layer-scale identities give dW2, db2, dgamma without saving z
         p_conv_w, p_conv_b, p_ln_w, p_ln_b, p_w1, p_b1, p_w2, p_b2, p_gamma = ctx.params
         G2, s = _wgrad(dz, g, M, C, C4, True)

@@ -233,6 +233,12 @@ CNX_API int cnx_mlp_fused_fwd(const void* xn, const void* W1, const float* b1, c
  * gprime = GELU'(h) as saved by cnx_gemm_bias_gelu_fwd. */
 CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,
                             int64_t K, int dtype, int flags, void* stream);
+/* The same WITHOUT a saved GELU'(h): the fc1 pre-activation is recomputed in the kernel, dh = acc * GELU'(round(xn.W1^T + b1))
+ * (second accumulator in TMEM; xn [M,K], W1 [N,K] in the activation dtype, b1 fp32).  For the HBM-bound stages (C <= 192),
+ * where the tensor pipe idles: the forward then stores g only (cnx_gemm_bias_gelu_fwd with gprime_out = NULL), i.e. ONE
+ * [M,4C] tensor per Block instead of two.  bf16 only, N % 128 == 0, M >= 256.  Bit-identical to the saved-GELU' path. */
+CNX_API int cnx_gemm_dgrad_gelu_recompute_bwd(const void* dz, const void* Bt, const void* xn, const void* W1, const float* b1,
+                                      void* dh, int64_t M, int64_t N, int64_t K, int dtype, void* stream);
 
 /* plain GEMM with cast epilogue: out = A.B^T (dgrad of fc1; also patchify convs).  bias may be NULL. */
 CNX_API int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,

@@ -197,3 +197,29 @@ def test_x3_mlp_forward_is_fp32_accurate(M, C):
     L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g3), L.ptr(w23), L.ptr(b2), L.ptr(gamma), None, 49, L.ptr(sc), L.ptr(out3),
                                                  L.dt(torch.float32), M, C, 12 * C, L.dt(bf), 0, st))
     assert torch.equal(out, out3)
+
+
+@pytest.mark.parametrize("M,C", [(3136, 96), (1000, 128), (256, 192), (777, 192), (50176, 96)])
+def test_dgrad_gelu_recompute_matches_saved_gelu_prime(M, C):
+    """cnx_gemm_dgrad_gelu_recompute_bwd (GELU'(h) recomputed from xn, W1, b1 in a second TMEM accumulator) against the
+    two-kernel path it replaces at the HBM-bound stages: fc1 saving GELU'(h), then cnx_gemm_dgrad_gelu_bwd.  Same MMAs, same
+    roundings: bit-identical."""
+    from cabi import gemm_bias_gelu, gemm_dgelu
+    from imageclassification_b200 import _lib as L
+    lib = L.load()
+    bf = torch.bfloat16
+    xn, W1, b1, W2, b2, gamma = _mk(M, C, bf, 5 * M + C)
+    g = torch.Generator().manual_seed(M)
+    dz = torch.randn(M, C, generator=g).to(bf).to(DEV)
+    Bt = (gamma[:, None] * W2.float()).t().contiguous().to(bf)              # [4C, C] = (gamma . W2)^T
+    gp, _ = gemm_bias_gelu(xn, W1, b1)
+    ref = gemm_dgelu(dz, Bt, gp)
+    dh = torch.empty_like(ref)
+    L.check(lib.cnx_gemm_dgrad_gelu_recompute_bwd(L.ptr(dz), L.ptr(Bt), L.ptr(xn), L.ptr(W1), L.ptr(b1), L.ptr(dh), M, 4 * C, C,
+                                                  L.dt(bf), L.stream()), "gemm_dgrad_gelu_recompute_bwd")
+    assert torch.equal(dh, ref), max_rel(dh.float(), ref.float())
+    # and against float64 math on the same bf16 inputs
+    h = (xn.double() @ W1.double().t() + b1.double()).to(bf).double()
+    gpd = 0.5 * (1 + torch.erf(h / math.sqrt(2))) + h * torch.exp(-0.5 * h * h) / math.sqrt(2 * math.pi)
+    exact = (dz.double() @ Bt.double().t()) * gpd
+    assert max_rel(dh.double(), exact) <= 2e-2
