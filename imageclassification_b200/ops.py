@@ -30,10 +30,13 @@ KEEP_BF16_STREAM = os.environ.get("CNX_BF16_STREAM", "0") == "1"
 # with split bf16 operands (include/cnx.h "x3"): fp32-accurate (~2^-16 per product), 3 MMAs per product instead of CUDA-core
 # FMAs.  CNX_X3_FWD=0 selects the CUDA-core fp32 GEMMs for comparison.
 X3_FWD = os.environ.get("CNX_X3_FWD", "1") != "0"
-# Training forward at the HBM-bound stages (C <= RECOMPUTE_MAX_C, bf16): fc1 stores g only and the backward kernel recomputes
-# the pre-activation for GELU' (one [M,4C] tensor per Block instead of two; the tensor pipe idles there).  CNX_RECOMPUTE_C=0
-# turns it off (saved GELU'(h) everywhere).
-RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "192"))
+# Optional (CNX_RECOMPUTE_C=<max C>, default off): at C <= that, fc1 stores g only and the backward kernel recomputes the
+# pre-activation for GELU' in a second TMEM accumulator (one [M,4C] tensor per Block instead of two; bit-identical results).
+# Measured SLOWER on ConvNeXt-T/256 (profiles/r02k_*: fc1 K96 1.06 -> 0.89 ms but the data gradient 0.83 -> 1.19 ms; step 33.0 ->
+# 33.6 ms): these K <= 192 GEMMs are bound by their epilogue pipeline (TMEM -> registers -> GELU math -> shared memory -> TMA
+# store, ~2.3 us per 128 x 128 tile), not by the HBM writes the recomputation saves.  Kept for memory-limited runs: it saves
+# M*4C*2 bytes of saved activations per Block (2.3 GB per step for ConvNeXt-T at batch 256).
+RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "0"))
 
 
 def _act_dtype() -> torch.dtype:

@@ -185,3 +185,23 @@ def test_convnext_tiny_fp32_nograd_forward_on_tensor_cores():
     with torch.no_grad():
         lo, lp = o(x), p(x)
     assert max_rel(lp, lo) <= 1e-4
+
+
+@pytest.mark.parametrize("C,H", [(96, 28), (192, 14)])
+def test_block_backward_with_recomputed_gelu_prime(C, H, monkeypatch):
+    """ops.RECOMPUTE_MAX_C (CNX_RECOMPUTE_C): the forward stores g only and the backward kernel recomputes GELU'(h) — the same
+    gradients, bit for bit, as the default path that saves GELU'(h)."""
+    from imageclassification_b200 import ops
+    o, p = _pair_block(C, 0.0, 1.0, 7)
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(8, C, H, H, generator=g).to(DEV)
+    dout = torch.randn(8, C, H, H, generator=g).to(DEV)
+    y0, dx0, g0 = _run(p, x, dout, True, 1)
+    p.zero_grad()
+    monkeypatch.setattr(ops, "RECOMPUTE_MAX_C", 192)
+    y1, dx1, g1 = _run(p, x, dout, True, 1)
+    assert torch.equal(y0, y1) and torch.equal(dx0, dx1)
+    for n in g0:
+        assert torch.equal(g0[n], g1[n]), n
+    yo, dxo, go = _run(o, x, dout, True, 1)
+    assert max_rel(dx1, dxo) <= 2e-2
