@@ -246,6 +246,12 @@ def kernel_work(name, a):
         M, N1, N2 = a[2:5]
         e = es(a[10])
         return M * (N1 + N2) * e + N1 * N2 * 4, 2 * M * N1 * N2, f"wgrad {N1}x{N2}"
+    if name == "cnx_gemm_wgrad_x3":
+        M, N1, N2 = a[2:5]
+        return 3 * M * (N1 + N2) * 2 + N1 * N2 * 4, 2 * M * N1 * N2, f"wgrad_x3 {N1}x{N2}"
+    if name in ("cnx_gelu_split", "cnx_mul_split"):
+        M, N = (a[1:3] if name == "cnx_gelu_split" else a[2:4])
+        return M * N * (4 + 4 + 4), 0, f"{name[4:]} N{N}"
     if name == "cnx_grad_prep":
         M, C = a[4:6]
         return M * C * (es(a[1]) + es(a[7])), 0, f"grad_prep C{C}"

@@ -12,7 +12,7 @@ template <typename TIN>
 int gemm_wgrad_simt(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                     float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
-                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx = 0, int64_t ldy = 0);
 int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
                      cudaStream_t s);
@@ -149,6 +149,24 @@ int cnx_gemm_wgrad(const void* X, const void* Y, int64_t M, int64_t N1, int64_t 
   if (dtype == CNX_F32) return gemm_wgrad_simt<float>(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
   if (flags & CNX_GEMM_FORCE_SIMT) return gemm_wgrad_simt<bf16>(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
   return gemm_wgrad_tc(X, Y, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s);
+}
+
+/* fp32-accurate weight gradient on the tensor cores: X2 [M, 2*N1] = [hi | mid] and Y2 [M, 2*N2] = [hi | mid] (cnx_split3 with
+ * segments = 2, or the split outputs of the x3 kernels); out = Xhi^T.Yhi + Xmid^T.Yhi + Xhi^T.Ymid (three bf16 wgrad GEMMs over
+ * column blocks of the split tensors, accumulated in fp32), colsum_x = column sums of Xhi + Xmid. */
+int cnx_gemm_wgrad_x3(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                      float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream) {
+  CNX_REQUIRE(X2 && Y2 && out && workspace, CNX_E_BADARG, "gemm_wgrad_x3: null pointer");
+  CNX_REQUIRE(M > 0 && N1 > 0 && N2 > 0, CNX_E_BADARG, "gemm_wgrad_x3: bad shape");
+  CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_x3: N1, N2 must be multiples of 8");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bf16* Xh = (const bf16*)X2;
+  const bf16* Xm = Xh + N1;
+  const bf16* Yh = (const bf16*)Y2;
+  const bf16* Ym = Yh + N2;
+  if (int rc = gemm_wgrad_tc(Xh, Yh, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, s, 2 * N1, 2 * N2)) return rc;
+  if (int rc = gemm_wgrad_tc(Xm, Yh, M, N1, N2, 1, out, colsum_x, workspace, workspace_bytes, s, 2 * N1, 2 * N2)) return rc;
+  return gemm_wgrad_tc(Xh, Ym, M, N1, N2, 1, out, nullptr, workspace, workspace_bytes, s, 2 * N1, 2 * N2);
 }
 
 }  // extern "C"

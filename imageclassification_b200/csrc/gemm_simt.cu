@@ -226,6 +226,52 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
   }
 }
 
+__device__ __forceinline__ void split_store8(bf16* o, int64_t N, const float (&a)[8]) {
+  uint4 hi;
+  float r[8];
+  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    h2[k] = __floats2bfloat162_rn(a[2 * k], a[2 * k + 1]);
+    r[2 * k] = a[2 * k] - __low2float(h2[k]);
+    r[2 * k + 1] = a[2 * k + 1] - __high2float(h2[k]);
+  }
+  *reinterpret_cast<uint4*>(o) = hi;
+  store8(o + N, r);
+}
+
+// fp32 training on the tensor cores (split operands): h [M,N] fp32 (fc1 pre-activation incl. bias) ->
+//   g2 [M,2N] bf16 = [hi | mid] of GELU_erf(h)  (A operand of fc2),  h <- GELU_erf'(h) in place (what backward needs of h)
+__global__ void __launch_bounds__(256) gelu_split_kernel(float* __restrict__ h, int64_t M, int64_t N, bf16* __restrict__ g2) {
+  pdl_wait();
+  const int64_t vpr = N >> 3, total = M * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / vpr, v = i - m * vpr;
+    float a[8], g[8];
+    load8(h + m * N + v * 8, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { g[k] = gelu_erf(a[k]); a[k] = gelu_erf_grad(a[k]); }
+    split_store8(g2 + m * 2 * N + v * 8, N, g);
+    store8(h + m * N + v * 8, a);
+  }
+}
+
+// out2 [M,2N] bf16 = [hi | mid] of t[m,n] * u[m,n]  (dh = (dz.W2s) * GELU'(h), leaving as the split operand of the next GEMMs)
+__global__ void __launch_bounds__(256) mul_split_kernel(const float* __restrict__ t, const float* __restrict__ u, int64_t M, int64_t N,
+                                                        bf16* __restrict__ out2) {
+  pdl_wait();
+  const int64_t vpr = N >> 3, total = M * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t m = i / vpr, v = i - m * vpr;
+    float a[8], b[8];
+    load8(t + m * N + v * 8, a);
+    load8(u + m * N + v * 8, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= b[k];
+    split_store8(out2 + m * 2 * N + v * 8, N, a);
+  }
+}
+
 template <typename TO>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, int64_t R, int64_t Cc,
                                                           const float* __restrict__ row_scale, int mode,
@@ -409,6 +455,26 @@ int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_ti
               "weight_prep_multi: bad argument");
   launch_pdl(weight_prep_multi_kernel, dim3((unsigned)total_tiles), dim3(256), 0, (cudaStream_t)stream, (const WeightPrepEntry*)table_dev, n_entries);
   return check_launch("weight_prep_multi");
+}
+
+int cnx_gelu_split(float* h, int64_t M, int64_t N, void* g2, void* stream) {
+  CNX_REQUIRE(h && g2 && M > 0 && N > 0, CNX_E_BADARG, "gelu_split: bad argument");
+  CNX_REQUIRE(N % 8 == 0 && (((uintptr_t)h) & 15) == 0 && (((uintptr_t)g2) & 15) == 0, CNX_E_SHAPE,
+              "gelu_split: N=%lld must be a multiple of 8 and the pointers 16-byte aligned", (long long)N);
+  int64_t grid = (M * (N / 8) + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  launch_pdl(gelu_split_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, h, M, N, (bf16*)g2);
+  return check_launch("gelu_split");
+}
+
+int cnx_mul_split(const float* t, const float* u, int64_t M, int64_t N, void* out2, void* stream) {
+  CNX_REQUIRE(t && u && out2 && M > 0 && N > 0, CNX_E_BADARG, "mul_split: bad argument");
+  CNX_REQUIRE(N % 8 == 0 && ((((uintptr_t)t) | ((uintptr_t)u) | ((uintptr_t)out2)) & 15) == 0, CNX_E_SHAPE,
+              "mul_split: N=%lld must be a multiple of 8 and the pointers 16-byte aligned", (long long)N);
+  int64_t grid = (M * (N / 8) + 255) / 256;
+  if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+  launch_pdl(mul_split_kernel, dim3((unsigned)grid), dim3(256), 0, (cudaStream_t)stream, t, u, M, N, (bf16*)out2);
+  return check_launch("mul_split");
 }
 
 int cnx_layerscale_finalize(const float* G2, const float* s, const float* W2, const float* b2, const float* gamma,

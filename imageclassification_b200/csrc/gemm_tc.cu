@@ -1537,13 +1537,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 row-major tensor [rows, cols]; box = [box_rows][64 cols], 128-byte swizzle, OOB -> zeros
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows, int64_t ld = 0) {
   EncodeTiledFn enc = get_encode();
   CNX_REQUIRE(enc != nullptr, CNX_E_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   CNX_REQUIRE((((uintptr_t)ptr) & 15) == 0, CNX_E_SHAPE, "GEMM operand must be 16-byte aligned");
   CNX_REQUIRE(cols % 8 == 0, CNX_E_SHAPE, "GEMM operand inner dimension %lld must be a multiple of 8", (long long)cols);
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * 2};     // ld: row stride in elements when the operand is a column block
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
@@ -1863,14 +1863,16 @@ static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int
 }
 
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
-                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx, int64_t ldy) {
   CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_tc: N1, N2 must be multiples of 8");
+  CNX_REQUIRE((ldx == 0 || (ldx >= N1 && ldx % 8 == 0)) && (ldy == 0 || (ldy >= N2 && ldy % 8 == 0)), CNX_E_SHAPE,
+              "gemm_wgrad_tc: row strides must cover the rows and be multiples of 8");
   const WgPlan pl = wgrad_plan_tc(M, N1, N2);
   const int splits = pl.splits;
   CNX_REQUIRE(workspace_bytes >= (int64_t)splits * (N1 * N2 + N1) * 4, CNX_E_WORKSPACE, "gemm_wgrad: workspace too small");
   CUtensorMap tmX, tmY;
-  if (int rc = tc::make_map(&tmX, X, M, N1, tc::BK)) return rc;
-  if (int rc = tc::make_map(&tmY, Y, M, N2, tc::BK)) return rc;
+  if (int rc = tc::make_map(&tmX, X, M, N1, tc::BK, ldx)) return rc;
+  if (int rc = tc::make_map(&tmY, Y, M, N2, tc::BK, ldy)) return rc;
   const int64_t kb_total = (M + tc::BK - 1) / tc::BK;
   const int kb_per_split = (int)((kb_total + splits - 1) / splits);
   float* part = (float*)workspace;

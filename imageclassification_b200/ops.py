@@ -37,6 +37,10 @@ X3_FWD = os.environ.get("CNX_X3_FWD", "1") != "0"
 # store, ~2.3 us per 128 x 128 tile), not by the HBM writes the recomputation saves.  Kept for memory-limited runs: it saves
 # M*4C*2 bytes of saved activations per Block (2.3 GB per step for ConvNeXt-T at batch 256).
 RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "0"))
+# fp32 TRAINING (no autocast: the reference's --use_amp false default, BASELINE config 1) on the tensor cores: forward and the
+# four backward GEMMs of the Block run as split-operand (x3) tcgen05 GEMMs, fp32-accurate to ~2^-16 per product, instead of the
+# CUDA-core fp32 GEMMs.  CNX_X3_TRAIN=0 selects the CUDA-core kernels for comparison.
+X3_TRAIN = os.environ.get("CNX_X3_TRAIN", "1") != "0"
 
 
 def _act_dtype() -> torch.dtype:
@@ -245,6 +249,60 @@ def _wgrad(X, Y, M, N1, N2, want_colsum: bool, out=None, cs=None, accumulate: in
     return out, cs
 
 
+def _split_of(params, tag, build32, rows, cols):
+    """[hi | hi | mid] bf16 split (weight-prep mode 3) of a derived fp32 weight layout, rebuilt when the parameters change"""
+    def build():
+        w32 = build32()
+        out = torch.empty((rows, 3 * cols), dtype=torch.bfloat16, device=w32.device)
+        L.check(L.load().cnx_weight_prep(L.ptr(w32), rows, cols, None, 3, L.ptr(out), L.dt(torch.bfloat16), L.stream()), "weight_prep(x3)")
+        return out
+    return _derived(params, tag, build)
+
+
+def _mlp_backward_x3(lib, params, doutl, a2, gp, g2, w1, w2, b2, gamma, dp, M, C, C4, rows_per_sample, dev, st):
+    """Backward of fc1 -> GELU -> fc2 -> layer-scale in fp32 accuracy on the tensor cores (split operands):
+    -> dxn fp32 [M,C], dW1, db1, dW2, db2, dgamma (None where a gradient sink took the result)."""
+    p_w1, p_b1, p_w2, p_b2, p_gamma = params[4:9]
+    bf, f32 = torch.bfloat16, torch.float32
+    # 1. dz = dp * dout (fp32), as the split operand [hi | mid]
+    dz32 = doutl.reshape(M, C)
+    if dp is not None:
+        t = torch.empty((M, C), dtype=f32, device=dev)
+        L.check(lib.cnx_grad_prep(L.ptr(dz32), L.dt(f32), L.ptr(dp), rows_per_sample, M, C, L.ptr(t), L.dt(f32), st), "grad_prep")
+        dz32 = t
+    dz2 = torch.empty((M, 2 * C), dtype=bf, device=dev)
+    L.check(lib.cnx_split3(L.ptr(dz32), M, C, L.ptr(dz2), 2, st), "split3")
+    # 2. dh = (dz . (gamma*W2)) * GELU'(h), leaving as a split operand
+    w2gt3 = _split_of((w2, gamma), ("w2gt_x3",), lambda: _weight_prep(w2, 2, gamma, f32), C4, C)            # [4C, 3C]
+    t1 = torch.empty((M, C4), dtype=f32, device=dev)
+    L.check(lib.cnx_gemm_plain(L.ptr(dz2), L.ptr(w2gt3), None, L.ptr(t1), L.dt(f32), M, C4, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st),
+            "gemm_plain(x3 dgrad fc2)")
+    dh2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)
+    L.check(lib.cnx_mul_split(L.ptr(t1), L.ptr(gp), M, C4, L.ptr(dh2), st), "mul_split")
+    del t1
+    # 3. fc2 wgrad on the unscaled gradient + layer-scale identities
+    ws_bytes = max(lib.cnx_gemm_wgrad_workspace_bytes(M, C, C4, L.CNX_BF16, 0), lib.cnx_gemm_wgrad_workspace_bytes(M, C4, C, L.CNX_BF16, 0))
+    ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
+    G2 = torch.empty((C, C4), dtype=f32, device=dev)
+    s = torch.empty((C,), dtype=f32, device=dev)
+    L.check(lib.cnx_gemm_wgrad_x3(L.ptr(dz2), L.ptr(g2), M, C, C4, 0, L.ptr(G2), L.ptr(s), L.ptr(ws), ws_bytes, st), "gemm_wgrad_x3")
+    d_fc2 = _Dest((p_w2, p_b2, p_gamma), (w2.shape, b2.shape, (C,)))
+    L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, d_fc2.acc,
+                                        L.ptr(d_fc2.bufs[0]), L.ptr(d_fc2.bufs[1]), L.ptr(d_fc2.bufs[2]), st), "layerscale_finalize")
+    dW2, db2, dgamma = d_fc2.results()
+    # 4. dxn = dh . W1
+    w1t3 = _split_of((w1,), ("w1t_x3",), lambda: _weight_prep(w1, 1, None, f32), C, C4)                      # [C, 3*4C]
+    dxn = torch.empty((M, C), dtype=f32, device=dev)
+    L.check(lib.cnx_gemm_plain(L.ptr(dh2), L.ptr(w1t3), None, L.ptr(dxn), L.dt(f32), M, C, 3 * C4, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st),
+            "gemm_plain(x3 dgrad fc1)")
+    # 5. fc1 wgrad + bias grad
+    d_fc1 = _Dest((p_w1, p_b1), (w1.shape, (C4,)))
+    L.check(lib.cnx_gemm_wgrad_x3(L.ptr(dh2), L.ptr(a2), M, C4, C, d_fc1.acc, L.ptr(d_fc1.bufs[0]), L.ptr(d_fc1.bufs[1]), L.ptr(ws),
+                                  ws_bytes, st), "gemm_wgrad_x3")
+    dW1, db1 = d_fc1.results()
+    return dxn, dW1, db1, dW2, db2, dgamma
+
+
 class _BlockFn(torch.autograd.Function):
     """dwconv7 -> LN -> fc1 -> GELU -> fc2 -> gamma -> drop_path -> + shortcut, forward and backward."""
 
@@ -286,6 +344,29 @@ class _BlockFn(torch.autograd.Function):
                                                          L.ptr(dp), H * W, L.ptr(xl), L.ptr(out), sd, M, C, 3 * C4, L.dt(bf),
                                                          L.CNX_GEMM_A_SPLIT2, st), "gemm_bias_scale_residual_fwd(x3)")
             return out.permute(0, 3, 1, 2)
+        if need_grad and X3_TRAIN and act_dtype == torch.float32 and C % 32 == 0 and C4 % 64 == 0 and GEMM_FLAGS == 0:
+            # fp32 training on the tensor cores: every GEMM operand crosses as [hi | mid] bf16 pieces and the K loops cover
+            # hi.hi + mid.hi + hi.mid (include/cnx.h "x3").  Saved for backward: y, the split xn, GELU'(h) (fp32, in h's buffer),
+            # the split g
+            bf = torch.bfloat16
+            a2 = torch.empty((M, 2 * C), dtype=bf, device=dev)
+            L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(xl), L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C,
+                                              L.ptr(y), L.ptr(a2), L.ptr(mean), L.ptr(rstd), 2, st), "dwconv7_ln_fwd_x3")
+            h = torch.empty((M, C4), dtype=torch.float32, device=dev)
+            L.check(lib.cnx_gemm_plain(L.ptr(a2), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), L.ptr(h), L.dt(torch.float32), M, C4,
+                                       3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st), "gemm_plain(x3 fc1)")
+            g2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)
+            L.check(lib.cnx_gelu_split(L.ptr(h), M, C4, L.ptr(g2), st), "gelu_split")         # h now holds GELU'(h)
+            out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+            L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g2), L.ptr(_weight_prep(w2, 3, None, bf)), L.ptr(b2), L.ptr(gamma),
+                                                         L.ptr(dp), H * W, L.ptr(xl), L.ptr(out), sd, M, C, 3 * C4, L.dt(bf),
+                                                         L.CNX_GEMM_A_SPLIT2, st), "gemm_bias_scale_residual_fwd(x3)")
+            ctx.save_for_backward(xl, y, a2, mean, rstd, h, g2, conv_w, ln_w, w1, w2, b2, gamma, dp)
+            ctx.shape = (N, C, H, W)
+            ctx.act_dtype = act_dtype
+            ctx.x3 = True
+            ctx.params = (conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma)
+            return out.permute(0, 3, 1, 2)
         xn = torch.empty((M, C), dtype=act_dtype, device=dev)
         L.check(lib.cnx_dwconv7_ln_fwd(L.ptr(xl), sd, L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps,
                                        N, H, W, C, L.ptr(y), L.ptr(xn), ad, L.ptr(mean), L.ptr(rstd), st), "dwconv7_ln_fwd")
@@ -316,6 +397,7 @@ class _BlockFn(torch.autograd.Function):
             ctx.save_for_backward(xl, y, xn, mean, rstd, h, g, conv_w, ln_w, w1, w2, b2, gamma, dp)
             ctx.shape = (N, C, H, W)
             ctx.act_dtype = act_dtype
+            ctx.x3 = False
             ctx.params = (conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma)     # the leaves themselves (gradient sinks)
         return out.permute(0, 3, 1, 2)
 
@@ -332,39 +414,43 @@ class _BlockFn(torch.autograd.Function):
         doutl = _nhwc(dout)
         if doutl.dtype != xl.dtype:
             doutl = doutl.to(xl.dtype)
-        # 1. dz = act(dp * dout): the operand copy of the incoming gradient (drop-path folded in once)
-        if dp is None and act_dtype == xl.dtype:
-            dz = doutl.reshape(M, C)
-        else:
-            dz = torch.empty((M, C), dtype=act_dtype, device=dev)
-            L.check(lib.cnx_grad_prep(L.ptr(doutl), sd, L.ptr(dp), H * W, M, C, L.ptr(dz), ad, st), "grad_prep")
-        # 2. dh = (dz . (gamma*W2)) * GELU'(h)
-        w2gt = _weight_prep(w2, 2, gamma, act_dtype)            # [4C, C]
-        dh = torch.empty((M, C4), dtype=act_dtype, device=dev)
-        if h is None:
-            # GELU'(h) was not saved: the kernel recomputes h = xn . W1^T + b1 beside the data gradient
-            L.check(lib.cnx_gemm_dgrad_gelu_recompute_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(xn), L.ptr(_weight_prep(w1, 0, None, act_dtype)),
-                                                          L.ptr(ctx.params[5]), L.ptr(dh), M, C4, C, ad, st),
-                    "gemm_dgrad_gelu_recompute_bwd")
-        else:
-            L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
-                    "gemm_dgrad_gelu_bwd")
-        # 3. fc2 wgrad on the UNSCALED gradient; layer-scale identities give dW2, db2, dgamma without saving z
         p_conv_w, p_conv_b, p_ln_w, p_ln_b, p_w1, p_b1, p_w2, p_b2, p_gamma = ctx.params
-        G2, s = _wgrad(dz, g, M, C, C4, True)
-        d_fc2 = _Dest((p_w2, p_b2, p_gamma), (w2.shape, b2.shape, (C,)))
-        dW2, db2, dgamma = d_fc2.bufs
-        L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, d_fc2.acc,
-                                            L.ptr(dW2), L.ptr(db2), L.ptr(dgamma), st), "layerscale_finalize")
-        dW2, db2, dgamma = d_fc2.results()
-        # 4. dxn = dh . W1
-        w1t = _weight_prep(w1, 1, None, act_dtype)              # [C, 4C]
-        dxn = torch.empty((M, C), dtype=act_dtype, device=dev)
-        L.check(lib.cnx_gemm_plain(L.ptr(dh), L.ptr(w1t), None, L.ptr(dxn), ad, M, C, C4, ad, GEMM_FLAGS, st), "gemm_plain")
-        # 5. fc1 wgrad + bias grad
-        d_fc1 = _Dest((p_w1, p_b1), (w1.shape, (C4,)))
-        _wgrad(dh, xn, M, C4, C, True, out=d_fc1.bufs[0], cs=d_fc1.bufs[1], accumulate=d_fc1.acc)
-        dW1, db1 = d_fc1.results()
+        if ctx.x3:
+            dxn, dW1, db1, dW2, db2, dgamma = _mlp_backward_x3(lib, ctx.params, doutl, xn, h, g, w1, w2, b2, gamma, dp, M, C, C4,
+                                                              H * W, dev, st)
+        else:
+            # 1. dz = act(dp * dout): the operand copy of the incoming gradient (drop-path folded in once)
+            if dp is None and act_dtype == xl.dtype:
+                dz = doutl.reshape(M, C)
+            else:
+                dz = torch.empty((M, C), dtype=act_dtype, device=dev)
+                L.check(lib.cnx_grad_prep(L.ptr(doutl), sd, L.ptr(dp), H * W, M, C, L.ptr(dz), ad, st), "grad_prep")
+            # 2. dh = (dz . (gamma*W2)) * GELU'(h)
+            w2gt = _weight_prep(w2, 2, gamma, act_dtype)            # [4C, C]
+            dh = torch.empty((M, C4), dtype=act_dtype, device=dev)
+            if h is None:
+                # GELU'(h) was not saved: the kernel recomputes h = xn . W1^T + b1 beside the data gradient
+                L.check(lib.cnx_gemm_dgrad_gelu_recompute_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(xn), L.ptr(_weight_prep(w1, 0, None, act_dtype)),
+                                                              L.ptr(ctx.params[5]), L.ptr(dh), M, C4, C, ad, st),
+                        "gemm_dgrad_gelu_recompute_bwd")
+            else:
+                L.check(lib.cnx_gemm_dgrad_gelu_bwd(L.ptr(dz), L.ptr(w2gt), L.ptr(h), L.ptr(dh), M, C4, C, ad, GEMM_FLAGS, st),
+                        "gemm_dgrad_gelu_bwd")
+            # 3. fc2 wgrad on the UNSCALED gradient; layer-scale identities give dW2, db2, dgamma without saving z
+            G2, s = _wgrad(dz, g, M, C, C4, True)
+            d_fc2 = _Dest((p_w2, p_b2, p_gamma), (w2.shape, b2.shape, (C,)))
+            dW2, db2, dgamma = d_fc2.bufs
+            L.check(lib.cnx_layerscale_finalize(L.ptr(G2), L.ptr(s), L.ptr(w2), L.ptr(b2), L.ptr(gamma), C, C4, d_fc2.acc,
+                                                L.ptr(dW2), L.ptr(db2), L.ptr(dgamma), st), "layerscale_finalize")
+            dW2, db2, dgamma = d_fc2.results()
+            # 4. dxn = dh . W1
+            w1t = _weight_prep(w1, 1, None, act_dtype)              # [C, 4C]
+            dxn = torch.empty((M, C), dtype=act_dtype, device=dev)
+            L.check(lib.cnx_gemm_plain(L.ptr(dh), L.ptr(w1t), None, L.ptr(dxn), ad, M, C, C4, ad, GEMM_FLAGS, st), "gemm_plain")
+            # 5. fc1 wgrad + bias grad
+            d_fc1 = _Dest((p_w1, p_b1), (w1.shape, (C4,)))
+            _wgrad(dh, xn, M, C4, C, True, out=d_fc1.bufs[0], cs=d_fc1.bufs[1], accumulate=d_fc1.acc)
+            dW1, db1 = d_fc1.results()
         # 6. LayerNorm backward
         P = _num_partials(C)
         dy = torch.empty((M, C), dtype=act_dtype, device=dev)

@@ -221,6 +221,19 @@ CNX_API int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* 
 CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
                               void* g3, int a_segments, void* stream);
 
+/* fp32 TRAINING on the tensor cores (the reference's default --use_amp false): the same split-operand scheme for the training
+ * forward and the four backward GEMMs.  Elementwise pieces between the GEMMs:
+ *   cnx_gelu_split   h fp32 [M,N] (fc1 pre-activation incl. bias, from cnx_gemm_plain) -> g2 bf16 [M,2N] = [hi | mid] of GELU_erf(h)
+ *                    (A operand of fc2); h is overwritten with GELU_erf'(h) (saved for backward)
+ *   cnx_mul_split    out2 bf16 [M,2N] = [hi | mid] of t * u   (dh = (dz.W2s) * GELU'(h))
+ *   cnx_gemm_wgrad_x3  out fp32 [N1,N2] (+)= X^T.Y from X2 [M,2*N1] = [hi | mid], Y2 [M,2*N2] = [hi | mid]: three bf16 wgrad GEMMs
+ *                    (hi.hi + mid.hi + hi.mid) accumulated in fp32; colsum_x [N1] (+)= column sums of X (may be NULL).
+ *                    workspace as cnx_gemm_wgrad_workspace_bytes(M, N1, N2, CNX_BF16, 0). */
+CNX_API int cnx_gelu_split(float* h, int64_t M, int64_t N, void* g2, void* stream);
+CNX_API int cnx_mul_split(const float* t, const float* u, int64_t M, int64_t N, void* out2, void* stream);
+CNX_API int cnx_gemm_wgrad_x3(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                      float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Fused no-grad MLP forward for the HBM-bound stages (C in {96, 128, 192}; bf16 operands, fp32 residual stream):
  *   out[m,:] = shortcut[m,:] + dp[m / rows_per_sample] * gamma * (GELU_erf(xn[m,:].W1^T + b1).W2^T + b2)
  * in one kernel — the [M,4C] hidden activation stays in shared / tensor memory (convnext.py:48-55 in one pass).
