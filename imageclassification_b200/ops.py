@@ -237,6 +237,22 @@ class _Dest:
 
 def _wgrad(X, Y, M, N1, N2, want_colsum: bool, out=None, cs=None, accumulate: int = 0):
     lib = L.load()
+    if X.dtype == torch.float32 and Y.dtype == torch.float32 and X3_TRAIN and GEMM_FLAGS == 0 and N1 % 8 == 0 and N2 % 8 == 0:
+        # fp32 operands: three bf16 tensor-core wgrad GEMMs over the split operands (fp32-accurate), not the CUDA-core kernel
+        bf = torch.bfloat16
+        x2 = torch.empty((M, 2 * N1), dtype=bf, device=X.device)
+        y2 = torch.empty((M, 2 * N2), dtype=bf, device=X.device)
+        L.check(lib.cnx_split3(L.ptr(X), M, N1, L.ptr(x2), 2, L.stream()), "split3")
+        L.check(lib.cnx_split3(L.ptr(Y), M, N2, L.ptr(y2), 2, L.stream()), "split3")
+        ws_bytes = lib.cnx_gemm_wgrad_workspace_bytes(M, N1, N2, L.CNX_BF16, 0)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=X.device)
+        if out is None:
+            out = torch.empty((N1, N2), dtype=torch.float32, device=X.device)
+        if cs is None and want_colsum:
+            cs = torch.empty((N1,), dtype=torch.float32, device=X.device)
+        L.check(lib.cnx_gemm_wgrad_x3(L.ptr(x2), L.ptr(y2), M, N1, N2, int(accumulate), L.ptr(out), L.ptr(cs), L.ptr(ws), ws_bytes,
+                                      L.stream()), "gemm_wgrad_x3")
+        return out, cs
     d = L.dt(X)
     ws_bytes = lib.cnx_gemm_wgrad_workspace_bytes(M, N1, N2, d, GEMM_FLAGS)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=X.device)
@@ -541,9 +557,34 @@ def _gemm_plain(A, B, bias, out_dtype):
     lib = L.load()
     M, K = A.shape
     Nn = B.shape[0]
+    if (A.dtype == torch.float32 and B.dtype == torch.float32 and out_dtype == torch.float32 and X3_TRAIN and GEMM_FLAGS == 0
+            and K % 8 == 0 and Nn % 8 == 0):
+        return _gemm_plain_f32_x3(A, B, bias)          # fp32 operands: fp32-accurate split-operand GEMM on the tensor cores
     out = torch.empty((M, Nn), dtype=out_dtype, device=A.device)
     L.check(lib.cnx_gemm_plain(L.ptr(A), L.ptr(B), L.ptr(bias), L.ptr(out), L.dt(out_dtype), M, Nn, K, L.dt(A), GEMM_FLAGS,
                                L.stream()), "gemm_plain")
+    return out
+
+
+def _gemm_plain_f32_x3(A, B32, bias):
+    """fp32 out[M,N] = A[M,K] . B32[N,K]^T + bias with split bf16 operands: B's [hi | hi | mid] layout is cached per version of
+    B32, A is split on the fly ([hi | mid] + wrapping K loop where K is a multiple of 32, three segments otherwise)."""
+    lib = L.load()
+    M, K = A.shape
+    Nn = B32.shape[0]
+    bf = torch.bfloat16
+
+    def build():
+        out = torch.empty((Nn, 3 * K), dtype=bf, device=B32.device)
+        L.check(lib.cnx_weight_prep(L.ptr(B32), Nn, K, None, 3, L.ptr(out), L.dt(bf), L.stream()), "weight_prep(x3)")
+        return out
+    B3 = _derived((B32,), ("b_x3",), build)
+    seg2 = K % 32 == 0
+    a3 = torch.empty((M, (2 if seg2 else 3) * K), dtype=bf, device=A.device)
+    L.check(lib.cnx_split3(L.ptr(A), M, K, L.ptr(a3), 2 if seg2 else 3, L.stream()), "split3")
+    out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    L.check(lib.cnx_gemm_plain(L.ptr(a3), L.ptr(B3), L.ptr(bias), L.ptr(out), L.dt(torch.float32), M, Nn, 3 * K, L.dt(bf),
+                               L.CNX_GEMM_A_SPLIT2 if seg2 else 0, L.stream()), "gemm_plain(x3)")
     return out
 
 

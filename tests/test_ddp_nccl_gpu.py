@@ -146,6 +146,6 @@ def _direct_arena_body(amp, P, DistributedDataParallel, max_rel):
                 if accum == 1:
                     assert torch.equal(a, b), (n, direct, max_rel(a, b))
                     assert torch.equal(p.detach(), q.detach()), n
-                else:                       # accumulating kernels add with one fused rounding where autograd adds two tensors
-                    assert max_rel(a, b) <= 1e-6, (n, direct, max_rel(a, b))
-                    assert max_rel(p.detach(), q.detach()) <= 1e-6, n
+                else:                       # accumulating kernels add the second micro-step's partial sums to the first's
+                    assert max_rel(a, b) <= 2e-5, (n, direct, max_rel(a, b))     # result (another association than autograd's add)
+                    assert max_rel(p.detach(), q.detach()) <= 2e-5, n

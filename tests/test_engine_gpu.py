@@ -46,7 +46,10 @@ def test_engine_matches_reference_golden_config1():
                                num_training_steps_per_epoch=2, update_freq=1, use_amp=False, num_classes=2, verbose=False)
     assert abs(stats["loss"] - float(z["b.loss"])) <= 1e-4 * abs(float(z["b.loss"]))
     assert stats["class_acc"] == float(z["b.class_acc"])
-    np.testing.assert_allclose(_norms(model.parameters()), z["b.param_norms"], rtol=1e-4, atol=1e-6)
+    # (absolute floor for the zero-initialised biases: after two Adam steps every element has moved by ~lr = 1e-3 in the direction
+    # of its gradient's sign whatever the gradient's size, so the 1e-5 gradient noise of the split-operand tensor-core GEMMs — inside the
+    # 1e-4 gradient bar, tests/test_block_gpu.py — can turn single near-zero elements: measured 2.4e-5 on a 1.3e-2 norm)
+    np.testing.assert_allclose(_norms(model.parameters()), z["b.param_norms"], rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(_norms(ema.module.parameters()), z["b.ema_norms"], rtol=1e-5, atol=1e-8)
     ps = np.array([p.detach().double().sum().item() for p in model.parameters()])
     np.testing.assert_allclose(ps, z["b.param_sums"], rtol=0, atol=2e-3 * np.abs(z["b.param_norms"]).max())
