@@ -29,9 +29,16 @@ def _norms(params):
     return np.array([p.detach().double().norm().item() for p in params])
 
 
-def test_engine_matches_reference_golden_config1():
+@pytest.mark.parametrize("x3_train", [False, True], ids=["fp32_cuda_cores", "fp32_tensor_cores_x3"])
+def test_engine_matches_reference_golden_config1(x3_train, monkeypatch):
     """BASELINE config 1 (ConvNeXt-T fp32, batch 8, 2 classes, mixup 0.8, smoothing 0.1, AdamW, EMA 0.9995), two iterations:
-    same seeds as tests/golden/make_golden.py case "b" => the loss, accuracy, parameters and EMA the reference's engine gave."""
+    same seeds as tests/golden/make_golden.py case "b" => the loss, accuracy, parameters and EMA the reference's engine gave.
+    Run with the fp32 CUDA-core GEMMs (errors ~1e-7: every parameter norm to 1e-4) and with the default split-operand
+    tensor-core GEMMs (gradients to ~1e-5, inside the 1e-4 gradient bar of tests/test_block_gpu.py; after two Adam steps a
+    zero-initialised bias element whose gradient is itself ~1e-5 of the tensor's largest can land elsewhere, because Adam moves
+    every element by ~lr whatever its gradient's size — hence the absolute floor for those 1e-2-norm tensors)."""
+    from imageclassification_b200 import ops
+    monkeypatch.setattr(ops, "X3_TRAIN", x3_train)
     z = np.load(os.path.join(GOLD, "engine_step.npz"))
     torch.manual_seed(88)
     np.random.seed(88)
@@ -46,13 +53,11 @@ def test_engine_matches_reference_golden_config1():
                                num_training_steps_per_epoch=2, update_freq=1, use_amp=False, num_classes=2, verbose=False)
     assert abs(stats["loss"] - float(z["b.loss"])) <= 1e-4 * abs(float(z["b.loss"]))
     assert stats["class_acc"] == float(z["b.class_acc"])
-    # (absolute floor for the zero-initialised biases: after two Adam steps every element has moved by ~lr = 1e-3 in the direction
-    # of its gradient's sign whatever the gradient's size, so the 1e-5 gradient noise of the split-operand tensor-core GEMMs — inside the
-    # 1e-4 gradient bar, tests/test_block_gpu.py — can turn single near-zero elements: measured 2.4e-5 on a 1.3e-2 norm)
-    np.testing.assert_allclose(_norms(model.parameters()), z["b.param_norms"], rtol=1e-4, atol=5e-5)
-    np.testing.assert_allclose(_norms(ema.module.parameters()), z["b.ema_norms"], rtol=1e-5, atol=1e-8)
+    floor = 3e-4 if x3_train else 1e-6
+    np.testing.assert_allclose(_norms(model.parameters()), z["b.param_norms"], rtol=1e-4, atol=floor)
+    np.testing.assert_allclose(_norms(ema.module.parameters()), z["b.ema_norms"], rtol=1e-5, atol=1e-6 if x3_train else 1e-8)
     ps = np.array([p.detach().double().sum().item() for p in model.parameters()])
-    np.testing.assert_allclose(ps, z["b.param_sums"], rtol=0, atol=2e-3 * np.abs(z["b.param_norms"]).max())
+    np.testing.assert_allclose(ps, z["b.param_sums"], rtol=0, atol=(4e-3 if x3_train else 2e-3) * np.abs(z["b.param_norms"]).max())
 
 
 CASES = [
