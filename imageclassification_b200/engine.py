@@ -104,7 +104,7 @@ class DevicePrefetcher:
                                                  "busy": False}
         if st["busy"]:
             # a second loader iterated while another one is live on this device (nested loops): private stream and buffers
-            return {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None], "busy": True}
+            return {"stream": torch.cuda.Stream(self.device), "bufs": {}, "released": [None, None], "busy": True, "private": True}
         st["busy"] = True
         return st
 
@@ -161,6 +161,12 @@ class DevicePrefetcher:
                 if ev is not None:
                     torch.cuda.current_stream(dev).wait_event(ev)
                 prev_slot = slot
+                if st is not None and st.get("private"):
+                    # private buffers die with this iterator: tell the caching allocator that the consumer's stream uses them,
+                    # so that their memory is not handed out again while kernels enqueued there still read it
+                    for buf in (s, t):
+                        if buf.is_cuda:
+                            buf.record_stream(torch.cuda.current_stream(dev))
                 nxt = fetch()
                 yield s, t
         finally:
