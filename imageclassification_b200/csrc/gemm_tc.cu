@@ -236,9 +236,18 @@ __device__ __forceinline__ float exp2f_fast(float x) {
 // Phi(x) - 0.5 = xc * P(xc^2) on |x| <= 4.5 (clamped beyond: |Phi - {0,1}| < 3.4e-6 there), degree-9 minimax fit of the
 // normal CDF, max abs error 1.4e-5 (profiles/fit_phi.py) — far below the bf16 resolution of the stored results.  No MUFU, no
 // division; evaluated two elements at a time with the packed fp32x2 FMA so the epilogue costs half the issue slots.
+// copysign(min(|x|, r), x) in ONE instruction (min.xorsign.abs: sign = sign(x) ^ sign(r), r > 0)
+__device__ __forceinline__ float clamp_sym(float x, float r) {
+  float y;
+  asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(r));
+  return y;
+}
 __device__ __forceinline__ float2 phi_minus_half2(float2 x) {
+  // symmetric input clamp: one FMNMX per element instead of a min and a max.  No clamp of the result: the fit leaves
+  // Phi in [-1.4e-5, 1 + 1.4e-5], i.e. |g - GELU(x)| <= 1.4e-5 |x| <= 6.3e-5 on the clamped range — four FMNMX per pair less
+  // in an epilogue that is bound by its instruction count (profiles/r02p_*: 8 of ~35 math instructions per pair were clamps)
   const float R = 4.5f;
-  float2 xc = make_float2(fminf(fmaxf(x.x, -R), R), fminf(fmaxf(x.y, -R), R));
+  float2 xc = make_float2(clamp_sym(x.x, R), clamp_sym(x.y, R));
   const float2 t = __fmul2_rn(xc, xc);
   float2 p = make_float2(-1.726107430e-12f, -1.726107430e-12f);
   p = __ffma2_rn(p, t, make_float2(2.022235545e-10f, 2.022235545e-10f));
@@ -250,10 +259,7 @@ __device__ __forceinline__ float2 phi_minus_half2(float2 x) {
   p = __ffma2_rn(p, t, make_float2(9.891897850e-03f, 9.891897850e-03f));
   p = __ffma2_rn(p, t, make_float2(-6.642163740e-02f, -6.642163740e-02f));
   p = __ffma2_rn(p, t, make_float2(3.989305611e-01f, 3.989305611e-01f));
-  float2 s = __fmul2_rn(p, xc);
-  s.x = fminf(fmaxf(s.x, -0.5f), 0.5f);
-  s.y = fminf(fmaxf(s.y, -0.5f), 0.5f);
-  return s;
+  return __fmul2_rn(p, xc);
 }
 // g = GELU(x) = x * Phi(x); if WITH_GRAD also gp = GELU'(x) = Phi(x) + x * pdf(x)
 template <bool WITH_GRAD>
@@ -265,9 +271,10 @@ __device__ __forceinline__ void gelu_pair(float2 x, float2& g, float2& gp) {
     // pdf(x) = exp2(-x^2 * log2(e)/2) / sqrt(2 pi)
     const float2 t = __fmul2_rn(x, x);
     const float kc = -0.72134752044448170368f;
+    const float2 ta = __fmul2_rn(t, make_float2(kc, kc));
     float2 e;
-    e.x = exp2f_fast(t.x * kc);
-    e.y = exp2f_fast(t.y * kc);
+    e.x = exp2f_fast(ta.x);
+    e.y = exp2f_fast(ta.y);
     const float2 xk = __fmul2_rn(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f));
     gp = __ffma2_rn(xk, e, phi);
   }
