@@ -24,6 +24,8 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--only", default="")
 ap.add_argument("--stages", default="0,1,2,3")
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--call-log", default=None, help="write [C-ABI name, bench label] of EVERY libcnx call of this run, in launch order "
+                                                 "(to match an ncu launch list of the same command: profiles/make_traffic.py)")
 args = ap.parse_args()
 dev = "cuda"
 peaks = bench._peaks()
@@ -32,8 +34,21 @@ STAGES = [(96, 56), (192, 28), (384, 14), (768, 7)]
 only = set(args.only.split(",")) if args.only else None
 
 
+CALLS = []
+
+
+class _Log:
+    """stands in for a KernelTimer between timed sections: records every call's name and arguments, no events"""
+    names = None
+
+    class _Rec(list):
+        def append(self, r):
+            CALLS.append((r[0], r[3]))
+    records = _Rec()
+
+
 def timeit(tag, fn):
-    L.TIMER = None
+    L.TIMER = _Log if args.call_log else None
     for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
@@ -44,7 +59,10 @@ def timeit(tag, fn):
         fn()
         torch.cuda.synchronize()
         recs.append(L.TIMER.summary())
-        L.TIMER = None
+        for name, lst in recs[-1].items():
+            pass
+        CALLS.extend((r[0], r[3]) for r in L.TIMER.records)
+        L.TIMER = _Log if args.call_log else None
     # sum over the C-ABI calls of one fn() invocation, min over iterations
     best = None
     for r in recs:
@@ -64,6 +82,8 @@ def timeit(tag, fn):
 
 
 bf, f32 = torch.bfloat16, torch.float32
+if args.call_log:
+    L.TIMER = _Log
 for si in [int(s) for s in args.stages.split(",")]:
     C, H = STAGES[si]
     N = args.n
@@ -129,3 +149,8 @@ for si in [int(s) for s in args.stages.split(",")]:
         timeit(f"wgrad_fc1 {tag}", lambda: cabi.gemm_wgrad(gg, A))
         del A, hh, gg
     torch.cuda.empty_cache()
+
+if args.call_log:
+    L.TIMER = None
+    with open(args.call_log, "w") as f:
+        json.dump([[n, bench.kernel_work(n, a)[2]] for n, a in CALLS], f)
