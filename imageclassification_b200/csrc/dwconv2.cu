@@ -121,21 +121,43 @@ __device__ __forceinline__ uint4 pack16(const float (&v)[4], float*) {
   return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
 }
 
-// fp32-accurate forward ("x3", include/cnx.h): the normalised row leaves as the A-side split operand [hi | mid | hi] (bf16,
-// row stride 3C) instead of fp32 xn — 4 values per lane, three 8-byte stores
-__device__ __forceinline__ void store_split3(bf16* row3, int C, int col, const float (&x)[4], bool third) {
-  uint2 hi, mid;
+// LayerNorm half: one lane item = 8 consecutive channels = one 16-byte vector of bf16 or two of fp32 (fp32 activations used to go
+// 4 channels per item: twice the memory instructions per element and 8-byte split stores; the LayerNorm half sets the time of the
+// fp32-activation forward)
+template <typename TOUT> struct LnIO;
+template <> struct LnIO<bf16> { static constexpr int NV = 1; };
+template <> struct LnIO<float> { static constexpr int NV = 2; };
+__device__ __forceinline__ void ln_load8(const bf16* p, uint4 (&raw)[1]) { raw[0] = ld_global_16(p); }
+__device__ __forceinline__ void ln_load8(const float* p, uint4 (&raw)[2]) { raw[0] = ld_global_16(p); raw[1] = ld_global_16(p + 4); }
+__device__ __forceinline__ void ln_unpack8(const uint4 (&raw)[1], float (&v)[8], bf16* t) { unpack16(raw[0], v, t); }
+__device__ __forceinline__ void ln_unpack8(const uint4 (&raw)[2], float (&v)[8], float* t) {
+  unpack16(raw[0], *reinterpret_cast<float(*)[4]>(&v[0]), t);
+  unpack16(raw[1], *reinterpret_cast<float(*)[4]>(&v[4]), t);
+}
+__device__ __forceinline__ void ln_store8(bf16* p, const float (&v)[8]) { *reinterpret_cast<uint4*>(p) = pack16(v, (bf16*)nullptr); }
+__device__ __forceinline__ void ln_store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack16(*reinterpret_cast<const float(*)[4]>(&v[0]), (float*)nullptr);
+  *reinterpret_cast<uint4*>(p + 4) = pack16(*reinterpret_cast<const float(*)[4]>(&v[4]), (float*)nullptr);
+}
+// fp32-accurate forward ("x3", include/cnx.h): the normalised row leaves as the A-side split operand [hi | mid (| hi)] (bf16,
+// row stride 2C or 3C; in the 2-segment form the consuming GEMM's K loop wraps instead) — 8 values per lane, 16-byte stores
+__device__ __forceinline__ void store_split8(bf16* row3, int C, int col, const float (&x)[8], bool third) {
+  uint4 hi;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(x[1]), "f"(x[0]));
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(x[3]), "f"(x[2]));
-  const float r0 = x[0] - __uint_as_float(hi.x << 16), r1 = x[1] - __uint_as_float(hi.x & 0xffff0000u);
-  const float r2 = x[2] - __uint_as_float(hi.y << 16), r3 = x[3] - __uint_as_float(hi.y & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.x) : "f"(r1), "f"(r0));
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.y) : "f"(r3), "f"(r2));
-  *reinterpret_cast<uint2*>(row3 + col) = hi;
-  *reinterpret_cast<uint2*>(row3 + C + col) = mid;
-  if (third) *reinterpret_cast<uint2*>(row3 + 2 * C + col) = hi;      // 2-segment form: the consuming GEMM's K loop wraps instead
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.z) : "f"(x[5]), "f"(x[4]));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi.w) : "f"(x[7]), "f"(x[6]));
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r[2 * i] = x[2 * i] - __uint_as_float(h[i] << 16);
+    r[2 * i + 1] = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+  }
+  *reinterpret_cast<uint4*>(row3 + col) = hi;
+  *reinterpret_cast<uint4*>(row3 + C + col) = pack16(r, (bf16*)nullptr);
+  if (third) *reinterpret_cast<uint4*>(row3 + 2 * C + col) = hi;
 }
-__device__ __forceinline__ void store_split3(bf16*, int, int, const float (&)[8], bool) {}   // bf16 activations: never taken
 
 // tile pixel slot p (row-major over [NB][ROWS][TW]) -> global pixel index, or -1 outside the tensor
 template <class G, bool EXACT>
@@ -293,9 +315,9 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
   } else if (MODE == MODE_FWD) {
     // ===== LayerNorm: xn = (y - mean) * rstd * w + b over the tile the compute warps just finished =====
-    constexpr int VEC = Vec16<TOUT>::N;
+    constexpr int VEC = 8, NV = LnIO<TOUT>::NV;
     const int lw = warp - 1 - NWC;
-    const int VPR = C / VEC;                               // 16-byte vectors per pixel row
+    const int VPR = C / VEC;                               // 8-channel lane items per pixel row
     if (VPR <= 32) {
       // several pixels per warp pass; this lane's slice of ln_w / ln_b stays in registers for the whole kernel
       const int ppw = 32 / VPR;
@@ -304,14 +326,14 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float w[VEC], b[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) { w[e] = active ? __ldg(ln_w + v * VEC + e) : 0.f; b[e] = active ? __ldg(ln_b + v * VEC + e) : 0.f; }
-      constexpr int U = CNX_DW_LNU1;
+      constexpr int U = CNX_DW_LNU1 / NV;                  // the same bytes in flight per lane for both dtypes
       for (int i = 0; i < my_tiles; ++i) {
         const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
         const int tb = i & 1;
         mbar_wait(lnfull_bar(tb), (uint32_t)((i >> 1) & 1));
         const float2* stp = stats + tb * STATS_STRIDE;
         for (int p0 = lw * ppw; p0 < G::P; p0 += NLN * ppw * U) {
-          uint4 raw[U];
+          uint4 raw[U][NV];
           int64_t off[U], mm[U];
           float2 ms[U];
 #pragma unroll
@@ -323,7 +345,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               if (m >= 0) {
                 off[u] = m * C + v * VEC;
                 mm[u] = m;
-                raw[u] = ld_global_16(out + off[u]);
+                ln_load8(out + off[u], raw[u]);
                 ms[u] = stp[p];
               }
             }
@@ -332,11 +354,11 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           for (int u = 0; u < U; ++u) {
             if (off[u] >= 0) {
               float x[VEC];
-              unpack16(raw[u], x, (TOUT*)nullptr);
+              ln_unpack8(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
               for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-              if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mm[u] * xseg * C, C, v * VEC, x, xseg == 3);
-              else *reinterpret_cast<uint4*>(xn + off[u]) = pack16(x, (TOUT*)nullptr);
+              if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split8(xn3 + mm[u] * xseg * C, C, v * VEC, x, xseg == 3);
+              else ln_store8(xn + off[u], x);
             }
           }
         }
@@ -345,7 +367,7 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     } else {
       // wide rows: one pixel per warp pass, lanes stride over the row; two pixels in flight
-      constexpr int U = CNX_DW_LNU2;
+      constexpr int U = (CNX_DW_LNU2 / NV) > 0 ? (CNX_DW_LNU2 / NV) : 1;
       for (int i = 0; i < my_tiles; ++i) {
         const TileCoord t = decode_tile<G>((int)blockIdx.x + i * (int)gridDim.x, tiles_x, tiles_y);
         const int tb = i & 1;
@@ -362,10 +384,10 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
           for (int v0 = 0; v0 < VPR; v0 += 32) {
             const int v = v0 + lane;
-            uint4 raw[U];
+            uint4 raw[U][NV];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-              if (v < VPR && mrow[u] >= 0) raw[u] = ld_global_16(out + mrow[u] * C + v * VEC);
+              if (v < VPR && mrow[u] >= 0) ln_load8(out + mrow[u] * C + v * VEC, raw[u]);
             if (v < VPR) {
               float w[VEC], b[VEC];
 #pragma unroll
@@ -379,11 +401,11 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               for (int u = 0; u < U; ++u) {
                 if (mrow[u] >= 0) {
                   float x[VEC];
-                  unpack16(raw[u], x, (TOUT*)nullptr);
+                  ln_unpack8(raw[u], x, (TOUT*)nullptr);
 #pragma unroll
                   for (int e = 0; e < VEC; ++e) x[e] = fmaf((x[e] - ms[u].x) * ms[u].y, w[e], b[e]);
-                  if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split3(xn3 + mrow[u] * xseg * C, C, v * VEC, x, xseg == 3);
-                  else *reinterpret_cast<uint4*>(xn + mrow[u] * C + v * VEC) = pack16(x, (TOUT*)nullptr);
+                  if (sizeof(TOUT) == 4 && xn3 != nullptr) store_split8(xn3 + mrow[u] * xseg * C, C, v * VEC, x, xseg == 3);
+                  else ln_store8(xn + mrow[u] * C + v * VEC, x);
                 }
               }
             }
