@@ -176,6 +176,10 @@ def kernel_work(name, a):
         N, H, W, C = a[6:10]
         MC = N * H * W * C
         return MC * (es(a[1]) + (2 if a[3] else 1) * es(a[5])), 98 * MC, f"dwconv7_dgrad C{C} H{H}"
+    if name == "cnx_dwconv7_dgrad_dz":      # dy bf16 in, dres in, dx out (stream dtype) + the upstream Block's bf16 operand copy
+        N, H, W, C = a[5:9]
+        MC = N * H * W * C
+        return MC * (2 + (2 if a[2] else 1) * es(a[4]) + 2), 98 * MC, f"dwconv7_dgrad C{C} H{H} +dz"
     if name == "cnx_dwconv7_wgrad":
         N, H, W, C = a[4:8]
         MC = N * H * W * C

@@ -48,7 +48,7 @@ int dwconv7_ln_fwd_v2(const void* x, int x_dtype, const float* wt, const float* 
                       float eps, int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn, int act_dtype, float* mean,
                       float* rstd, cudaStream_t s);
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
-                     int64_t H, int64_t W, int64_t C, cudaStream_t s);
+                     int64_t H, int64_t W, int64_t C, void* dz_up, const float* dp_up, cudaStream_t s);
 int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, const float* ln_w, const float* ln_b, float eps,
                          int64_t N, int64_t H, int64_t W, int64_t C, void* y, void* xn3, int segments, float* mean, float* rstd,
                          cudaStream_t s);
@@ -92,7 +92,16 @@ int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void*
   CNX_REQUIRE(dtype_ok(dy_dtype) && dtype_ok(stream_dtype), CNX_E_BADARG, "dwconv7_dgrad: bad dtype");
   CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_dgrad: bad shape");
   CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_dgrad: C=%lld must be a multiple of 32", (long long)C);
-  return dwconv7_dgrad_v2(dy, dy_dtype, wt, dres, dx, stream_dtype, N, H, W, C, (cudaStream_t)stream);
+  return dwconv7_dgrad_v2(dy, dy_dtype, wt, dres, dx, stream_dtype, N, H, W, C, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int cnx_dwconv7_dgrad_dz(const void* dy, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N, int64_t H,
+                         int64_t W, int64_t C, void* dz_up, const float* dp_up, void* stream) {
+  CNX_REQUIRE(dy && wt && dx && dz_up, CNX_E_BADARG, "dwconv7_dgrad_dz: null pointer");
+  CNX_REQUIRE(dtype_ok(stream_dtype), CNX_E_BADARG, "dwconv7_dgrad_dz: bad dtype");
+  CNX_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, CNX_E_BADARG, "dwconv7_dgrad_dz: bad shape");
+  CNX_REQUIRE(C % 32 == 0, CNX_E_SHAPE, "dwconv7_dgrad_dz: C=%lld must be a multiple of 32", (long long)C);
+  return dwconv7_dgrad_v2(dy, CNX_BF16, wt, dres, dx, stream_dtype, N, H, W, C, dz_up, dp_up, (cudaStream_t)stream);
 }
 
 int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W,

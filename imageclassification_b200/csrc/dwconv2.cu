@@ -170,7 +170,10 @@ __device__ __forceinline__ int64_t tile_pixel(const TileCoord& t, int p, int N, 
 
 // ------------------------------------------------------------------------------------------------
 // forward (MODE_FWD):  y = conv(x) + bias -> TOUT ; LayerNorm over C -> xn, mean, rstd
-// dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT
+// dgrad   (MODE_DGRAD): dx = dres + conv_flipped(dy) -> TOUT; with bf16 activations optionally also the operand copy the
+//                       UPSTREAM Block's backward needs of this gradient, dz_up = bf16(dp_up[n] * dx) (its cnx_grad_prep pass,
+//                       a 6-byte-per-element round trip, folded into this epilogue).  In this mode `xn3` carries dz_up and `ln_w`
+//                       carries dp_up (per-sample drop-path scale of the upstream Block, or null).
 // ------------------------------------------------------------------------------------------------
 template <class G, int MODE, typename TIN, typename TOUT, bool EXACT>
 __global__ void __launch_bounds__(ConvCfg<G, MODE, TIN, TOUT>::NT, 1)
@@ -246,6 +249,9 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       float2 st[NPIX];
 #pragma unroll
       for (int p = 0; p < NPIX; ++p) st[p] = make_float2(0.f, 0.f);
+      const bool want_dz = (MODE == MODE_DGRAD) && sizeof(TIN) == 2 && xn3 != nullptr;
+      float sc2 = 1.0f;
+      if (want_dz && ln_w != nullptr) sc2 = __ldg(ln_w + (n_ok ? n : 0));
       for (int k = 0; k < nchunks; ++k) {
         const int c = k * CH + 2 * cp;
         float2 b2 = make_float2(0.f, 0.f);
@@ -286,7 +292,13 @@ dwconv7_v2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             } else {
               v = __fadd2_rn(v, dr[q][r]);
             }
-            if (EXACT || (n_ok && gx0 + q < W && gy0 + r < H)) st_pair(reinterpret_cast<TOUT*>(op + poff[q * G::TH + r]), v);
+            if (EXACT || (n_ok && gx0 + q < W && gy0 + r < H)) {
+              st_pair(reinterpret_cast<TOUT*>(op + poff[q * G::TH + r]), v);
+              if (want_dz) {
+                const float2 vs = round_pair(v, (TOUT*)nullptr);          // the value as stored in dx, then scaled and rounded
+                st_pair(xn3 + pix0 * C + c + poff[q * G::TH + r] / (uint32_t)sizeof(TOUT), make_float2(vs.x * sc2, vs.y * sc2));
+              }
+            }
           }
         }
       }
@@ -644,14 +656,17 @@ int dwconv7_ln_fwd_x3_v2(const void* x, const float* wt, const float* bias, cons
 }
 
 int dwconv7_dgrad_v2(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
-                     int64_t H, int64_t W, int64_t C, cudaStream_t s) {
+                     int64_t H, int64_t W, int64_t C, void* dz_up, const float* dp_up, cudaStream_t s) {
   using namespace dw2;
-  if (dy_dtype == CNX_F32 && stream_dtype == CNX_F32)
+  if (dy_dtype == CNX_F32 && stream_dtype == CNX_F32) {
+    CNX_REQUIRE(dz_up == nullptr, CNX_E_BADARG, "dwconv7_dgrad: the folded operand copy is a bf16-activation feature");
     return pick_conv<MODE_DGRAD, float, float>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
+  }
+  // (dz_up, dp_up) ride in the forward-only (xn3, ln_w) parameters of the shared kernel
   if (dy_dtype == CNX_BF16 && stream_dtype == CNX_F32)
-    return pick_conv<MODE_DGRAD, bf16, float>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
+    return pick_conv<MODE_DGRAD, bf16, float>(dy, dy_dtype, wt, nullptr, dres, dx, dp_up, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s, dz_up);
   if (dy_dtype == CNX_BF16 && stream_dtype == CNX_BF16)
-    return pick_conv<MODE_DGRAD, bf16, bf16>(dy, dy_dtype, wt, nullptr, dres, dx, nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s);
+    return pick_conv<MODE_DGRAD, bf16, bf16>(dy, dy_dtype, wt, nullptr, dres, dx, dp_up, nullptr, 0.f, nullptr, nullptr, nullptr, N, H, W, C, s, dz_up);
   set_error("dwconv7_dgrad: fp32 activations with a bf16 stream is not a supported combination");
   return CNX_E_BADARG;
 }

@@ -318,14 +318,16 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 }
 
 // All derived weight layouts of a model in ONE launch: a device table of (source, scale, destination, shape, mode) entries,
-// one 32x32 tile per CTA found by binary search over the entries' first-tile prefix.  Replaces 4 launches per Block per step.
+// one 32x32 SOURCE tile per CTA found by binary search over the entries' first-tile prefix.  Entries of one source weight are
+// adjacent and share `tile_start` (a group): the CTA reads the fp32 tile once and writes every layout derived from it (bf16
+// copy, transposes, gamma-scaled transpose, split operand) — a Block's fc weights have five.  Replaces 4 launches per Block.
 struct WeightPrepEntry {
   const float* W;
   const float* row_scale;
   void* out;
   int64_t R, Cc;
   int32_t mode, out_dtype;
-  int64_t tile_start;      // first CTA of this entry
+  int64_t tile_start;      // first CTA of this entry's group
   int64_t tiles_x;         // ceil(Cc / 32)
 };
 
@@ -338,34 +340,37 @@ __global__ void __launch_bounds__(256) weight_prep_multi_kernel(const WeightPrep
     const int mid = (lo + hi + 1) >> 1;
     if (table[mid].tile_start <= b) lo = mid; else hi = mid - 1;
   }
-  const WeightPrepEntry e = table[lo];
-  const int64_t t = b - e.tile_start;
-  const int64_t r0 = (t / e.tiles_x) * 32, c0 = (t % e.tiles_x) * 32;
+  const int last = lo;                                   // last entry of the group; walk back to its first
+  const int64_t start = table[last].tile_start;
+  int first = last;
+  while (first > 0 && table[first - 1].tile_start == start) --first;
+  const WeightPrepEntry e0 = table[first];
+  const int64_t t = b - start;
+  const int64_t r0 = (t / e0.tiles_x) * 32, c0 = (t % e0.tiles_x) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8) {
     const int64_t r = r0 + i, c = c0 + tx;
-    float v = 0.f;
-    if (r < e.R && c < e.Cc) {
-      v = e.W[r * e.Cc + c];
-      if (e.mode == 2 && e.row_scale) v *= e.row_scale[r];
-    }
-    tile[i][tx] = v;
+    tile[i][tx] = (r < e0.R && c < e0.Cc) ? e0.W[r * e0.Cc + c] : 0.f;
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    int64_t r, c, o;
-    float v;
-    if (e.mode == 0 || e.mode == 3) { r = r0 + i; c = c0 + tx; o = r * e.Cc + c; v = tile[i][tx]; }
-    else { c = c0 + i; r = r0 + tx; o = c * e.R + r; v = tile[tx][i]; }
-    if (r < e.R && c < e.Cc) {
-      if (e.mode == 3) {                                   // [hi | hi | mid], bf16 only
-        bf16* o3 = reinterpret_cast<bf16*>(e.out) + r * 3 * e.Cc + c;
-        const bf16 hi = from_f32<bf16>(v);
-        o3[0] = hi;
-        o3[e.Cc] = hi;
-        o3[2 * e.Cc] = from_f32<bf16>(v - to_f32(hi));
-      } else if (e.out_dtype == CNX_F32) reinterpret_cast<float*>(e.out)[o] = v;
-      else reinterpret_cast<bf16*>(e.out)[o] = from_f32<bf16>(v);
+  for (int g = first; g <= last; ++g) {
+    const WeightPrepEntry e = table[g];
+    for (int i = ty; i < 32; i += 8) {
+      int64_t r, c, o;
+      float v;
+      if (e.mode == 0 || e.mode == 3) { r = r0 + i; c = c0 + tx; o = r * e.Cc + c; v = tile[i][tx]; }
+      else { c = c0 + i; r = r0 + tx; o = c * e.R + r; v = tile[tx][i]; }
+      if (r < e.R && c < e.Cc) {
+        if (e.mode == 2 && e.row_scale) v *= e.row_scale[r];
+        if (e.mode == 3) {                                   // [hi | hi | mid], bf16 only
+          bf16* o3 = reinterpret_cast<bf16*>(e.out) + r * 3 * e.Cc + c;
+          const bf16 hi = from_f32<bf16>(v);
+          o3[0] = hi;
+          o3[e.Cc] = hi;
+          o3[2 * e.Cc] = from_f32<bf16>(v - to_f32(hi));
+        } else if (e.out_dtype == CNX_F32) reinterpret_cast<float*>(e.out)[o] = v;
+        else reinterpret_cast<bf16*>(e.out)[o] = from_f32<bf16>(v);
+      }
     }
   }
 }

@@ -41,6 +41,14 @@ RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "0"))
 # four backward GEMMs of the Block run as split-operand (x3) tcgen05 GEMMs, fp32-accurate to ~2^-16 per product, instead of the
 # CUDA-core fp32 GEMMs.  CNX_X3_TRAIN=0 selects the CUDA-core kernels for comparison.
 X3_TRAIN = os.environ.get("CNX_X3_TRAIN", "1") != "0"
+# Backward hand-off between consecutive Blocks (bf16 activations): the dwconv backward-data kernel of Block i writes, beside
+# dx, the bf16 operand copy dz = bf16(dp * dx) that Block i-1's backward would make of it with cnx_grad_prep.  Forward notes
+# which Block produced a Block's input (`_LAST_OUT`); backward leaves the copy in `_DZ_HANDOFF` together with the dx tensor
+# it belongs to, and the consumer takes it only if the gradient it receives IS that tensor (same storage, shape, drop-path
+# vector) — otherwise it falls back to cnx_grad_prep.  CNX_DZ_HANDOFF=0 disables it.
+DZ_HANDOFF = os.environ.get("CNX_DZ_HANDOFF", "1") != "0"
+_LAST_OUT = None        # (data_ptr, (N, H, W, C), dp) of the last Block output produced with grad tracking
+_DZ_HANDOFF = None      # (dx NHWC tensor, dz [M, C] bf16, dp of the consumer)
 
 
 def _act_dtype() -> torch.dtype:
@@ -140,14 +148,20 @@ class _PrepRegistry:
                 self._drop(k)
                 continue
             live.append((k, e, w, sc))
+        # entries of one source weight are adjacent and share their first tile: the kernel reads a source tile once and writes
+        # every layout derived from it
+        live.sort(key=lambda it: it[2].data_ptr())
         if self.table is None or self.table[3] != [(k, w.data_ptr(), sc.data_ptr() if sc is not None else 0) for k, e, w, sc in live]:
-            rows, start = [], 0
+            rows, start, prev, ntile = [], 0, None, 0
             for k, e, w, sc in live:
                 R, Cc = w.shape[0], w.numel() // w.shape[0]
                 tx, ty = (Cc + 31) // 32, (R + 31) // 32
+                if prev != (w.data_ptr(), R, Cc):
+                    start += ntile
+                    prev, ntile = (w.data_ptr(), R, Cc), tx * ty
                 rows.append(L.WeightPrepEntry(w.data_ptr(), sc.data_ptr() if sc is not None else None, e["out"].data_ptr(), R, Cc,
                                               e["mode"], L.dt(e["dtype"]), start, tx))
-                start += tx * ty
+            start += ntile
             arr = (L.WeightPrepEntry * len(rows))(*rows)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             dev = host.to(self.device)
@@ -324,6 +338,8 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma, dp, eps, act_dtype, track):
+        global _LAST_OUT, _DZ_HANDOFF
+        last, _LAST_OUT = _LAST_OUT, None
         lib = L.load()
         L.require_cuda(x, conv_w, w1, w2)
         if x.dtype not in (torch.float32, torch.bfloat16):
@@ -381,6 +397,7 @@ class _BlockFn(torch.autograd.Function):
             ctx.shape = (N, C, H, W)
             ctx.act_dtype = act_dtype
             ctx.x3 = True
+            ctx.up_dp = None
             ctx.params = (conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma)
             return out.permute(0, 3, 1, 2)
         xn = torch.empty((M, C), dtype=act_dtype, device=dev)
@@ -399,6 +416,11 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.cnx_mlp_fused_fwd(L.ptr(xn), L.ptr(w1a), L.ptr(b1), L.ptr(w2a), L.ptr(b2), L.ptr(gamma), L.ptr(dp), H * W,
                                           L.ptr(xl), L.ptr(out), M, C, st), "mlp_fused_fwd")
             return out.permute(0, 3, 1, 2)
+        up = None
+        if need_grad and DZ_HANDOFF and act_dtype == torch.bfloat16:
+            _DZ_HANDOFF = None
+            if last is not None and last[0] == xl.data_ptr() and last[1] == (N, H, W, C) and ctx.needs_input_grad[0]:
+                up = last                            # this Block's input is the previous Block's output
         recompute = (need_grad and act_dtype == torch.bfloat16 and C <= RECOMPUTE_MAX_C and C4 % 128 == 0 and M >= 256
                      and GEMM_FLAGS == 0)
         h = torch.empty((M, C4), dtype=act_dtype, device=dev) if (need_grad and not recompute) else None     # holds GELU'(h)
@@ -415,10 +437,15 @@ class _BlockFn(torch.autograd.Function):
             ctx.act_dtype = act_dtype
             ctx.x3 = False
             ctx.params = (conv_w, conv_b, ln_w, ln_b, w1, b1, w2, b2, gamma)     # the leaves themselves (gradient sinks)
+            ctx.up_dp = (up[2],) if up is not None else None                      # drop-path vector of the producing Block
+            if DZ_HANDOFF and act_dtype == torch.bfloat16:
+                _LAST_OUT = (out.data_ptr(), (N, H, W, C), dp)
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dout):
+        global _DZ_HANDOFF
+        ho, _DZ_HANDOFF = _DZ_HANDOFF, None
         lib = L.load()
         xl, y, xn, mean, rstd, h, g, conv_w, ln_w, w1, w2, b2, gamma, dp = ctx.saved_tensors
         N, C, H, W = ctx.shape
@@ -432,12 +459,17 @@ class _BlockFn(torch.autograd.Function):
             doutl = doutl.to(xl.dtype)
         p_conv_w, p_conv_b, p_ln_w, p_ln_b, p_w1, p_b1, p_w2, p_b2, p_gamma = ctx.params
         if ctx.x3:
+            ho = None
             dxn, dW1, db1, dW2, db2, dgamma = _mlp_backward_x3(lib, ctx.params, doutl, xn, h, g, w1, w2, b2, gamma, dp, M, C, C4,
                                                               H * W, dev, st)
         else:
             # 1. dz = act(dp * dout): the operand copy of the incoming gradient (drop-path folded in once)
             if dp is None and act_dtype == xl.dtype:
                 dz = doutl.reshape(M, C)
+            elif (ho is not None and ho[0].data_ptr() == doutl.data_ptr() and ho[0].shape == doutl.shape and ho[0].dtype == doutl.dtype
+                  and ((ho[2] is None) if dp is None else (ho[2] is not None and ho[2].data_ptr() == dp.data_ptr()))
+                  and act_dtype == torch.bfloat16):
+                dz = ho[1]                           # written by the downstream Block's dwconv backward-data kernel
             else:
                 dz = torch.empty((M, C), dtype=act_dtype, device=dev)
                 L.check(lib.cnx_grad_prep(L.ptr(doutl), sd, L.ptr(dp), H * W, M, C, L.ptr(dz), ad, st), "grad_prep")
@@ -490,8 +522,14 @@ class _BlockFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dxl = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
-            L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
-                    "dwconv7_dgrad")
+            if ctx.up_dp is not None and not ctx.x3 and act_dtype == torch.bfloat16:
+                dz_up = torch.empty((M, C), dtype=act_dtype, device=dev)
+                L.check(lib.cnx_dwconv7_dgrad_dz(L.ptr(dy), L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C,
+                                                 L.ptr(dz_up), L.ptr(ctx.up_dp[0]), st), "dwconv7_dgrad_dz")
+                _DZ_HANDOFF = (dxl, dz_up, ctx.up_dp[0])
+            else:
+                L.check(lib.cnx_dwconv7_dgrad(L.ptr(dy), ad, L.ptr(_conv_weight_tap_major(conv_w)), L.ptr(doutl), L.ptr(dxl), sd, N, H, W, C, st),
+                        "dwconv7_dgrad")
             dx = dxl.permute(0, 3, 1, 2)
         return (dx, dconv_w, dconv_b, dln_w, dln_b, dW1, db1, dW2, db2, dgamma, None, None, None, None)
 

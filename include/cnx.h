@@ -165,6 +165,11 @@ CNX_API int cnx_reduce_partials_split(const float* partial, int P, int64_t La, i
  * dy [M,C] act dtype; dres, dx [M,C] stream dtype. */
 CNX_API int cnx_dwconv7_dgrad(const void* dy, int dy_dtype, const float* wt, const void* dres, void* dx, int stream_dtype,
                       int64_t N, int64_t H, int64_t W, int64_t C, void* stream);
+/* The same with bf16 activations (dy bf16), additionally writing the operand copy that the UPSTREAM Block's backward would
+ * otherwise make of dx with cnx_grad_prep: dz_up[m,c] = bf16(dp_up[n] * dx[m,c]) (dp_up: that Block's per-sample drop-path
+ * scale [N], NULL = 1), bit-identical to cnx_grad_prep(dx, ...).  Saves a read of dx per Block (engine.py:69 backward). */
+CNX_API int cnx_dwconv7_dgrad_dz(const void* dy, const float* wt, const void* dres, void* dx, int stream_dtype, int64_t N,
+                         int64_t H, int64_t W, int64_t C, void* dz_up, const float* dp_up, void* stream);
 
 /* dwconv backward-weights + bias grad: partial [P, 50, C] fp32 (taps 0..48 then bias), P CTAs (persistent). */
 CNX_API int cnx_dwconv7_wgrad(const void* dy, int dy_dtype, const void* x, int x_dtype, int64_t N, int64_t H, int64_t W,
@@ -280,8 +285,10 @@ CNX_API int cnx_weight_prep(const float* W, int64_t R, int64_t Ccols, const floa
 
 /* The same for MANY weights in one launch.  table_dev: device array of n_entries
  *   struct { const float* W; const float* row_scale; void* out; int64_t R, Cc; int32_t mode, out_dtype;
- *            int64_t tile_start, tiles_x; }          (tile_start = prefix sum of ceil(R/32)*ceil(Cc/32), tiles_x = ceil(Cc/32))
- * total_tiles = sum of the entries' tile counts. */
+ *            int64_t tile_start, tiles_x; }          (tiles_x = ceil(Cc/32))
+ * Entries that derive from the same source W (same R, Cc) are adjacent and carry the SAME tile_start (a group): one CTA reads
+ * a 32x32 source tile once and writes it into every layout of the group.  tile_start = prefix sum over GROUPS of
+ * ceil(R/32)*ceil(Cc/32); total_tiles = that sum over all groups. */
 CNX_API int cnx_weight_prep_multi(const void* table_dev, int n_entries, int64_t total_tiles, void* stream);
 
 /* Layer-scale gradient from the UNSCALED fc2 wgrad G2[c,k] = sum_m dz[m,c] g[m,k], s[c] = sum_m dz[m,c]:

@@ -78,6 +78,27 @@ def dwconv7_dgrad(dy2, w, dres_nhwc, shape, stream_dtype):
     return dx
 
 
+def dwconv7_dgrad_dz(dy2, w, dres_nhwc, shape, stream_dtype, dp_up):
+    """dx and the bf16 operand copy dz_up = bf16(dp_up[n] * dx) of the upstream Block, in one launch."""
+    lib = L.load()
+    w = tap_major(w)
+    N, H, W, C = shape
+    dx = torch.empty((N, H, W, C), dtype=stream_dtype, device=dy2.device)
+    dz = torch.empty((N * H * W, C), dtype=torch.bfloat16, device=dy2.device)
+    L.check(lib.cnx_dwconv7_dgrad_dz(L.ptr(dy2), L.ptr(w), L.ptr(dres_nhwc), L.ptr(dx), L.dt(stream_dtype), N, H, W, C, L.ptr(dz),
+                                     L.ptr(dp_up), _st()), "dwconv7_dgrad_dz")
+    return dx, dz
+
+
+def grad_prep(dout_nhwc, dp, act_dtype):
+    lib = L.load()
+    N, H, W, C = dout_nhwc.shape
+    dz = torch.empty((N * H * W, C), dtype=act_dtype, device=dout_nhwc.device)
+    L.check(lib.cnx_grad_prep(L.ptr(dout_nhwc), L.dt(dout_nhwc), L.ptr(dp), H * W, N * H * W, C, L.ptr(dz), L.dt(act_dtype), _st()),
+            "grad_prep")
+    return dz
+
+
 def dwconv7_wgrad(dy2, x_nhwc, P=32):
     lib = L.load()
     N, H, W, C = x_nhwc.shape

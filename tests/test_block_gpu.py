@@ -205,3 +205,45 @@ def test_block_backward_with_recomputed_gelu_prime(C, H, monkeypatch):
         assert torch.equal(g0[n], g1[n]), n
     yo, dxo, go = _run(o, x, dout, True, 1)
     assert max_rel(dx1, dxo) <= 2e-2
+
+
+@pytest.mark.parametrize("drop_path", [0.0, 0.3])
+def test_block_chain_backward_operand_handoff(drop_path, monkeypatch):
+    """ops.DZ_HANDOFF: between consecutive Blocks under bf16 autocast the dwconv backward-data kernel of Block i also writes the
+    bf16 operand copy of its dx that Block i-1's backward needs (instead of a cnx_grad_prep pass there).  Same gradients, bit for
+    bit, as without the hand-off; the copy is only taken when the incoming gradient IS that dx (a tensor hook that replaces it
+    falls back to cnx_grad_prep)."""
+    from imageclassification_b200 import _lib as L, ops
+    torch.manual_seed(3)
+    C, H, N = 96, 28, 6
+    blocks = torch.nn.Sequential(*[P.ConvNeXtBlock(C, drop_path=drop_path, ls_init_value=1.0) for _ in range(3)]).to(DEV)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, C, H, H, generator=g).to(DEV)
+    dout = torch.randn(N, C, H, H, generator=g).to(DEV)
+
+    def run(hook=False):
+        blocks.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        torch.manual_seed(11)
+        c0 = dict(L.CALL_COUNTS)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            t = blocks[0](xi)
+            t = blocks[1](t)
+            if hook:
+                t.register_hook(lambda gr: gr * 1.0)            # a NEW tensor reaches Block 1's backward
+            y = blocks[2](t)
+        y.backward(dout)
+        n = {k: L.CALL_COUNTS[k] - c0.get(k, 0) for k in ("cnx_grad_prep", "cnx_dwconv7_dgrad_dz", "cnx_dwconv7_dgrad")}
+        return y, xi.grad, [p.grad.clone() for p in blocks.parameters()], n
+
+    y1, dx1, g1, n1 = run()
+    assert n1 == {"cnx_grad_prep": 1, "cnx_dwconv7_dgrad_dz": 2, "cnx_dwconv7_dgrad": 1}, n1
+    y2, dx2, g2, n2 = run(hook=True)
+    assert n2["cnx_grad_prep"] == 2 and n2["cnx_dwconv7_dgrad_dz"] == 2, n2
+    monkeypatch.setattr(ops, "DZ_HANDOFF", False)
+    y0, dx0, g0, n0 = run()
+    assert n0 == {"cnx_grad_prep": 3, "cnx_dwconv7_dgrad_dz": 0, "cnx_dwconv7_dgrad": 3}, n0
+    for a, b in ((y1, y0), (dx1, dx0), (y2, y0), (dx2, dx0)):
+        assert torch.equal(a, b)
+    for a, b, c in zip(g1, g0, g2):
+        assert torch.equal(a, b) and torch.equal(c, b)

@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from cabi import (dwconv7_dgrad, dwconv7_ln_fwd, dwconv7_wgrad, ln_bwd, ln_fwd, max_rel)
+from cabi import (dwconv7_dgrad, dwconv7_dgrad_dz, dwconv7_ln_fwd, dwconv7_wgrad, grad_prep, ln_bwd, ln_fwd, max_rel)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -91,6 +91,23 @@ def test_dwconv_bwd(shape, dtypes):
     assert max_rel(db, br.grad) <= 1e-4
     dw2, _ = dwconv7_wgrad(dy, x, P=64)                   # different CTA count -> same sums within fp32 reassociation
     assert max_rel(dw2, wr.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(16, 56, 56, 96), (32, 14, 14, 384)])
+@pytest.mark.parametrize("sd", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_dp", [True, False])
+def test_dwconv_dgrad_with_upstream_operand_copy(shape, sd, with_dp):
+    """cnx_dwconv7_dgrad_dz: dx is bit-identical to cnx_dwconv7_dgrad's and the folded copy dz_up to cnx_grad_prep(dx, dp_up)."""
+    N, H, W, C = shape
+    g = torch.Generator().manual_seed(H * 3 + C)
+    w = (torch.randn(C, 1, 7, 7, generator=g) * 0.2).to(DEV)
+    dy = torch.randn(N * H * W, C, generator=g).to(torch.bfloat16).to(DEV)
+    dres = torch.randn(N, H, W, C, generator=g).to(sd).to(DEV)
+    dp = ((torch.rand(N, generator=g) < 0.7).float() / 0.7).to(DEV) if with_dp else None
+    dx_ref = dwconv7_dgrad(dy, w, dres, shape, sd)
+    dx, dz = dwconv7_dgrad_dz(dy, w, dres, shape, sd, dp)
+    assert torch.equal(dx, dx_ref)
+    assert torch.equal(dz, grad_prep(dx_ref, dp, torch.bfloat16))
 
 
 @pytest.mark.parametrize("shape", SHAPES)

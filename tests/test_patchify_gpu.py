@@ -121,6 +121,20 @@ def test_weight_prep_registry_refreshes_all_in_one_launch():
     for w, o in zip(ws, again):
         assert torch.equal(o, w.t().to(torch.bfloat16))
     assert torch.equal(again[3], (ws[0] * sc[:, None]).t().to(torch.bfloat16))
+    # five layouts of one source (what a Block's fc weight has) share its tiles: still one launch, every layout right
+    w = ws[1]
+    lay = lambda: [ops._weight_prep(w, 0, None, torch.bfloat16), ops._weight_prep(w, 3, None, torch.bfloat16),
+                   ops._weight_prep(w, 1, None, torch.float32), ops._weight_prep(w, 1, None, torch.bfloat16)]
+    lay()
+    with torch.no_grad():
+        w.add_(0.125)
+    c0 = L.CALL_COUNTS["cnx_weight_prep_multi"]
+    o0, o3, o1f, o1 = lay()
+    assert L.CALL_COUNTS["cnx_weight_prep_multi"] - c0 == 1
+    hi = w.to(torch.bfloat16)
+    assert torch.equal(o0, hi) and torch.equal(o1f, w.t()) and torch.equal(o1, w.t().to(torch.bfloat16))
+    assert torch.equal(o3, torch.cat([hi, hi, (w - hi.float()).to(torch.bfloat16)], dim=1))
+    assert torch.equal(ops._weight_prep(ws[0], 2, sc, torch.bfloat16), (ws[0] * sc[:, None]).t().to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
