@@ -1365,23 +1365,28 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_cons
 }
 
 // ================================================================================================
-// wgrad on CTA pairs: one tcgen05.mma.cta_group::2 spans a 256 x BN tile of out = X^T.Y (BN = 128 or 256).  Each CTA stages
+// wgrad on CTA pairs: one tcgen05.mma.cta_group::2 spans a 256 x BN tile of out = X^T.Y (BN = 128, 256 or 384).  Each CTA stages
 // its own 128 channels of X (two 64-channel MN-major boxes) and HALF of the BN channels of Y per 64-row k-block, so a CTA moves
 // 24 / 32 KB per k-block where the single-CTA 128 x 128 tile moves 32 KB for a quarter / half of the MACs.  Bias gradient,
 // split-K partials and the deterministic reduction are as in gemm_wgrad_tc_kernel.  grid = (2 * tiles, splits), cluster (2,1,1).
+// BN = 384 (N2 a multiple of 384: the 4C x C and C x 4C weights of C = 96 k): two MMAs per k-step, N = 256 into TMEM columns
+// 0..255 and N = 128 into 256..383 — 40 KB staged per CTA and k-block for 1.5x the MACs of the 256 x 256 tile (these long-K
+// GEMMs are bound by the bytes an SM takes in and reads back per clock), and N2 = 384 is ONE tile instead of
+// two 256-wide ones of which the second is half zero fill.
 // ================================================================================================
 template <int BN> struct WgPairCfg {
   static constexpr int A_BYTES = 2 * 64 * BK * 2;                      // own 128 channels of X
   static constexpr int B_BOXES = BN / 2 / 64;                          // 64-channel boxes of Y staged by one CTA
   static constexpr int B_BYTES = B_BOXES * 64 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = (BN <= 256) ? 6 : 5;
   static constexpr int CS_COL = BN;                                    // 16 column-sum columns after the accumulator
   static constexpr int TMEM_COLS = (BN + 16 <= 256) ? 256 : 512;
   static constexpr int EPI_COLS = BN / 2;
   static constexpr int ONES_BYTES = 2048;
   static constexpr int SMEM = STAGES * STAGE_BYTES + ONES_BYTES + 1024 + 256;
-  static_assert(BN == 128 || BN == 256, "the pair's half of the Y tile must be whole 64-channel boxes");
+  static_assert(BN == 128 || BN == 256 || BN == 384, "the pair's half of the Y tile must be whole 64-channel boxes");
+  static_assert(SMEM <= 227 * 1024, "wgrad pair ring does not fit in shared memory");
 };
 
 template <int BN>
@@ -1440,7 +1445,10 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       const int32_t a_ch = (int32_t)(it * 256 + rank * 128);
-      const int32_t b_ch = (int32_t)(jt * BN + rank * (BN / 2));
+      // BN <= 256: this CTA's half of the tile's channels.  BN = 384: the halves of the N = 256 MMA's channels (boxes 0, 1)
+      // and of the N = 128 MMA's (box 2), so that accumulator columns stay in channel order
+      const int32_t b_ch = (int32_t)(jt * BN + rank * (BN == 384 ? 128 : BN / 2));
+      const int32_t b_ch2 = (int32_t)(jt * BN + 256 + rank * 64);
       for (int kb = 0; kb < nkb; ++kb) {
         const int32_t mrow = (kb0 + kb) * BK;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -1449,14 +1457,15 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tma_load_2d_pair(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), a_ch + 64, mrow);
 #pragma unroll
         for (int b = 0; b < Cfg::B_BOXES; ++b)
-          tma_load_2d_pair(sB + s * Cfg::B_BYTES + b * 8192, &tmY, full_bar(s), b_ch + 64 * b, mrow);
+          tma_load_2d_pair(sB + s * Cfg::B_BYTES + b * 8192, &tmY, full_bar(s), (BN == 384 && b == 2) ? b_ch2 : b_ch + 64 * b, mrow);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0 && rank == 0 && nkb > 0) {
-      constexpr uint32_t idesc = make_idesc(256, BN, 1, 1);
+      constexpr uint32_t idesc = make_idesc(256, BN == 384 ? 256 : BN, 1, 1);
+      constexpr uint32_t idesc_hi = make_idesc(256, 128, 1, 1);         // BN = 384: columns 256..383
       constexpr uint32_t idesc_ones = make_idesc(256, 16, 1, 1);
       const uint64_t odesc = make_smem_desc(sOnes, 8192, 1024);
       int s = 0; uint32_t ph = 0;
@@ -1468,6 +1477,10 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           umma_f16_pair(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+          if constexpr (BN == 384) {
+            const uint64_t bdesc2 = make_smem_desc(sB + s * Cfg::B_BYTES + 2 * 8192, 8192, 1024);
+            umma_f16_pair(tmem_base + 256, adesc + (uint64_t)(k * 128), bdesc2 + (uint64_t)(k * 128), idesc_hi, (kb | k) != 0);
+          }
           if (do_colsum) umma_f16_pair(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
         }
         umma_commit_pair(empty_bar(s));
@@ -1814,6 +1827,15 @@ CNX_INST(EPI_DGELU, bf16)
 CNX_INST(EPI_BIAS_GELU3, bf16)
 #undef CNX_INST
 
+static bool wgrad384_enabled() {               // CNX_WGRAD_BN384=0: 256 x 256 pair tiles only (A/B measurements)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNX_WGRAD_BN384");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 // tile plan of the wgrad GEMM: CTA pairs (256 x BN) where both dimensions carry at least a tile, single CTAs otherwise
 struct WgPlan { int pair; int bn; int splits; int64_t tiles; };
 static WgPlan wgrad_plan_tc(int64_t M, int64_t N1, int64_t N2) {
@@ -1822,6 +1844,9 @@ static WgPlan wgrad_plan_tc(int64_t M, int64_t N1, int64_t N2) {
   if (p.pair) {
     // 256-wide tiles even when the last one is ragged (TMA zero fill): measured faster than exact 128-wide tiles (384 -> 2 x 256)
     p.bn = (N2 >= 192) ? 256 : 128;
+    // 256 x 384 only where 256-wide tiles would be ragged (N2 = 384: one tile instead of 1.5): measured +16 % there and
+    // -2..-5 % where N2 is a multiple of 256 as well (profiles/r02v_kbench_wgrad_bn384_*.jsonl)
+    if (N2 % 384 == 0 && N2 % 256 != 0 && wgrad384_enabled()) p.bn = 384;
     p.tiles = ((N1 + 255) / 256) * ((N2 + p.bn - 1) / p.bn);
   } else {
     p.bn = (N2 % 128 == 0) ? 128 : ((N2 % 96 == 0) ? 96 : 128);
@@ -1885,7 +1910,9 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
   float* part = (float*)workspace;
   float* cs_part = part + (int64_t)splits * N1 * N2;
   if (pl.pair) {
-    int rc = (pl.bn == 256)
+    int rc = (pl.bn == 384)
+                 ? launch_wgrad_pair<384>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s)
+             : (pl.bn == 256)
                  ? launch_wgrad_pair<256>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s)
                  : launch_wgrad_pair<128>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s);
     if (rc) return rc;
