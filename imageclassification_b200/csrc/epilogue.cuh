@@ -31,6 +31,8 @@ struct EpiParams {
   const void* b2;
   int32_t a_wrap;           // tcgen05 kernels: A is stored with only this many columns and the K loop wraps around it (0 = off):
                             // the split operand [hi | mid | hi] kept as [hi | mid], its third segment re-reads the first
+  int32_t pf_tiles;         // tcgen05 kernels: the TMA producer prefetches into L2 the A rows (and the epilogue's input slab rows)
+                            // of the tile this many persistent-loop steps ahead (0 = off; set by the launcher)
 };
 
 // acc[8] -> global, columns n..n+7 of row m (n % 8 == 0, N % 8 == 0 so vectors never straddle a row end)

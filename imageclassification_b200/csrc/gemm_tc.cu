@@ -208,6 +208,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                "r"(c1)
                : "memory");
 }
+// L2 prefetch of one box of a tensor map (no shared memory, no barrier): the later TMA load of the same box hits in L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -408,6 +412,23 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
         const int32_t arow = (int32_t)(mt * TM + rank * BM);
         const int32_t brow = (int32_t)(nt * BN + rank * Cfg::B_ROWS);
+        // The ring holds 3-5 k-blocks (the epilogue slabs take 64-128 KB): too little data in flight to cover an HBM round trip
+        // under the epilogue's write stream.  Prefetch the A rows (and the rows of the epilogue's input slabs) of a later tile
+        // of this CTA into L2, so that the ring's own loads are L2 hits (profiles/r02w_*: the epilogue warps of the K <= 384
+        // GEMMs waited 25 % of their time for an accumulator whose operands had not arrived).
+        if (ep.pf_tiles > 0) {
+          const int64_t tp = tile + (int64_t)ep.pf_tiles * tile_step;
+          if (tp < num_tiles) {
+            const int64_t mtp = tp / n_tiles, ntp = tp - mtp * n_tiles;
+            const int32_t prow = (int32_t)(mtp * TM + rank * BM);
+            const int ka = ep.a_wrap > 0 ? (int)ep.a_wrap : (int)K;
+            for (int c = 0; c < ka; c += BK) tma_prefetch_2d(&tmA, c, prow);     // (CTAs that share an m-tile repeat it: L2 hits)
+            if (HAS_IN) {
+              for (int q = 0; q < BM / 32; ++q)
+                for (int c = 0; c < Cfg::NCHUNK; ++c) tma_prefetch_2d(&tmIn, (int32_t)(ntp * BN + c * 32), prow + q * 32);
+            }
+          }
+        }
         for (int kk = 0; kk < (DUAL ? 2 : 1) * nkb; ++kk) {
           const int kb = (DUAL && kk >= nkb) ? kk - nkb : kk;
           const CUtensorMap* mA = (DUAL && kk >= nkb) ? &tmIn : &tmA;
@@ -524,6 +545,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int as = 0; uint32_t aph = 0;
     int buf = 0; uint32_t inph[2] = {0u, 0u};
     int64_t t_cur = first_tile; int c_cur = half;
+    // Column chunks go to the NGRP warps of a lane quarter round-robin.  Where NCHUNK is not a multiple of NGRP (BN = 192 with
+    // 16 epilogue warps: 6 chunks over 4 groups) the round-robin continues ACROSS tiles instead of restarting at every tile —
+    // restarting gave two groups 2 chunks and two groups 1 chunk of every tile, i.e. half the warps idle a quarter of the time
+    // (profiles/r02w_ncu_source_stalls.txt: 25 % of the x3 fc1 epilogue warps' samples waiting for the next accumulator).
+    constexpr bool ROT = (Cfg::NCHUNK % NGRP) != 0;
+    static_assert(!ROT || NGRP <= Cfg::NCHUNK, "every epilogue warp must visit every tile");
+    bool new_tile = true;
     auto chunk_coords = [&](int64_t tile, int c, int32_t& x, int32_t& y) {
       const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
       x = (int32_t)(nt * BN + c * 32);
@@ -537,7 +565,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     while (t_cur < num_tiles) {
       int64_t t_nxt = t_cur; int c_nxt = c_cur + NGRP;
-      if (c_nxt >= Cfg::NCHUNK) { c_nxt = half; t_nxt += tile_step; }
+      if (c_nxt >= Cfg::NCHUNK) { c_nxt = ROT ? c_nxt - Cfg::NCHUNK : half; t_nxt += tile_step; }
       const uint32_t slab = slab0 + (uint32_t)buf * kSlabBytes;
       if (lane == 0) {
         if (HAS_IN) {
@@ -552,10 +580,11 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           bulk_wait_read1();                         // the store issued two chunks ago has finished reading this slab
         }
       }
-      if (c_cur == half) {                           // first chunk of a tile for this warp
+      if (new_tile) {                                // first chunk of a tile for this warp
         mbar_wait(tfull_bar(as), aph);
         tc_fence_after();
       }
+      new_tile = (t_nxt != t_cur);
       float v[32];
       float u[DUAL ? 32 : 1];       // DUAL: the recomputed pre-activation chunk (upper 128 columns of the accumulator buffer)
       tmem_ld32(tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + c_cur * 32, v);
@@ -720,227 +749,6 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-
-// ================================================================================================
-// Staged-epilogue variant for the two N = 4C GEMMs whose epilogue is the whole cost (fc1 + bias + GELU, and the
-// fc2 data gradient times GELU'): at K = C = 96 a 128x128 tile needs 6 MMAs but 16 K-elements of epilogue math.
-//   * 16 epilogue warps (4 per SM sub-partition) instead of 8: each owns one 32-lane TMEM quarter x 32 columns;
-//   * results are packed to bf16 in registers, written to a 128B-swizzled shared-memory staging tile (conflict-free
-//     16-byte stores) and leave the SM as TMA stores (cp.async.bulk.tensor) — no per-thread global addressing, ragged
-//     M tiles are clipped by the tensor map;
-//   * the GELU' input tile h[m,n] is prefetched by the TMA producer into shared memory (same swizzle) while the MMAs
-//     of the tile run;
-//   * GELU uses an erf with |error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26 on MUFU rcp/ex2): far below bf16 resolution
-//     of the stored result, a third of the instructions of erff().
-// Requires N % 128 == 0 (4C always is), bf16 operands and outputs.
-// ================================================================================================
-constexpr int kStEpiWarps = 16;
-constexpr int kStThreads = (kFirstEpiWarp + kStEpiWarps) * 32;   // 640
-constexpr int kStStages = 4;
-constexpr int kStBN = 128;
-constexpr int kStABytes = BM * BK * 2, kStBBytes = kStBN * BK * 2;
-constexpr int kStBoxBytes = BM * 128;                            // [128 rows][64 bf16] = 16 KB
-constexpr int kStSmem = kStStages * (kStABytes + kStBBytes) + 4 * kStBoxBytes + 1024 + 256;
-
-
-template <int KIND>
-__global__ void __launch_bounds__(kStThreads, 1)
-gemm_tn_tc_staged_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1, int64_t M,
-                         int64_t N, int64_t K, const float* __restrict__ bias, int write_o0) {
-  constexpr int STAGES = kStStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = base;
-  const uint32_t sB = base + STAGES * kStABytes;
-  const uint32_t sO0 = sB + STAGES * kStBBytes;            // 2 boxes: out0 (h / dh), one per column half
-  const uint32_t sO1 = sO0 + 2 * kStBoxBytes;              // 2 boxes: out1 (g) for BIAS_GELU, aux-in (h) for DGELU
-  const uint32_t bars = sO1 + 2 * kStBoxBytes;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t aux_full = bars + 8u * (2 * STAGES + 4);
-  const uint32_t aux_empty = bars + 8u * (2 * STAGES + 5);
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = N / kStBN;
-  const int64_t num_tiles = m_tiles * n_tiles;
-  const int nkb = (int)((K + BK - 1) / BK);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmO0);
-    tma_prefetch_desc(&tmO1);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kStEpiWarps); }
-    mbar_init(aux_full, 1);
-    mbar_init(aux_empty, kStEpiWarps);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<256>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: operand ring + (DGELU) the h tile of each output tile =====
-      int s = 0; uint32_t ph = 0; uint32_t xph = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
-        if (KIND == EPI_DGELU) {
-          mbar_wait(aux_empty, xph ^ 1);
-          mbar_expect_tx(aux_full, 2 * kStBoxBytes);
-          tma_load_2d(sO1, &tmO1, aux_full, (int32_t)(nt * kStBN), (int32_t)(mt * BM));
-          tma_load_2d(sO1 + kStBoxBytes, &tmO1, aux_full, (int32_t)(nt * kStBN + 64), (int32_t)(mt * BM));
-          xph ^= 1;
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), kStABytes + kStBBytes);
-          tma_load_2d(sA + s * kStABytes, &tmA, full_bar(s), kb * BK, (int32_t)(mt * BM));
-          tma_load_2d(sB + s * kStBBytes, &tmB, full_bar(s), kb * BK, (int32_t)(nt * kStBN));
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc(BM, kStBN, 0, 0);
-      int s = 0; uint32_t ph = 0;
-      int as = 0; uint32_t aph = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * 128;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(sA + s * kStABytes, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sB + s * kStBBytes, 16, 1024);
-          int64_t krem = K - (int64_t)kb * BK;
-          const int kmma = krem >= BK ? BK / 16 : (int)((krem + 15) / 16);
-          for (int k = 0; k < kmma; ++k)
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          umma_commit(empty_bar(s));
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-        umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aph ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= kFirstEpiWarp) {
-    // ===== epilogue =====
-    const int ew = warp - kFirstEpiWarp;
-    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
-    const int colgroup = ew >> 2;                  // 32 columns each
-    const int boxg = colgroup >> 1, half = colgroup & 1;
-    const bool elected = (ew == boxg * 8) && lane == 0;      // one store issuer per column half
-    const int r = quarter * 32 + lane;             // row within the tile
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t swz = (uint32_t)(r & 7);
-    const uint32_t o0 = sO0 + boxg * kStBoxBytes + row_off;
-    const uint32_t o1 = sO1 + boxg * kStBoxBytes + row_off;
-    int as = 0; uint32_t aph = 0; uint32_t xph = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int64_t mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem_base + as * 128 + ((uint32_t)(quarter * 32) << 16) + colgroup * 32, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));            // accumulator buffer is free for tile+2
-      if (++as == 2) { as = 0; aph ^= 1; }
-
-      uint32_t p0[16], p1[16];
-      if (KIND == EPI_BIAS_GELU) {
-        const float* bp = bias + nt * kStBN + colgroup * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-          const float2 ha = __fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y));
-          const float2 hb = __fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w));
-          const uint32_t ua = pack_bf16(ha.x, ha.y);        // h rounded to bf16, as autocast's Linear output
-          const uint32_t ub = pack_bf16(hb.x, hb.y);
-          float2 ga, gb, da, db;
-          if (write_o0) {
-            gelu_pair<true>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
-            gelu_pair<true>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
-            p0[i / 2] = pack_bf16(da.x, da.y);              // GELU'(h): all that backward needs of h
-            p0[i / 2 + 1] = pack_bf16(db.x, db.y);
-          } else {
-            gelu_pair<false>(make_float2(bf16_lo(ua), bf16_hi(ua)), ga, da);
-            gelu_pair<false>(make_float2(bf16_lo(ub), bf16_hi(ub)), gb, db);
-          }
-          p1[i / 2] = pack_bf16(ga.x, ga.y);
-          p1[i / 2 + 1] = pack_bf16(gb.x, gb.y);
-        }
-      } else {   // EPI_DGELU: out0 = acc * gp, gp = GELU'(h) tile in shared memory (TMA, same 128B swizzle)
-        mbar_wait(aux_full, xph);
-        xph ^= 1;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t chunk = (uint32_t)(half * 4 + c);
-          lds128(o1 + ((chunk ^ swz) << 4), p1[4 * c], p1[4 * c + 1], p1[4 * c + 2], p1[4 * c + 3]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(aux_empty);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 r = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(bf16_lo(p1[i]), bf16_hi(p1[i])));
-          p0[i] = pack_bf16(r.x, r.y);
-        }
-      }
-
-      // staging tile must not be overwritten while the previous tile's TMA store is still reading it
-      if (elected) bulk_wait_read0();
-      named_bar(1 + 2 * boxg, 256);
-      const bool st0 = (KIND == EPI_DGELU) || write_o0;
-      if (st0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t chunk = (uint32_t)(half * 4 + c);
-          sts128(o0 + ((chunk ^ swz) << 4), p0[4 * c], p0[4 * c + 1], p0[4 * c + 2], p0[4 * c + 3]);
-        }
-      }
-      if (KIND == EPI_BIAS_GELU) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t chunk = (uint32_t)(half * 4 + c);
-          sts128(o1 + ((chunk ^ swz) << 4), p1[4 * c], p1[4 * c + 1], p1[4 * c + 2], p1[4 * c + 3]);
-        }
-      }
-      fence_proxy_async();
-      named_bar(2 + 2 * boxg, 256);
-      if (elected) {
-        const int32_t c0 = (int32_t)(nt * kStBN + boxg * 64), c1 = (int32_t)(mt * BM);
-        if (st0) tma_store_2d(&tmO0, sO0 + boxg * kStBoxBytes, c0, c1);
-        if (KIND == EPI_BIAS_GELU) tma_store_2d(&tmO1, sO1 + boxg * kStBoxBytes, c0, c1);
-        bulk_commit();
-      }
-    }
-    if (elected) bulk_wait0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
-  }
-}
 
 // ================================================================================================
 // wgrad: part[split][i][j] = sum_{m in split} X[m,i] * Y[m,j] ; cs_part[split][i] = sum_m X[m,i]
@@ -1611,16 +1419,14 @@ static bool pair_enabled() {
   return v != 0;
 }
 
-// CNX_GEMM_STAGED (experiments): unset -> the measured default; bit 0 / bit 1 force fc1+GELU / dGELU through the 16-warp
-// staged kernel, value 4 forces the slab kernel for both
-static bool staged_enabled(int kind, bool dflt) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CNX_GEMM_STAGED");
-    v = e ? atoi(e) : 8;
-  }
-  if (v == 8) return dflt;
-  return kind == EPI_BIAS_GELU ? (v & 1) != 0 : (v & 2) != 0;
+// CNX_GEMM_PF=<n>: L2 prefetch distance of the persistent GEMM's producer, in tiles of its own loop (0 = off).  Measured
+// (profiles/r02x_kbench_gemm_pf*.jsonl): -3..-8 % time for the split-output fc1 (EPI_BIAS_GELU3) at distance 1, +5..+45 % for
+// every kernel whose epilogue loads an input slab and for the plain data-gradient GEMM — so it is on for the former only.
+static int l2_prefetch_tiles(int kind) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("CNX_GEMM_PF"); v = e ? atoi(e) : -1; }
+  if (v >= 0) return v;
+  return kind == EPI_BIAS_GELU3 ? 1 : 0;
 }
 static bool bn384_enabled() {
   static int v = -1;
@@ -1663,6 +1469,8 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
     if (int rc = make_map(&tmB2, ep.b2, N, K, Cfg::B_ROWS)) return rc;        // B2 = W1
   auto k = gemm_tn_tc_kernel<BN, KIND, TOUT, NCTA, SLAB, NEPI>;
   if (int rc = set_smem(k, Cfg::SMEM)) return rc;
+  EpiParams epk = ep;
+  epk.pf_tiles = l2_prefetch_tiles(KIND);
   const int64_t tiles = ((M + BM * NCTA - 1) / (BM * NCTA)) * ((N + BN - 1) / BN);
   int64_t grid = sm_count() / NCTA;
   {
@@ -1688,7 +1496,7 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, tmB2, M, N, K, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, tmOut, tmIn, tmB2, M, N, K, epk);
   if (e != cudaSuccess) {
     set_error("gemm_tn_tc launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -1707,8 +1515,16 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
     const void* o = kGelu ? ep.out1 : ep.out0;
     if ((slab_enabled() || KIND == EPI_BIAS_GELU3) && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
       // the GELU epilogue is issue-bound: 16 epilogue warps (4 per scheduler) where the tile has >= 4 column chunks
-      if constexpr (kGelu && BN >= 128) return launch_tn_impl<BN, KIND, TOUT, NCTA, true, 16>(A, B, M, N, K, ep, s);
-      else return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
+      if constexpr (kGelu && BN >= 128) {
+        // 16 warps' slabs (128 KB) leave a 3-stage operand ring.  The split-output fc1 with K' >= 576 (C >= 192) is tensor-
+        // bound, not epilogue-bound: 8 warps and a 5-stage ring are 2-4 % faster there (profiles/r02z1_kbench_nepi8_*.jsonl);
+        // CNX_GEMM_NEPI8=0/1 forces 16 / 8 warps for every GELU-epilogue GEMM
+        static int nepi8 = -2;
+        if (nepi8 == -2) { const char* e = getenv("CNX_GEMM_NEPI8"); nepi8 = e ? (e[0] == '1' ? 1 : 0) : -1; }
+        const bool eight = nepi8 >= 0 ? nepi8 == 1 : (KIND == EPI_BIAS_GELU3 && K >= 576);
+        if (eight) return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
+        return launch_tn_impl<BN, KIND, TOUT, NCTA, true, 16>(A, B, M, N, K, ep, s);
+      } else return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
     }
   }
   if constexpr (KIND == EPI_BIAS_GELU3) {
@@ -1717,26 +1533,6 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
   } else {
     return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
   }
-}
-
-
-template <int KIND>
-static int launch_tn_staged(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
-  CUtensorMap tmA, tmB, tmO0, tmO1;
-  if (int rc = make_map(&tmA, A, M, K, BM)) return rc;
-  if (int rc = make_map(&tmB, B, N, K, kStBN)) return rc;
-  // BIAS_GELU: out0 = h (optional), out1 = g.   DGELU: out0 = dh, aux = h (loaded, same box shape)
-  void* o0 = ep.out0 ? ep.out0 : ep.out1;
-  const void* o1 = (KIND == EPI_BIAS_GELU) ? ep.out1 : ep.aux;
-  if (int rc = make_map(&tmO0, o0, M, N, BM)) return rc;
-  if (int rc = make_map(&tmO1, o1, M, N, BM)) return rc;
-  auto k = gemm_tn_tc_staged_kernel<KIND>;
-  if (int rc = set_smem(k, kStSmem)) return rc;
-  int64_t tiles = ((M + BM - 1) / BM) * (N / kStBN);
-  int64_t grid = sm_count();
-  if (grid > tiles) grid = tiles;
-  launch_pdl(k, dim3((unsigned)grid), dim3(kStThreads), kStSmem, s, tmA, tmB, tmO0, tmO1, M, N, K, ep.bias, ep.out0 != nullptr ? 1 : 0);
-  return check_launch("gemm_tn_tc_staged");
 }
 
 
@@ -1777,12 +1573,6 @@ template <int KIND, typename TOUT>
 int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {
   CNX_REQUIRE(N % 8 == 0 && K % 8 == 0, CNX_E_SHAPE, "gemm_tc: N=%lld and K=%lld must be multiples of 8", (long long)N,
               (long long)K);
-  if constexpr ((KIND == EPI_BIAS_GELU || KIND == EPI_DGELU) && sizeof(TOUT) == 2) {
-    // measured (profiles/r01e_*): the single-CTA 16-warp staged kernel still wins the fc1+GELU GEMM at K = 96 (pure
-    // HBM-write-bound); the CTA-pair slab kernel wins everywhere else
-    const bool prefer_staged = (KIND == EPI_BIAS_GELU) ? (K < 192) : false;
-    if (N % 128 == 0 && tc::staged_enabled(KIND, prefer_staged)) return tc::launch_tn_staged<KIND>(A, B, M, N, K, ep, s);
-  }
   // CTA-pair tiles (256 x BN) wherever a whole tile fits; CNX_GEMM_NCTA=1 in the environment selects the single-CTA kernel
   if (tc::pair_enabled() && M >= 256) {
     if constexpr (KIND == EPI_PLAIN || KIND == EPI_SCALE_RES) {
