@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("CNX_LIB", os.path.join(_HERE, "lib", "libcnx.so"))   
 CNX_F32, CNX_BF16 = 0, 1
 CNX_GEMM_FORCE_SIMT = 1
 CNX_GEMM_A_SPLIT2 = 2
+CNX_GEMM_OUT_ROUND_BF16 = 4
 CNX_EMA_CHUNK = 8192
 
 _lib = None

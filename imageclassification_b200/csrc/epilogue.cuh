@@ -31,6 +31,8 @@ struct EpiParams {
   const void* b2;
   int32_t a_wrap;           // tcgen05 kernels: A is stored with only this many columns and the K loop wraps around it (0 = off):
                             // the split operand [hi | mid | hi] kept as [hi | mid], its third segment re-reads the first
+  int32_t round_bf16;       // EPI_PLAIN with an fp32 output: store fp32(bf16(acc + bias)) — what a bf16 GEMM output widened by the
+                            // consumer holds, without the bf16 tensor and the cast pass (downsample conv -> fp32 residual stream)
   int32_t pf_tiles;         // tcgen05 kernels: the TMA producer prefetches into L2 the A rows (and the epilogue's input slab rows)
                             // of the tile this many persistent-loop steps ahead (0 = off; set by the launcher)
 };
@@ -45,6 +47,10 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int64_t m, i
       load8(p.bias + n, b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += b[i];
+    }
+    if (sizeof(TOUT) == 4 && p.round_bf16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __bfloat162float(__float2bfloat16_rn(acc[i]));
     }
     store8(reinterpret_cast<TOUT*>(p.out0) + off, acc);
   } else if (KIND == EPI_BIAS_GELU) {

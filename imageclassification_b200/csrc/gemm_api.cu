@@ -122,6 +122,11 @@ int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, i
                 "gemm_plain: CNX_GEMM_A_SPLIT2 needs bf16 operands and K/3 a multiple of 32 (K=%lld)", (long long)K);
     ep.a_wrap = (int32_t)(2 * (K / 3));
   }
+  if (flags & CNX_GEMM_OUT_ROUND_BF16) {
+    CNX_REQUIRE(dtype == CNX_BF16 && out_dtype == CNX_F32, CNX_E_BADARG,
+                "gemm_plain: CNX_GEMM_OUT_ROUND_BF16 is for bf16 operands with an fp32 output");
+    ep.round_bf16 = 1;
+  }
   if (dtype == CNX_F32) {
     CNX_REQUIRE(out_dtype == CNX_F32, CNX_E_BADARG, "gemm_plain: fp32 operands need an fp32 output");
     return gemm_tn_simt<float, float, EPI_PLAIN>(A, B, M, N, K, ep, s);

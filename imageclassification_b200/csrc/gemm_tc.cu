@@ -612,6 +612,13 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
         }
+        if (sizeof(TOUT) == 4 && ep.round_bf16) {        // fp32 output holding bf16-rounded values (EpiParams::round_bf16)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint32_t u = pack_bf16(v[i], v[i + 1]);
+            v[i] = bf16_lo(u); v[i + 1] = bf16_hi(u);
+          }
+        }
       } else if (KIND == EPI_SCALE_RES) {
         float sc = 1.0f;
         if (ep.dp) sc = __ldg(ep.dp + (m < M ? m : M - 1) / ep.rows_per_sample);

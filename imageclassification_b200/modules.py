@@ -122,7 +122,11 @@ class ConvNeXtStage(nn.Module):
         if isinstance(ds, nn.Sequential):
             conv = ds[1]
             if conv.kernel_size == (2, 2) and conv.stride == (2, 2) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-                x = torch.ops.cnx.downsample_forward(x, ds[0].weight, ds[0].bias, conv.weight, conv.bias, ds[0].eps)
+                # the first Block widens a bf16 conv output to fp32 on entry (fp32 layer scale): let the conv write that tensor
+                b0 = self.blocks[0] if len(self.blocks) else None
+                widen = (isinstance(b0, ConvNeXtBlock) and b0.gamma is not None and b0.gamma.dtype == torch.float32
+                         and not ops.KEEP_BF16_STREAM)
+                x = torch.ops.cnx.downsample_forward(x, ds[0].weight, ds[0].bias, conv.weight, conv.bias, ds[0].eps, widen)
             else:
                 x = ds(x)
         return self.blocks(x)

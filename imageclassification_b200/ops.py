@@ -590,8 +590,9 @@ def layer_norm_cl(x, w, b, eps: float):
     return _LayerNormCLFn.apply(x, w, b, float(eps), out_dtype)
 
 
-def _gemm_plain(A, B, bias, out_dtype):
-    """out[M,N] = A[M,K] . B[N,K]^T (+ bias[N]); A, B in the activation dtype, fp32 accumulate."""
+def _gemm_plain(A, B, bias, out_dtype, round_bf16=False):
+    """out[M,N] = A[M,K] . B[N,K]^T (+ bias[N]); A, B in the activation dtype, fp32 accumulate.  round_bf16: an fp32 output that
+    holds bf16-rounded values (include/cnx.h CNX_GEMM_OUT_ROUND_BF16)."""
     lib = L.load()
     M, K = A.shape
     Nn = B.shape[0]
@@ -599,8 +600,8 @@ def _gemm_plain(A, B, bias, out_dtype):
             and K % 8 == 0 and Nn % 8 == 0):
         return _gemm_plain_f32_x3(A, B, bias)          # fp32 operands: fp32-accurate split-operand GEMM on the tensor cores
     out = torch.empty((M, Nn), dtype=out_dtype, device=A.device)
-    L.check(lib.cnx_gemm_plain(L.ptr(A), L.ptr(B), L.ptr(bias), L.ptr(out), L.dt(out_dtype), M, Nn, K, L.dt(A), GEMM_FLAGS,
-                               L.stream()), "gemm_plain")
+    L.check(lib.cnx_gemm_plain(L.ptr(A), L.ptr(B), L.ptr(bias), L.ptr(out), L.dt(out_dtype), M, Nn, K, L.dt(A),
+                               GEMM_FLAGS | (L.CNX_GEMM_OUT_ROUND_BF16 if round_bf16 else 0), L.stream()), "gemm_plain")
     return out
 
 
@@ -734,13 +735,19 @@ class _DownsampleFn(torch.autograd.Function):
     """downsample: LayerNorm2d -> Conv2d(C, C2, 2, stride 2) (convnext.py:84-89) as LayerNorm + 2x2 patch gather + GEMM."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, conv_w, conv_b, eps, act_dtype, track):
+    def forward(ctx, x, ln_w, ln_b, conv_w, conv_b, eps, act_dtype, track, widen):
+        global _LAST_OUT
+        _LAST_OUT = None
         lib = L.load()
         L.require_cuda(x, conv_w, ln_w)
         N, C, H, W = x.shape
         C2 = conv_w.shape[0]
         xl = _nhwc(x.detach())
         M = N * H * W
+        # `widen`: the consumer (a Block with an fp32 layer scale, modules.ConvNeXtStage) widens this bf16 conv output to fp32 on
+        # entry (ATen type promotion in the reference, convnext.py:55): the GEMM then writes the fp32 tensor itself, holding the
+        # bf16-rounded values — no bf16 tensor, no cast pass; in backward the Block hands back the bf16 copy of its dx
+        widen = bool(widen) and act_dtype == torch.bfloat16 and GEMM_FLAGS == 0 and C2 % 8 == 0
         # LayerNorm writes the GEMM operand directly in 2x2-patch-major order (no gather pass)
         A = torch.empty((M // 4, 4 * C), dtype=act_dtype, device=x.device)
         mean = torch.empty((M,), dtype=torch.float32, device=x.device)
@@ -749,12 +756,16 @@ class _DownsampleFn(torch.autograd.Function):
                                       L.ptr(mean), L.ptr(rstd), L.stream()), "ln_fwd_patch2")
         if not track and X3_FWD and act_dtype == torch.float32 and C2 % 8 == 0:
             out = _gemm_plain_x3(A, conv_w, True, conv_b)
+        elif widen:
+            out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, torch.float32, round_bf16=True)
         else:
             out = _gemm_plain(A, _patch_weight(conv_w, act_dtype, True), conv_b, act_dtype)
         if track and (ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:5])):
             ctx.save_for_backward(xl, mean, rstd, A, conv_w, ln_w)
             ctx.shape = (N, C, H, W)
             ctx.act_dtype = act_dtype
+            if widen and DZ_HANDOFF:
+                _LAST_OUT = (out.data_ptr(), (N, H // 2, W // 2, C2), None)
         return out.view(N, H // 2, W // 2, C2).permute(0, 3, 1, 2)
 
     @staticmethod
@@ -765,9 +776,17 @@ class _DownsampleFn(torch.autograd.Function):
         act_dtype = ctx.act_dtype
         C2 = conv_w.shape[0]
         M = N * H * W
-        d2 = _nhwc(dout).reshape(M // 4, C2)
-        if d2.dtype != act_dtype:
-            d2 = d2.to(act_dtype)
+        global _DZ_HANDOFF
+        ho, _DZ_HANDOFF = _DZ_HANDOFF, None
+        dl = _nhwc(dout)
+        if (ho is not None and ho[2] is None and ho[0].data_ptr() == dl.data_ptr() and ho[0].shape == dl.shape
+                and ho[0].dtype == dl.dtype and ho[1].dtype == act_dtype):
+            d2 = ho[1].reshape(M // 4, C2)       # bf16 copy of this gradient, written by the first Block's dwconv backward-data kernel
+        else:
+            d2 = dl.reshape(M // 4, C2)
+            if d2.dtype != act_dtype:
+                d2 = d2.to(act_dtype)
+        del ho
         # weight / bias gradient: dWp[C2, 4C] = d2^T . A  (taps-last layout) -> canonical [C2, C, 2, 2]
         dWp, db = _wgrad(d2, A, M // 4, C2, 4 * C, True)
         dW = dWp.view(C2, 2, 2, C).permute(0, 3, 1, 2).contiguous()
@@ -785,7 +804,7 @@ class _DownsampleFn(torch.autograd.Function):
         L.check(lib.cnx_reduce_partials(L.ptr(part), P, 2 * C, 1.0, 0, L.ptr(dwb), L.stream()), "reduce_partials")
         dlw, dlb = dwb[:C], dwb[C:]
         dx = dxl.view(N, H, W, C).permute(0, 3, 1, 2)
-        return dx, dlw, dlb, dW, db, None, None, None
+        return dx, dlw, dlb, dW, db, None, None, None, None
 
 
 def stem_forward(x, conv_w, conv_b, ln_w, ln_b, eps: float):
@@ -793,9 +812,10 @@ def stem_forward(x, conv_w, conv_b, ln_w, ln_b, eps: float):
     return _StemFn.apply(x, conv_w, conv_b, ln_w, ln_b, float(eps), _act_dtype(), torch.is_grad_enabled())
 
 
-def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float):
-    """LayerNorm2d + Conv2d(C, C2, 2, 2) on a logical [N,C,H,W] stream -> logical [N,C2,H/2,W/2]."""
-    return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype(), torch.is_grad_enabled())
+def downsample_forward(x, ln_w, ln_b, conv_w, conv_b, eps: float, widen: bool = False):
+    """LayerNorm2d + Conv2d(C, C2, 2, 2) on a logical [N,C,H,W] stream -> logical [N,C2,H/2,W/2].  widen: under bf16 autocast
+    return the conv output as the fp32 tensor its consumer would widen it to (same values)."""
+    return _DownsampleFn.apply(x, ln_w, ln_b, conv_w, conv_b, float(eps), _act_dtype(), torch.is_grad_enabled(), bool(widen))
 
 
 class _HeadFn(torch.autograd.Function):
@@ -941,7 +961,8 @@ _SCHEMAS = {
                       "Tensor? gamma, Tensor? dp, float eps) -> Tensor", block_forward),
     "layer_norm_cl": ("(Tensor x, Tensor w, Tensor b, float eps) -> Tensor", layer_norm_cl),
     "stem_forward": ("(Tensor x, Tensor conv_w, Tensor conv_b, Tensor ln_w, Tensor ln_b, float eps) -> Tensor", stem_forward),
-    "downsample_forward": ("(Tensor x, Tensor ln_w, Tensor ln_b, Tensor conv_w, Tensor conv_b, float eps) -> Tensor", downsample_forward),
+    "downsample_forward": ("(Tensor x, Tensor ln_w, Tensor ln_b, Tensor conv_w, Tensor conv_b, float eps, bool widen=False) -> Tensor",
+                           downsample_forward),
     "head_forward": ("(Tensor x, Tensor ln_w, Tensor ln_b, Tensor fc_w, Tensor fc_b, float eps) -> Tensor", head_forward),
     "soft_target_cross_entropy": ("(Tensor x, Tensor target) -> Tensor", soft_target_cross_entropy),
     "mixup_target": ("(Tensor target, int num_classes, float lam=1.0, float smoothing=0.0) -> Tensor", mixup_target),

@@ -190,6 +190,10 @@ CNX_API int cnx_dwconv7_wgrad_finalize(const float* partial, int P, int64_t C, i
  * cnx_gemm_bias_gelu_fwd_x3, or by cnx_split3 / cnx_dwconv7_ln_fwd_x3 with segments = 2); the K loop covers three segments and
  * the third re-reads the first ([hi | mid | hi]) — the operand crosses HBM as 2 pieces instead of 3. */
 #define CNX_GEMM_A_SPLIT2 2
+/* cnx_gemm_plain, bf16 operands, fp32 output: store fp32(bf16(acc + bias)) — the values a bf16 output widened to fp32 by its
+ * consumer would hold (autocast's Conv2d output entering the fp32 residual stream, convnext.py:84-89 -> :55), without writing
+ * the bf16 tensor and re-reading it in a cast pass. */
+#define CNX_GEMM_OUT_ROUND_BF16 4
 
 /* fc1: h = round_dtype(A.W1^T + b1) ; g_out = GELU_erf(h) ; gprime_out = GELU_erf'(h) (what backward needs of h:
  * saved instead of h so the dgrad epilogue is one multiply).  gprime_out may be NULL (no-grad forward). */

@@ -171,3 +171,56 @@ def test_head_fwd_bwd(mode, N, C, H, K):
         assert max_rel(gp[n], go[n]) <= tol, n
     with torch.no_grad():                                    # fp32 no-grad: split-operand tensor-core GEMM
         assert max_rel(p(x), o(x)) <= 1e-4
+
+
+def test_downsample_widened_output_and_gradient_handoff(monkeypatch):
+    """Under bf16 autocast the downsample conv of a stage writes the fp32 tensor its first Block would widen the bf16 output to
+    (CNX_GEMM_OUT_ROUND_BF16: same values, no cast pass), and that Block's backward hands back the bf16 copy of its dx (no cast
+    pass either).  Outputs and every gradient are bit-identical to the path with the bf16 output and the two ATen casts."""
+    from imageclassification_b200 import modules as PM
+    torch.manual_seed(4)
+    stage = PM.ConvNeXtStage(96, 192, stride=2, depth=2, drop_path_rates=[0.0, 0.25], ls_init_value=1.0).to(DEV)
+    with torch.no_grad():
+        for p in stage.parameters():
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(6, 96, 28, 28, generator=g).to(DEV)
+    dout = torch.randn(6, 192, 14, 14, generator=g).to(DEV)
+
+    def run(widen):
+        stage.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        torch.manual_seed(21)
+        c0 = dict(L.CALL_COUNTS)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if widen:
+                y = stage(xi)
+            else:
+                ds = stage.downsample
+                t = torch.ops.cnx.downsample_forward(xi, ds[0].weight, ds[0].bias, ds[1].weight, ds[1].bias, ds[0].eps, False)
+                assert t.dtype == torch.bfloat16
+                y = stage.blocks(t)
+        y.backward(dout)
+        n = {k: L.CALL_COUNTS[k] - c0.get(k, 0) for k in ("cnx_grad_prep", "cnx_dwconv7_dgrad_dz")}
+        return y, xi.grad, [p.grad.clone() for p in stage.parameters()], n
+
+    y1, dx1, g1, n1 = run(True)
+    assert n1 == {"cnx_grad_prep": 1, "cnx_dwconv7_dgrad_dz": 2}, n1          # both Blocks hand their dx copy upstream
+    y0, dx0, g0, n0 = run(False)
+    assert n0 == {"cnx_grad_prep": 1, "cnx_dwconv7_dgrad_dz": 1}, n0
+    assert y1.dtype == torch.float32 and torch.equal(y1, y0) and torch.equal(dx1, dx0)
+    for a, b in zip(g1, g0):
+        assert torch.equal(a, b)
+    monkeypatch.setattr(ops, "DZ_HANDOFF", False)
+    y2, dx2, g2, n2 = run(True)
+    assert n2 == {"cnx_grad_prep": 2, "cnx_dwconv7_dgrad_dz": 0}, n2
+    assert torch.equal(y2, y0) and torch.equal(dx2, dx0)
+    for a, b in zip(g2, g0):
+        assert torch.equal(a, b)
+    # the widened tensor itself: fp32 holding bf16-representable values, equal to the bf16 output
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ds = stage.downsample
+        a = torch.ops.cnx.downsample_forward(x, ds[0].weight, ds[0].bias, ds[1].weight, ds[1].bias, ds[0].eps, True)
+        b = torch.ops.cnx.downsample_forward(x, ds[0].weight, ds[0].bias, ds[1].weight, ds[1].bias, ds[0].eps, False)
+    assert a.dtype == torch.float32 and b.dtype == torch.bfloat16 and torch.equal(a, b.float())
