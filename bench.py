@@ -235,6 +235,9 @@ def kernel_work(name, a):
     if name == "cnx_mlp_fused_fwd":
         M, C = a[10:12]
         return M * C * (2 + 4 + 4) + 8 * C * C * 2, 16 * M * C * C, f"mlp_fused_fwd C{C}"
+    if name == "cnx_mlp_fused_fwd_x3":      # xn as [hi | mid] bf16 in, fp32 residual in, fp32 out; the split weights from L2
+        M, C = a[10:12]
+        return M * C * (4 + 4 + 4) + 2 * 4 * C * 3 * C * 2, 16 * M * C * C, f"mlp_fused_x3 C{C}"
     if name == "cnx_gemm_dgrad_gelu_bwd":
         M, N, K = a[4:7]
         e = es(a[7])

@@ -13,6 +13,9 @@ int gemm_wgrad_simt(const void* X, const void* Y, int64_t M, int64_t N1, int64_t
                     float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                   float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx = 0, int64_t ldy = 0);
+int mlp_fused_fwd_x3_tc(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2, const float* gamma,
+                        const float* dp, int64_t rows_per_sample, const float* shortcut, float* out, int64_t M, int64_t C,
+                        cudaStream_t s);
 int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out, int64_t M, int64_t C,
                      cudaStream_t s);
@@ -86,6 +89,17 @@ int cnx_mlp_fused_fwd(const void* xn, const void* W1, const float* b1, const voi
   CNX_REQUIRE(xn && W1 && b1 && W2 && b2 && shortcut && out, CNX_E_BADARG, "mlp_fused_fwd: null pointer");
   CNX_REQUIRE(M > 0 && rows_per_sample > 0, CNX_E_BADARG, "mlp_fused_fwd: bad shape");
   return mlp_fused_fwd_tc(xn, W1, b1, W2, b2, gamma, dp, rows_per_sample, shortcut, out, M, C, (cudaStream_t)stream);
+}
+
+int cnx_mlp_fused_fwd_x3(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2, const float* gamma,
+                         const float* dp, int64_t rows_per_sample, const float* shortcut, float* out, int64_t M, int64_t C,
+                         void* stream) {
+  CNX_REQUIRE(xn2 && W1x3 && b1 && W2x3 && b2 && shortcut && out, CNX_E_BADARG, "mlp_fused_fwd_x3: null pointer");
+  CNX_REQUIRE(M > 0 && rows_per_sample > 0, CNX_E_BADARG, "mlp_fused_fwd_x3: bad shape");
+  CNX_REQUIRE(((uintptr_t)shortcut & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)b2 & 15) == 0 &&
+                  (gamma == nullptr || ((uintptr_t)gamma & 15) == 0) && ((uintptr_t)b1 & 15) == 0,
+              CNX_E_SHAPE, "mlp_fused_fwd_x3: shortcut, out, biases and gamma must be 16-byte aligned");
+  return mlp_fused_fwd_x3_tc(xn2, W1x3, b1, W2x3, b2, gamma, dp, rows_per_sample, shortcut, out, M, C, (cudaStream_t)stream);
 }
 
 int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,

@@ -1180,6 +1180,292 @@ mlp_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_cons
 }
 
 // ================================================================================================
+// Fused split-operand ("x3", fp32-accurate) MLP forward for C = 96, no-grad pass:
+//     out = x + dp * gamma * ( GELU_erf(xn . W1^T + b1) . W2^T + b2 )      with every product as hi.hi + mid.hi + hi.mid
+// The unfused pair writes the hidden activation as two bf16 pieces and reads it back: 2 x 8 bytes per hidden element, 6.1 KB of
+// the 7.2 KB a token moves at C = 96 — both GEMMs sit on the HBM roof there.  Here the [128, 64] hidden chunk goes
+// TMEM -> registers (bias, erf GELU in fp32, split into bf16 hi / mid) -> shared memory in the K-major 128B-swizzled layout of an
+// MMA A operand -> GEMM2, and never reaches HBM: a token moves 2C*2 (xn pieces) + C*4 (x) + C*4 (out) = 1.2 KB.
+// Structure as mlp_fused_fwd_kernel (producer warp, MMA issuer, 16 epilogue warps, acc1 double-buffered in TMEM, acc2
+// persistent over the tile); differences: operands arrive as (hi, mid) box pairs, each GEMM issues three products, the hidden
+// chunk has ONE shared-memory buffer pair (208 KB of shared memory are taken by the xn pieces, two weight stages and it), and the
+// final epilogue reads the residual / writes the output rows straight from registers (a lane owns a 128-byte line of each).
+// Operand tensors: xn2 [M, 2C] = [hi | mid] (cnx_dwconv7_ln_fwd_x3, segments = 2); W1x3 [4C, 3C] and W2x3 [C, 12C] = [hi | hi | mid]
+// (cnx_weight_prep mode 3): hi at column 0, mid at column 2K.
+// ================================================================================================
+template <int C> struct Fu3Cfg {
+  static constexpr int KBX = (C + 63) / 64;                 // 64-wide K boxes per piece of the xn / W1 tiles
+  static constexpr int XN_BYTES = 2 * KBX * BM * 128;       // hi and mid pieces of the [128, C] xn tile
+  static constexpr int W1_BYTES = 2 * KBX * kFuHCH * 128;   // hi and mid pieces of the [64 hidden rows, C] W1 chunk
+  static constexpr int W2_BYTES = 2 * C * 128;              // hi and mid pieces of the [C rows, 64 hidden k] W2 chunk
+  static constexpr int WST_BYTES = W1_BYTES + W2_BYTES;
+  static constexpr int G_BYTES = 2 * BM * 128;              // hi and mid pieces of the [128, 64] GELU chunk
+  static constexpr int NCH32 = C / 32;
+  static constexpr int NFIN = NCH32 * 4;                    // warps of the final epilogue: one (lane quarter, 32-column chunk) each
+  static constexpr int NBARS = 2 + 8 + 4 + 2 + 2 + 1;
+  static constexpr int SMEM = XN_BYTES + 2 * WST_BYTES + G_BYTES + 1024 + 8 * NBARS + 64;
+  static constexpr int ACC2_COL = 128;
+  static_assert(C % 32 == 0 && NFIN <= kFuEpiWarps && ACC2_COL + C <= 256, "fused x3 MLP tile shape");
+  static_assert((C * 128) % 1024 == 0, "W2 pieces must stay 1024-byte aligned for the 128B swizzle");
+  static_assert(SMEM <= 227 * 1024, "fused x3 MLP does not fit in shared memory");
+};
+
+template <int C>
+__global__ void __launch_bounds__(kFuThreads, 1)
+mlp_fused_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_constant__ CUtensorMap tmW1,
+                        const __grid_constant__ CUtensorMap tmW2, int64_t M, const float* __restrict__ b1,
+                        const float* __restrict__ b2, const float* __restrict__ gamma, const float* __restrict__ dp,
+                        int64_t rows_per_sample, const float* __restrict__ shortcut, float* __restrict__ out) {
+  typedef Fu3Cfg<C> Cfg;
+  constexpr int NJ = 4 * C / kFuHCH;                 // hidden chunks per tile
+  constexpr int KBX = Cfg::KBX;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sXn = base;
+  const uint32_t sW = sXn + Cfg::XN_BYTES;
+  const uint32_t sG = sW + 2 * Cfg::WST_BYTES;
+  const uint32_t bars = sG + Cfg::G_BYTES;
+  int bi = 0;
+  auto nb = [&](int n) { const uint32_t a = bars + 8u * bi; bi += n; return a; };
+  const uint32_t xn_full = nb(1), xn_empty = nb(1);
+  // the W1 and W2 pieces of a weight stage have their own barrier pairs: W1(j) is free again as soon as GEMM1(j) has retired,
+  // a whole chunk before GEMM2(j) lets go of W2(j) — with one pair per stage every GEMM1 waited for a reload that could only
+  // start when the GEMM2 of two chunks ago had retired (tensor pipe 22 % active, profiles/r02z6_stalls.txt)
+  const uint32_t w1_full = nb(2), w1_empty = nb(2), w2_full = nb(2), w2_empty = nb(2);
+  const uint32_t a1_full = nb(2), a1_empty = nb(2);
+  const uint32_t g_full = nb(1), g_empty = nb(1);
+  const uint32_t a2_full = nb(1), a2_empty = nb(1);
+  const uint32_t tmem_slot = nb(1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmXn); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(xn_full, 1); mbar_init(xn_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(w1_full + 8 * i, 1); mbar_init(w1_empty + 8 * i, 1);
+      mbar_init(w2_full + 8 * i, 1); mbar_init(w2_empty + 8 * i, 1);
+      mbar_init(a1_full + 8 * i, 1); mbar_init(a1_empty + 8 * i, kFuEpiWarps);
+    }
+    mbar_init(g_full, kFuEpiWarps); mbar_init(g_empty, 1);
+    mbar_init(a2_full, 1); mbar_init(a2_empty, Cfg::NFIN);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: the (hi, mid) xn tile once per tile; per hidden chunk the (hi, mid) W1 pieces — one chunk AHEAD of the
+      // (hi, mid) W2 pieces, since GEMM1 runs a chunk ahead of GEMM2 =====
+      const int64_t my_tiles = ((int64_t)blockIdx.x < m_tiles) ? (m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int64_t total = my_tiles * NJ;                         // hidden chunks this CTA walks
+      auto load_xn = [&](int64_t t) {
+        const int64_t tile = blockIdx.x + t * gridDim.x;
+        mbar_wait(xn_empty, (uint32_t)((t & 1) ^ 1));
+        mbar_expect_tx(xn_full, Cfg::XN_BYTES);
+        for (int seg = 0; seg < 2; ++seg)
+          for (int kb = 0; kb < KBX; ++kb)
+            tma_load_2d(sXn + (seg * KBX + kb) * (BM * 128), &tmXn, xn_full, seg * C + kb * 64, (int32_t)(tile * BM));
+        // the xn tile has ONE buffer: the next tile's load can only be issued when this tile's last GEMM1 has retired, so at
+        // least make it an L2 hit
+        if (tile + gridDim.x < m_tiles)
+          for (int c = 0; c < 2 * C; c += 64) tma_prefetch_2d(&tmXn, c, (int32_t)((tile + gridDim.x) * BM));
+      };
+      auto load_w1 = [&](int64_t c) {
+        const uint32_t ws = (uint32_t)(c & 1), wu = (uint32_t)(c >> 1);
+        const int j = (int)(c % NJ);
+        mbar_wait(w1_empty + 8 * ws, (wu & 1) ^ 1);
+        mbar_expect_tx(w1_full + 8 * ws, Cfg::W1_BYTES);
+        const uint32_t wb = sW + ws * Cfg::WST_BYTES;
+        for (int seg = 0; seg < 2; ++seg)
+          for (int kb = 0; kb < KBX; ++kb)
+            tma_load_2d(wb + (seg * KBX + kb) * (kFuHCH * 128), &tmW1, w1_full + 8 * ws, seg * 2 * C + kb * 64, j * kFuHCH);
+      };
+      auto load_w2 = [&](int64_t c) {
+        const uint32_t ws = (uint32_t)(c & 1), wu = (uint32_t)(c >> 1);
+        const int j = (int)(c % NJ);
+        mbar_wait(w2_empty + 8 * ws, (wu & 1) ^ 1);
+        mbar_expect_tx(w2_full + 8 * ws, Cfg::W2_BYTES);
+        const uint32_t wb = sW + ws * Cfg::WST_BYTES + Cfg::W1_BYTES;
+        for (int seg = 0; seg < 2; ++seg) tma_load_2d(wb + seg * (C * 128), &tmW2, w2_full + 8 * ws, seg * 8 * C + j * kFuHCH, 0);
+      };
+      if (total > 0) {
+        load_xn(0);
+        load_w1(0);
+      }
+      for (int64_t c = 0; c < total; ++c) {
+        if (c + 1 < total) {
+          if ((c + 1) % NJ == 0) load_xn((c + 1) / NJ);            // first chunk of the next tile: its xn pieces first
+          load_w1(c + 1);
+        }
+        load_w2(c);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: GEMM1(j) runs one chunk ahead of GEMM2(j-1); each is three products (hi.hi, mid.hi, hi.mid) =====
+      constexpr uint32_t idesc1 = make_idesc(BM, kFuHCH, 0, 0);
+      constexpr uint32_t idesc2 = make_idesc(BM, C, 0, 0);
+      uint32_t tcnt = 0, cc = 0;
+      for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++tcnt) {
+        mbar_wait(xn_full, tcnt & 1);
+        for (int j = 0; j <= NJ; ++j) {
+          if (j < NJ) {
+            const uint32_t c = cc + j, b = c & 1, u = c >> 1;
+            mbar_wait(w1_full + 8 * b, u & 1);
+            mbar_wait(a1_empty + 8 * b, (u & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d1 = tmem_base + b * kFuHCH;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              const int aseg = (p == 1) ? 1 : 0, bseg = (p == 2) ? 1 : 0;
+#pragma unroll
+              for (int kb = 0; kb < KBX; ++kb) {
+                const uint64_t adesc = make_smem_desc(sXn + (aseg * KBX + kb) * (BM * 128), 16, 1024);
+                const uint64_t bdesc = make_smem_desc(sW + b * Cfg::WST_BYTES + (bseg * KBX + kb) * (kFuHCH * 128), 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (kb * 64 + k * 16 < C) { umma_f16(d1, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc1, acc); acc = 1; }
+              }
+            }
+            umma_commit(a1_full + 8 * b);
+            umma_commit(w1_empty + 8 * b);
+            if (j == NJ - 1) umma_commit(xn_empty);
+          }
+          if (j > 0) {
+            const uint32_t c = cc + j - 1, b = c & 1;
+            mbar_wait(w2_full + 8 * b, (c >> 1) & 1);
+            mbar_wait(g_full, c & 1);
+            if (j == 1) mbar_wait(a2_empty, (tcnt & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              const int aseg = (p == 1) ? 1 : 0, bseg = (p == 2) ? 1 : 0;
+              const uint64_t adesc = make_smem_desc(sG + aseg * (BM * 128), 16, 1024);
+              const uint64_t bdesc = make_smem_desc(sW + b * Cfg::WST_BYTES + Cfg::W1_BYTES + bseg * (C * 128), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base + Cfg::ACC2_COL, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc2, ((j - 1) | p | k) != 0);
+            }
+            umma_commit(g_empty);
+            umma_commit(w2_empty + 8 * b);
+            if (j == NJ) umma_commit(a2_full);
+          }
+        }
+        cc += NJ;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kFirstEpiWarp) {
+    const int ew = warp - kFirstEpiWarp;
+    const int quarter = warp & 3;
+    const int cg = ew >> 2;                           // 16 of the chunk's 64 hidden columns; 32 of the output tile's columns
+    const int r = quarter * 32 + lane;                // row within the tile
+    const uint32_t lane_t = (uint32_t)(quarter * 32) << 16;
+    const uint32_t g_row = sG + (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    const bool fin = ew < Cfg::NFIN;
+    uint32_t cc = 0, tcnt = 0;
+    for (int64_t tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++tcnt) {
+      if (fin) {
+        // the residual line of this lane's output row: pulled into L2 now, read after the tile's last chunk
+        const int64_t m = tile * BM + r;
+        if (m < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(shortcut + m * C + cg * 32));
+      }
+      for (int j = 0; j < NJ; ++j, ++cc) {
+        const uint32_t b = cc & 1, u = cc >> 1;
+        // the chunk's bias slice is fetched BEFORE the wait for its accumulator (it was 8 % of all warp samples as the first use
+        // after the wait, profiles/r02z6_stalls.txt)
+        float4 bq[4];
+        const float* bp = b1 + j * kFuHCH + cg * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bq[i] = __ldg(reinterpret_cast<const float4*>(bp + 4 * i));
+        mbar_wait(a1_full + 8 * b, u & 1);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(tmem_base + b * kFuHCH + lane_t + cg * 16, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a1_empty + 8 * b);
+        uint32_t ph[8], pm[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = bq[i / 4];
+          // fp32 h (no rounding), erf GELU in fp32, g ~ hi + mid to 2^-17 relative
+          const float2 ga = gelu_as2(__fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y)));
+          const float2 gb = gelu_as2(__fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w)));
+          const uint32_t ha = pack_bf16(ga.x, ga.y), hb = pack_bf16(gb.x, gb.y);
+          ph[i / 2] = ha;
+          ph[i / 2 + 1] = hb;
+          const float2 ra = __fadd2_rn(ga, make_float2(-bf16_lo(ha), -bf16_hi(ha)));
+          const float2 rb = __fadd2_rn(gb, make_float2(-bf16_lo(hb), -bf16_hi(hb)));
+          pm[i / 2] = pack_bf16(ra.x, ra.y);
+          pm[i / 2 + 1] = pack_bf16(rb.x, rb.y);
+        }
+        mbar_wait(g_empty, (cc & 1) ^ 1);             // GEMM2 of the previous chunk has consumed the buffer pair
+        const uint32_t o0 = ((uint32_t)(cg * 2) ^ swz) << 4, o1 = ((uint32_t)(cg * 2 + 1) ^ swz) << 4;
+        sts128(g_row + o0, ph[0], ph[1], ph[2], ph[3]);
+        sts128(g_row + o1, ph[4], ph[5], ph[6], ph[7]);
+        sts128(g_row + BM * 128 + o0, pm[0], pm[1], pm[2], pm[3]);
+        sts128(g_row + BM * 128 + o1, pm[4], pm[5], pm[6], pm[7]);
+        fence_proxy_async();                          // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_full);
+      }
+      if (fin) {
+        // ===== final epilogue: this warp's (lane quarter, 32-column chunk) of the [128, C] output tile =====
+        mbar_wait(a2_full, tcnt & 1);
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem_base + Cfg::ACC2_COL + lane_t + cg * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a2_empty);
+        const int64_t m = tile * BM + r;
+        if (m < M) {
+          const float sc = dp ? __ldg(dp + m / rows_per_sample) : 1.0f;
+          const int n0 = cg * 32;
+          const float4* res = reinterpret_cast<const float4*>(shortcut + m * C + n0);
+          float4* dst = reinterpret_cast<float4*>(out + m * C + n0);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n0 + i));
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + n0 + i));
+            const float4 x4 = __ldg(res + i / 4);
+            float4 o;
+            o.x = x4.x + sc * (g4.x * (v[i] + b4.x));
+            o.y = x4.y + sc * (g4.y * (v[i + 1] + b4.y));
+            o.z = x4.z + sc * (g4.z * (v[i + 2] + b4.z));
+            o.w = x4.w + sc * (g4.w * (v[i + 3] + b4.w));
+            dst[i / 4] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ================================================================================================
 // wgrad on CTA pairs: one tcgen05.mma.cta_group::2 spans a 256 x BN tile of out = X^T.Y (BN = 128, 256 or 384).  Each CTA stages
 // its own 128 channels of X (two 64-channel MN-major boxes) and HALF of the BN channels of Y per 64-row k-block, so a CTA moves
 // 24 / 32 KB per k-block where the single-CTA 128 x 128 tile moves 32 KB for a quarter / half of the MACs.  Bias gradient,
@@ -1563,6 +1849,23 @@ static int launch_mlp_fused(const void* xn, const void* W1, const float* b1, con
   return check_launch("mlp_fused_fwd");
 }
 
+template <int C>
+static int launch_mlp_fused_x3(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2, const float* gamma,
+                               const float* dp, int64_t rows_per_sample, const float* shortcut, float* out, int64_t M, cudaStream_t s) {
+  typedef Fu3Cfg<C> Cfg;
+  CUtensorMap tmXn, tmW1, tmW2;
+  if (int rc = make_map(&tmXn, xn2, M, 2 * C, BM)) return rc;                 // [hi | mid]
+  if (int rc = make_map(&tmW1, W1x3, 4 * C, 3 * C, kFuHCH)) return rc;        // [hi | hi | mid]: pieces at columns 0 and 2C
+  if (int rc = make_map(&tmW2, W2x3, C, 12 * C, C)) return rc;                // [hi | hi | mid]: pieces at columns 0 and 8C
+  auto k = mlp_fused_x3_fwd_kernel<C>;
+  if (int rc = set_smem(k, Cfg::SMEM)) return rc;
+  int64_t grid = sm_count();
+  const int64_t tiles = (M + BM - 1) / BM;
+  if (grid > tiles) grid = tiles;
+  launch_pdl(k, dim3((unsigned)grid), dim3(kFuThreads), Cfg::SMEM, s, tmXn, tmW1, tmW2, M, b1, b2, gamma, dp, rows_per_sample, shortcut, out);
+  return check_launch("mlp_fused_fwd_x3");
+}
+
 }  // namespace tc
 
 int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
@@ -1575,6 +1878,14 @@ int mlp_fused_fwd_tc(const void* xn, const void* W1, const float* b1, const void
   return CNX_E_SHAPE;
 }
 
+
+int mlp_fused_fwd_x3_tc(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2, const float* gamma,
+                        const float* dp, int64_t rows_per_sample, const float* shortcut, float* out, int64_t M, int64_t C,
+                        cudaStream_t s) {
+  if (C == 96) return tc::launch_mlp_fused_x3<96>(xn2, W1x3, b1, W2x3, b2, gamma, dp, rows_per_sample, shortcut, out, M, s);
+  set_error("mlp_fused_fwd_x3: C=%lld is not a fused shape (96)", (long long)C);
+  return CNX_E_SHAPE;
+}
 
 template <int KIND, typename TOUT>
 int gemm_tn_tc(const void* A, const void* B, int64_t M, int64_t N, int64_t K, const EpiParams& ep, cudaStream_t s) {

@@ -21,6 +21,7 @@ from . import _lib as L
 GEMM_FLAGS = 0
 # The fused no-grad MLP kernel (C <= 192); CNX_FUSED_MLP=0 in the environment selects the two-GEMM path for comparison.
 FUSED_MLP = os.environ.get("CNX_FUSED_MLP", "1") != "0"
+FUSED_MLP_X3 = os.environ.get("CNX_FUSED_MLP_X3", "1") != "0"     # fused split-operand MLP in the fp32 no-grad forward (C = 96)
 # The reference's `gamma * x` (fp32 parameter x bf16 activation) and the residual add promote the stream to fp32 at the first
 # Block after every bf16 downsample conv (convnext.py:52-55 under autocast).  CNX_BF16_STREAM=1 keeps the stream in bf16 through
 # stages 1-3 instead (a third less activation traffic there, still inside the bf16 tolerance) — NOT the reference's dtypes,
@@ -365,11 +366,18 @@ class _BlockFn(torch.autograd.Function):
             a3 = torch.empty((M, 2 * C), dtype=bf, device=dev)             # [hi | mid] of xn: fc1's K loop wraps for the third segment
             L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(xl), L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C,
                                               L.ptr(y), L.ptr(a3), L.ptr(mean), L.ptr(rstd), 2, st), "dwconv7_ln_fwd_x3")
+            out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
+            if FUSED_MLP_X3 and C == 96 and C4 == 4 * C and M >= 128:
+                # fc1 -> GELU -> split -> fc2 -> gamma / drop-path / residual in one kernel: the hidden activation (85 % of the
+                # bytes the unfused pair moves at C = 96) never reaches HBM
+                L.check(lib.cnx_mlp_fused_fwd_x3(L.ptr(a3), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1),
+                                                 L.ptr(_weight_prep(w2, 3, None, bf)), L.ptr(b2), L.ptr(gamma), L.ptr(dp), H * W,
+                                                 L.ptr(xl), L.ptr(out), M, C, st), "mlp_fused_fwd_x3")
+                return out.permute(0, 3, 1, 2)
             g2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)            # [hi | mid] of g
             L.check(lib.cnx_gemm_bias_gelu_fwd_x3(L.ptr(a3), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), M, C4, 3 * C,
                                                   L.ptr(g2), 2, st), "gemm_bias_gelu_fwd_x3")
             del a3
-            out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
             # (running fc1 -> fc2 over L2-sized row blocks so that g never reaches HBM was measured SLOWER: 36.9-41.1 ms/step
             # against 35.0 for blocks of 96-32 MB — launch-bound, and the L2 does not keep a written block resident)
             L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g2), L.ptr(_weight_prep(w2, 3, None, bf)), L.ptr(b2), L.ptr(gamma),

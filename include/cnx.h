@@ -251,6 +251,15 @@ CNX_API int cnx_mlp_fused_fwd(const void* xn, const void* W1, const float* b1, c
                       const float* gamma, const float* dp, int64_t rows_per_sample, const void* shortcut, void* out,
                       int64_t M, int64_t C, void* stream);
 
+/* The same on split operands (fp32-accurate "x3" forward, C = 96; no-grad pass of an fp32 model or the fp32 accuracy forward of
+ * engine.py:89-97): xn2 [M,2C] bf16 = [hi | mid] (cnx_dwconv7_ln_fwd_x3 with segments = 2), W1x3 [4C,3C] and W2x3 [C,12C] bf16 =
+ * [hi | hi | mid] (cnx_weight_prep mode 3), shortcut/out [M,C] fp32.  Every product is hi.hi + mid.hi + hi.mid with fp32
+ * accumulation, GELU is the fp32 erf form of cnx_gemm_bias_gelu_fwd_x3; the hidden activation (2 x 8 bytes per element through
+ * HBM in the unfused pair) stays on chip. */
+CNX_API int cnx_mlp_fused_fwd_x3(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2,
+                         const float* gamma, const float* dp, int64_t rows_per_sample, const float* shortcut, float* out,
+                         int64_t M, int64_t C, void* stream);
+
 /* dgrad of fc2 with GELU': dh[m,n] = acc[m,n] * gprime[m,n],  acc = dz.W2s (B given as [N=4C, K=C]),
  * gprime = GELU'(h) as saved by cnx_gemm_bias_gelu_fwd. */
 CNX_API int cnx_gemm_dgrad_gelu_bwd(const void* dz, const void* Bt, const void* gprime, void* dh, int64_t M, int64_t N,

@@ -140,6 +140,11 @@ for si in [int(s) for s in args.stages.split(",")]:
         timeit(f"fc2_scale_res_x3 {tag}", lambda: L.check(lib.cnx_gemm_bias_scale_residual_fwd(
             L.ptr(g2), L.ptr(w23), L.ptr(b2), L.ptr(gam), None, H * H, L.ptr(xs), L.ptr(o32), L.dt(f32), M, C, 12 * C, L.dt(bf),
             L.CNX_GEMM_A_SPLIT2, st)))
+        if C == 96:
+            a2 = a3[:, :2 * C].contiguous()
+            timeit(f"mlp_fused_fwd_x3 {tag}", lambda: L.check(lib.cnx_mlp_fused_fwd_x3(
+                L.ptr(a2), L.ptr(w13), L.ptr(b1), L.ptr(w23), L.ptr(b2), L.ptr(gam), None, H * H, L.ptr(xs), L.ptr(o32), M, C, st)))
+            del a2
         del a3, g2, o32
         W2t = W2.t().contiguous()
         timeit(f"dgrad_fc2_gelu {tag}", lambda: cabi.gemm_dgelu(A, W2t, hh))

@@ -247,3 +247,48 @@ def test_block_chain_backward_operand_handoff(drop_path, monkeypatch):
         assert torch.equal(a, b)
     for a, b, c in zip(g1, g0, g2):
         assert torch.equal(a, b) and torch.equal(c, b)
+
+
+@pytest.mark.parametrize("N,H,W", [(8, 56, 56), (3, 28, 28), (1, 9, 13), (5, 7, 7), (2, 16, 8)])
+@pytest.mark.parametrize("drop_path,gamma_init", [(0.0, 1.0), (0.35, 1e-6), (0.0, None)])
+def test_block_fused_x3_mlp_matches_unfused(N, H, W, drop_path, gamma_init, monkeypatch):
+    """cnx_mlp_fused_fwd_x3 (C = 96: fc1 -> GELU -> split -> fc2 in one kernel, hidden activation on chip) against the unfused
+    split-operand pair and against the fp32 oracle: whole and ragged 128-row tiles (M = 117 ... 25088), drop-path in train mode,
+    tiny and absent layer scale.  Same products, another summation order: 2e-5 between the two; the fp32 bar (1e-4) vs the oracle."""
+    from imageclassification_b200 import _lib as L, ops
+    C = 96
+    o, p = _pair_block(C, drop_path, gamma_init, N * H + W)
+    x = torch.randn(N, C, H, W, device=DEV)
+    if N * H * W < 128:
+        pytest.skip("below one tile the Block takes the unfused pair")
+
+    def run(mod):
+        torch.manual_seed(5)                                    # the same drop-path draw
+        with torch.no_grad():
+            return mod(x)
+
+    o.train()
+    p.train()
+    yo = run(o)
+    c0 = L.CALL_COUNTS["cnx_mlp_fused_fwd_x3"]
+    yf = run(p)
+    assert L.CALL_COUNTS["cnx_mlp_fused_fwd_x3"] == c0 + 1
+    monkeypatch.setattr(ops, "FUSED_MLP_X3", False)
+    yu = run(p)
+    assert L.CALL_COUNTS["cnx_mlp_fused_fwd_x3"] == c0 + 1
+    assert yf.dtype == torch.float32
+    assert max_rel(yf, yu) <= 2e-6 and max_rel(yf, yo) <= 1e-4
+    if gamma_init is None or gamma_init >= 1e-2:          # with a 1e-6 layer scale the branch is below the ulp of x + branch
+        assert max_rel(yf - x, yu - x) <= 2e-5, max_rel(yf - x, yu - x)
+        assert max_rel(yf - x, yo - x) <= 1e-4, max_rel(yf - x, yo - x)
+    else:                                                 # ... so look at the branch through a unit layer scale instead
+        g0 = p.gamma.detach().clone()
+        with torch.no_grad():
+            p.gamma.fill_(1.0)
+        monkeypatch.setattr(ops, "FUSED_MLP_X3", True)
+        b1_ = run(p) - x
+        monkeypatch.setattr(ops, "FUSED_MLP_X3", False)
+        b0_ = run(p) - x
+        with torch.no_grad():
+            p.gamma.copy_(g0)
+        assert max_rel(b1_, b0_) <= 2e-5, max_rel(b1_, b0_)
