@@ -70,6 +70,17 @@ def test_config2_full_size_against_oracle(gamma):
         off += q.numel()
         cos = (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
         assert cos >= 0.98 or b.norm().item() < 1e-12, (n, cos)
+    # the accuracy forward the reference places outside autocast (engine.py:89-97): fp32, no grad, train mode, on the ORIGINAL
+    # batch — split-operand tensor-core GEMMs (fused fc1 -> GELU -> fc2 kernel at C = 96) against the oracle in fp32, fp32 bar
+    o.zero_grad(set_to_none=True)
+    p.zero_grad(set_to_none=True)
+    del res, go, gp
+    with torch.no_grad():
+        ao = o(x)
+        torch.cuda.synchronize()
+        ap = p(x)
+    assert ap.dtype == torch.float32 and max_rel(ap, ao) <= 1e-4, max_rel(ap, ao)
+    assert torch.equal(ap.argmax(1), ao.argmax(1)) or (ap.argmax(1) != ao.argmax(1)).float().mean().item() < 0.01
 
 
 CASES = [("fp32", False, 64, 8, 2, 0.0, 1.0, 0.0, 1), ("fp32_accum_cutmix", False, 64, 8, 5, 0.0, 1.0, 1.0, 2),
