@@ -1203,7 +1203,10 @@ template <int C> struct Fu3Cfg {
   static constexpr int NCH32 = C / 32;
   static constexpr int NFIN = NCH32 * 4;                    // warps of the final epilogue: one (lane quarter, 32-column chunk) each
   static constexpr int NBARS = 2 + 8 + 4 + 2 + 2 + 1;
-  static constexpr int SMEM = XN_BYTES + 2 * WST_BYTES + G_BYTES + 1024 + 8 * NBARS + 64;
+  // final epilogue: one 4 KB transposition slab per warp; the first G_BYTES / 4096 of them reuse the hidden buffer pair (idle
+  // between a tile's last GEMM2 and the next tile's first chunk), the rest get their own space
+  static constexpr int XSLAB_BYTES = (NFIN * 4096 > G_BYTES) ? NFIN * 4096 - G_BYTES : 0;
+  static constexpr int SMEM = XN_BYTES + 2 * WST_BYTES + G_BYTES + XSLAB_BYTES + 1024 + 8 * NBARS + 64;
   static constexpr int ACC2_COL = 128;
   static_assert(C % 32 == 0 && NFIN <= kFuEpiWarps && ACC2_COL + C <= 256, "fused x3 MLP tile shape");
   static_assert((C * 128) % 1024 == 0, "W2 pieces must stay 1024-byte aligned for the 128B swizzle");
@@ -1224,7 +1227,7 @@ mlp_fused_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_c
   const uint32_t sXn = base;
   const uint32_t sW = sXn + Cfg::XN_BYTES;
   const uint32_t sG = sW + 2 * Cfg::WST_BYTES;
-  const uint32_t bars = sG + Cfg::G_BYTES;
+  const uint32_t bars = sG + Cfg::G_BYTES + Cfg::XSLAB_BYTES;     // (the extra slabs follow the hidden buffer pair: one slab array)
   int bi = 0;
   auto nb = [&](int n) { const uint32_t a = bars + 8u * bi; bi += n; return a; };
   const uint32_t xn_full = nb(1), xn_empty = nb(1);
@@ -1434,27 +1437,51 @@ mlp_fused_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmXn, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_empty);
+        // A lane holds 32 columns of ONE row.  Reading the residual and writing the output from that layout touches 32
+        // different 128-byte lines per instruction (measured: 38 % of the kernel's time, profiles/r02z13_*).  The values are
+        // transposed through a 4 KB shared-memory slab instead: written row-per-lane (swizzled, conflict-free), read back so
+        // that one instruction covers 4 rows x 128 contiguous bytes, and the residual load / output store use that layout.
         const int64_t m = tile * BM + r;
-        if (m < M) {
-          const float sc = dp ? __ldg(dp + m / rows_per_sample) : 1.0f;
-          const int n0 = cg * 32;
-          const float4* res = reinterpret_cast<const float4*>(shortcut + m * C + n0);
-          float4* dst = reinterpret_cast<float4*>(out + m * C + n0);
+        const float sc = dp ? __ldg(dp + (m < M ? m : M - 1) / rows_per_sample) : 1.0f;
+        const int n0 = cg * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n0 + i));
-            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + n0 + i));
-            const float4 x4 = __ldg(res + i / 4);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n0 + i));
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + n0 + i));
+          v[i] = sc * (g4.x * (v[i] + b4.x));
+          v[i + 1] = sc * (g4.y * (v[i + 1] + b4.y));
+          v[i + 2] = sc * (g4.z * (v[i + 2] + b4.z));
+          v[i + 3] = sc * (g4.w * (v[i + 3] + b4.w));
+        }
+        const uint32_t slab = sG + (uint32_t)ew * 4096u;
+        const uint32_t rsw = (uint32_t)(lane & 7);
+#pragma unroll
+        for (int jv = 0; jv < 8; ++jv)
+          sts128(slab + (uint32_t)lane * 128u + (((uint32_t)jv ^ rsw) << 4), __float_as_uint(v[4 * jv]), __float_as_uint(v[4 * jv + 1]),
+                 __float_as_uint(v[4 * jv + 2]), __float_as_uint(v[4 * jv + 3]));
+        __syncwarp();
+        const int64_t row0 = tile * BM + quarter * 32;
+        const int c16 = lane & 7;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int rr = t * 4 + (lane >> 3);
+          uint32_t a0, a1, a2, a3;
+          lds128(slab + (uint32_t)rr * 128u + (((uint32_t)c16 ^ (uint32_t)(rr & 7)) << 4), a0, a1, a2, a3);
+          const int64_t mm = row0 + rr;
+          if (mm < M) {
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(shortcut + mm * C + n0 + c16 * 4));
             float4 o;
-            o.x = x4.x + sc * (g4.x * (v[i] + b4.x));
-            o.y = x4.y + sc * (g4.y * (v[i + 1] + b4.y));
-            o.z = x4.z + sc * (g4.z * (v[i + 2] + b4.z));
-            o.w = x4.w + sc * (g4.w * (v[i + 3] + b4.w));
-            dst[i / 4] = o;
+            o.x = x4.x + __uint_as_float(a0);
+            o.y = x4.y + __uint_as_float(a1);
+            o.z = x4.z + __uint_as_float(a2);
+            o.w = x4.w + __uint_as_float(a3);
+            *reinterpret_cast<float4*>(out + mm * C + n0 + c16 * 4) = o;
           }
         }
       }
+      // no warp may write the next tile's first hidden chunk while a slab in the hidden buffer pair is still being read
+      named_bar(1, kFuEpiWarps * 32);
     }
   }
   tc_fence_before();
