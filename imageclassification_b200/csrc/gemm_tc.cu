@@ -1627,7 +1627,15 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       tc_fence_after();
     }
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll
+    // A lane holds 32 columns of ONE accumulator row: stored from that layout every instruction touches 32 different lines of the
+    // partial buffer.  Each 32 x 32 chunk is transposed through a 4 KB slab of the (now idle) operand ring instead, so that one
+    // store instruction covers 4 rows x 128 contiguous bytes.
+    const uint32_t slab = sA + (uint32_t)(warp - kFirstEpiWarp) * 4096u;
+    static_assert(STAGES * Cfg::A_BYTES >= kEpiWarps * 4096, "the A ring must hold one slab per epilogue warp");
+    const int64_t row0 = it * 256 + rank * 128 + quarter * 32;
+    const uint32_t rsw = (uint32_t)(lane & 7);
+    const int c16 = lane & 7;
+#pragma unroll 1
     for (int c = 0; c < Cfg::EPI_COLS; c += 32) {
       const int col = half * Cfg::EPI_COLS + c;
       float v[32];
@@ -1638,12 +1646,21 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      const int64_t jj = jt * BN + col;
-      if (i < N1) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          if (jj + j < N2) store8(po + i * N2 + jj + j, *reinterpret_cast<float(*)[8]>(&v[j]));
+      for (int jv = 0; jv < 8; ++jv)
+        sts128(slab + (uint32_t)lane * 128u + (((uint32_t)jv ^ rsw) << 4), __float_as_uint(v[4 * jv]), __float_as_uint(v[4 * jv + 1]),
+               __float_as_uint(v[4 * jv + 2]), __float_as_uint(v[4 * jv + 3]));
+      __syncwarp();
+      const int64_t jj = jt * BN + col + c16 * 4;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rr = t * 4 + (lane >> 3);
+        uint32_t a0, a1, a2, a3;
+        lds128(slab + (uint32_t)rr * 128u + (((uint32_t)c16 ^ (uint32_t)(rr & 7)) << 4), a0, a1, a2, a3);
+        if (row0 + rr < N1 && jj < N2)
+          *reinterpret_cast<uint4*>(po + (row0 + rr) * N2 + jj) = make_uint4(a0, a1, a2, a3);
       }
+      __syncwarp();
     }
     if (do_colsum && half == 0) {
       float v[16];
