@@ -56,6 +56,18 @@ int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, i
   return gemm_tn_tc<EPI_BIAS_GELU3, bf16>(A3, W3, M, N, K3, ep, (cudaStream_t)stream);
 }
 
+int cnx_gemm_bias_gelu_fwd_x3_train(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3, void* g3,
+                                    float* gprime, int a_segments, void* stream) {
+  CNX_REQUIRE(A3 && W3 && b1 && g3 && gprime, CNX_E_BADARG, "gemm_bias_gelu_fwd_x3_train: null pointer");
+  CNX_REQUIRE(M > 0 && N > 0 && K3 > 0 && K3 % 24 == 0, CNX_E_BADARG, "gemm_bias_gelu_fwd_x3_train: bad shape (K3 = 3K, K %% 8 == 0)");
+  CNX_REQUIRE(N % 32 == 0, CNX_E_SHAPE, "gemm_bias_gelu_fwd_x3_train: N=%lld must be a multiple of 32", (long long)N);
+  CNX_REQUIRE(a_segments == 3 || (a_segments == 2 && (K3 / 3) % 32 == 0), CNX_E_SHAPE,
+              "gemm_bias_gelu_fwd_x3_train: a_segments must be 3, or 2 with K3/3 a multiple of 32 (K3=%lld)", (long long)K3);
+  EpiParams ep = {b1, nullptr, nullptr, 1, nullptr, gprime, g3, N};
+  if (a_segments == 2) ep.a_wrap = (int32_t)(2 * (K3 / 3));
+  return gemm_tn_tc<EPI_BIAS_GELU3, bf16>(A3, W3, M, N, K3, ep, (cudaStream_t)stream);
+}
+
 int cnx_gemm_bias_scale_residual_fwd(const void* A, const void* W2, const float* b2, const float* gamma,
                                      const float* dp, int64_t rows_per_sample, const void* shortcut, void* out,
                                      int stream_dtype, int64_t M, int64_t N, int64_t K, int dtype, int flags,

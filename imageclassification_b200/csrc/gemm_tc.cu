@@ -318,6 +318,23 @@ __device__ __forceinline__ float2 gelu_as2(float2 h) {
   return __fmul2_rn(h, phi);
 }
 
+// the same with the derivative: gp = GELU'(h) = Phi(h) + h * pdf(h), pdf(h) = exp(-h^2/2) / sqrt(2 pi) from the exponential already formed
+__device__ __forceinline__ float2 gelu_as2_grad(float2 h, float2& gp) {
+  const float2 d = __ffma2_rn(make_float2(fabsf(h.x), fabsf(h.y)), make_float2(0.23164190398f, 0.23164190398f), make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_fast(d.x), rcp_fast(d.y));
+  float2 p = __ffma2_rn(make_float2(0.5307027145f, 0.5307027145f), t, make_float2(-0.7265760135f, -0.7265760135f));
+  p = __ffma2_rn(p, t, make_float2(0.7107068705f, 0.7107068705f));
+  p = __ffma2_rn(p, t, make_float2(-0.142248368f, -0.142248368f));
+  p = __ffma2_rn(p, t, make_float2(0.127414796f, 0.127414796f));
+  p = __fmul2_rn(p, t);
+  const float2 a = __fmul2_rn(__fmul2_rn(h, h), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  const float2 e = make_float2(exp2f_fast(a.x), exp2f_fast(a.y));
+  const float2 q = __fmul2_rn(p, e);
+  const float2 phi = make_float2(h.x >= 0.f ? 1.0f - q.x : q.x, h.y >= 0.f ? 1.0f - q.y : q.y);
+  gp = __ffma2_rn(__fmul2_rn(h, make_float2(0.39894228040143267794f, 0.39894228040143267794f)), e, phi);
+  return __fmul2_rn(h, phi);
+}
+
 constexpr int kSlabBytes = 4096;                 // one epilogue slab: [32 rows][32 columns] of <= 4-byte elements
 template <int BN, int NCTA, bool SLAB, int NEPI = kEpiWarps, bool DUAL = false> struct TnCfg {
   static constexpr int THREADS = (kFirstEpiWarp + NEPI) * 32;
@@ -576,6 +593,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_expect_tx(in_bar(ew, buf ^ 1), 32 * ROWB);
             tma_load_2d(slab0 + (uint32_t)(buf ^ 1) * kSlabBytes, &tmIn, in_bar(ew, buf ^ 1), x, y);
           }
+        } else if (KIND == EPI_BIAS_GELU3 && ep.out0 != nullptr) {
+          bulk_wait_read0();                         // with the fp32 GELU' output a chunk uses BOTH slabs: all earlier stores done
         } else {
           bulk_wait_read1();                         // the store issued two chunks ago has finished reading this slab
         }
@@ -652,12 +671,25 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t pg[16], pd[16];
       const bool want_gp = (KIND == EPI_BIAS_GELU3) || ((KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr));
       if (KIND == EPI_BIAS_GELU3) {
-        // fp32 h, exact-erf GELU in fp32, g split into two bf16 pieces: g ~ hi + mid to 2^-17 relative
+        // fp32 h, exact-erf GELU in fp32, g split into two bf16 pieces: g ~ hi + mid to 2^-17 relative.  Training (ep.out0): the
+        // fp32 GELU'(h) leaves through the OTHER slab of this warp ([32 rows][128 B], fp32 swizzle) as it is formed
+        const bool gp3 = ep.out0 != nullptr;
+        const uint32_t oslab = slab0 + (uint32_t)(buf ^ 1) * kSlabBytes + (uint32_t)lane * 128u;
+        if (gp3) __syncwarp();                       // lane 0's wait above covers the whole warp before the first store
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + i));
-          const float2 ga = gelu_as2(__fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y)));
-          const float2 gb = gelu_as2(__fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w)));
+          float2 ga, gb;
+          if (gp3) {
+            float2 da, db;
+            ga = gelu_as2_grad(__fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y)), da);
+            gb = gelu_as2_grad(__fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w)), db);
+            sts128(oslab + ((((uint32_t)i >> 2) ^ (uint32_t)(lane & 7)) << 4), __float_as_uint(da.x), __float_as_uint(da.y),
+                   __float_as_uint(db.x), __float_as_uint(db.y));
+          } else {
+            ga = gelu_as2(__fadd2_rn(make_float2(v[i], v[i + 1]), make_float2(b4.x, b4.y)));
+            gb = gelu_as2(__fadd2_rn(make_float2(v[i + 2], v[i + 3]), make_float2(b4.z, b4.w)));
+          }
           const uint32_t ha = pack_bf16(ga.x, ga.y), hb = pack_bf16(gb.x, gb.y);
           pg[i / 2] = ha;
           pg[i / 2 + 1] = hb;
@@ -736,6 +768,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_store_2d(&tmOut, slab, x, y);
         if (KIND == EPI_BIAS_GELU3) {              // [hi | mid] column blocks of the [M, 2N] split operand
           tma_store_2d(&tmOut, slab + 2048u, x + (int32_t)N, y);
+          if (ep.out0 != nullptr) tma_store_2d(&tmIn, slab0 + (uint32_t)(buf ^ 1) * kSlabBytes, x, y);      // fp32 GELU'(h) [M, N]
         } else if (want_gp) {
           tma_store_2d(&tmIn, slab + 2048u, x, y);
         }
@@ -1793,8 +1826,11 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
     void* o = kGelu ? ep.out1 : ep.out0;
     const void* in = kGelu ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
     if (int rc = make_slab_map(&tmOut, o, M, (KIND == EPI_BIAS_GELU3) ? 2 * N : N, (int)sizeof(TOUT))) return rc;
-    if (KIND == EPI_BIAS_GELU3) tmIn = tmOut;
-    else if (KIND == EPI_DGELU_RC) {
+    if (KIND == EPI_BIAS_GELU3) {
+      tmIn = tmOut;
+      if (ep.out0 != nullptr)
+        if (int rc = make_slab_map(&tmIn, ep.out0, M, N, 4)) return rc;         // fp32 GELU'(h), training
+    } else if (KIND == EPI_DGELU_RC) {
       if (int rc = make_map(&tmIn, ep.a2, M, K, BM)) return rc;               // A2 = xn
     } else if (int rc = make_slab_map(&tmIn, in, M, N, (int)sizeof(TOUT))) return rc;
   } else {

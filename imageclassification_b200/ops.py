@@ -42,6 +42,7 @@ RECOMPUTE_MAX_C = int(os.environ.get("CNX_RECOMPUTE_C", "0"))
 # four backward GEMMs of the Block run as split-operand (x3) tcgen05 GEMMs, fp32-accurate to ~2^-16 per product, instead of the
 # CUDA-core fp32 GEMMs.  CNX_X3_TRAIN=0 selects the CUDA-core kernels for comparison.
 X3_TRAIN = os.environ.get("CNX_X3_TRAIN", "1") != "0"
+X3_TRAIN_FUSED = os.environ.get("CNX_X3_TRAIN_FUSED", "1") != "0"   # fp32 training: GELU, split and GELU'(h) in the fc1 epilogue
 # Backward hand-off between consecutive Blocks (bf16 activations): the dwconv backward-data kernel of Block i writes, beside
 # dx, the bf16 operand copy dz = bf16(dp * dx) that Block i-1's backward would make of it with cnx_grad_prep.  Forward notes
 # which Block produced a Block's input (`_LAST_OUT`); backward leaves the copy in `_DZ_HANDOFF` together with the dx tensor
@@ -393,10 +394,15 @@ class _BlockFn(torch.autograd.Function):
             L.check(lib.cnx_dwconv7_ln_fwd_x3(L.ptr(xl), L.ptr(wt), L.ptr(conv_b), L.ptr(ln_w), L.ptr(ln_b), eps, N, H, W, C,
                                               L.ptr(y), L.ptr(a2), L.ptr(mean), L.ptr(rstd), 2, st), "dwconv7_ln_fwd_x3")
             h = torch.empty((M, C4), dtype=torch.float32, device=dev)
-            L.check(lib.cnx_gemm_plain(L.ptr(a2), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), L.ptr(h), L.dt(torch.float32), M, C4,
-                                       3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st), "gemm_plain(x3 fc1)")
             g2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)
-            L.check(lib.cnx_gelu_split(L.ptr(h), M, C4, L.ptr(g2), st), "gelu_split")         # h now holds GELU'(h)
+            if X3_TRAIN_FUSED and C4 % 32 == 0:
+                # fc1 + bias + erf GELU + hi / mid split + GELU'(h) from ONE epilogue: no fp32 pre-activation round trip
+                L.check(lib.cnx_gemm_bias_gelu_fwd_x3_train(L.ptr(a2), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), M, C4, 3 * C,
+                                                            L.ptr(g2), L.ptr(h), 2, st), "gemm_bias_gelu_fwd_x3_train")
+            else:
+                L.check(lib.cnx_gemm_plain(L.ptr(a2), L.ptr(_weight_prep(w1, 3, None, bf)), L.ptr(b1), L.ptr(h), L.dt(torch.float32), M,
+                                           C4, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st), "gemm_plain(x3 fc1)")
+                L.check(lib.cnx_gelu_split(L.ptr(h), M, C4, L.ptr(g2), st), "gelu_split")     # h now holds GELU'(h)
             out = torch.empty((N, H, W, C), dtype=xl.dtype, device=dev)
             L.check(lib.cnx_gemm_bias_scale_residual_fwd(L.ptr(g2), L.ptr(_weight_prep(w2, 3, None, bf)), L.ptr(b2), L.ptr(gamma),
                                                          L.ptr(dp), H * W, L.ptr(xl), L.ptr(out), sd, M, C, 3 * C4, L.dt(bf),

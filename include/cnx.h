@@ -229,6 +229,11 @@ CNX_API int cnx_dwconv7_ln_fwd_x3(const float* x, const float* wt, const float* 
 /* a_segments = 3: A3 is [M, K3]; a_segments = 2: A3 is [M, 2*K3/3] = [hi | mid] and the K loop wraps (K3/3 a multiple of 32). */
 CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
                               void* g3, int a_segments, void* stream);
+/* The same for fp32 TRAINING on the tensor cores: additionally writes gprime [M,N] fp32 = GELU_erf'(acc + b1) (what backward needs
+ * of the pre-activation) from the same epilogue — replaces cnx_gemm_plain (fp32 h) + cnx_gelu_split, i.e. one write and one read
+ * of an fp32 [M,4C] tensor per Block (convnext.py:48-49 under engine.py:52 without autocast). */
+CNX_API int cnx_gemm_bias_gelu_fwd_x3_train(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
+                                    void* g3, float* gprime, int a_segments, void* stream);
 
 /* fp32 TRAINING on the tensor cores (the reference's default --use_amp false): the same split-operand scheme for the training
  * forward and the four backward GEMMs.  Elementwise pieces between the GEMMs:
