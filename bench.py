@@ -213,6 +213,9 @@ def kernel_work(name, a):
     if name == "cnx_gemm_bias_gelu_fwd_x3_train":     # the same + the fp32 GELU'(h) tensor written by the epilogue
         M, N, K3 = a[3:6]
         return (M * (K3 // 3) * a[8] + N * K3 + M * 2 * N) * 2 + M * N * 4, 2 * M * N * (K3 // 3), f"fc1_gelu_x3_train K{K3 // 3}"
+    if name == "cnx_gemm_dgrad_gelu_bwd_x3":          # dz pieces + split weights in, fp32 GELU' in, [hi | mid] of dh out
+        M, N, K3 = a[4:7]
+        return (M * (K3 // 3) * a[7] + N * K3 + M * 2 * N) * 2 + M * N * 4, 2 * M * N * (K3 // 3), f"dgrad_fc2_gelu_x3 K{K3 // 3}"
     if name == "cnx_dwconv7_ln_fwd_x3":
         N, H, W, C = a[6:10]
         MC = N * H * W * C

@@ -14,8 +14,10 @@ enum {
   EPI_DGELU = 3,        // out0 = acc * gp[m,n]                                 [act dtype], aux = gp = GELU'(h) saved by BIAS_GELU
   EPI_BIAS_GELU3 = 4,   // fp32-accurate forward: g = GELU_erf(acc + b1) in fp32 -> out1 bf16 [M, 2N] = [hi(g) | mid(g)]
                         // (split operand of the next GEMM, read with a_wrap = 2N; tcgen05 slab epilogue only)
-  EPI_DGELU_RC = 5      // out0 = acc * GELU'(round(acc2 + b1)), acc2 = A2.B2^T RECOMPUTED in the same kernel (A2 = xn, B2 = W1): the
+  EPI_DGELU_RC = 5,     // out0 = acc * GELU'(round(acc2 + b1)), acc2 = A2.B2^T RECOMPUTED in the same kernel (A2 = xn, B2 = W1): the
                         // forward then stores g only, not GELU'(h) (tcgen05 CTA-pair slab kernel only; HBM-bound stages)
+  EPI_DGELU3 = 6        // fp32 training: dh = acc * gp[m,n] with gp = GELU'(h) in FP32 (aux) -> out0 bf16 [M, 2N] = [hi(dh) | mid(dh)]
+                        // (split operand of the two GEMMs that consume dh; tcgen05 slab epilogue only)
 };
 
 struct EpiParams {

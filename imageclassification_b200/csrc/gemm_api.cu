@@ -136,6 +136,18 @@ int cnx_gemm_dgrad_gelu_recompute_bwd(const void* dz, const void* Bt, const void
   return gemm_dgelu_recompute_tc(dz, Bt, M, N, K, ep, (cudaStream_t)stream);
 }
 
+int cnx_gemm_dgrad_gelu_bwd_x3(const void* dz2, const void* Bt3, const float* gprime, void* dh2, int64_t M, int64_t N, int64_t K3,
+                               int a_segments, void* stream) {
+  CNX_REQUIRE(dz2 && Bt3 && gprime && dh2, CNX_E_BADARG, "gemm_dgrad_gelu_bwd_x3: null pointer");
+  CNX_REQUIRE(M > 0 && N > 0 && K3 > 0 && K3 % 24 == 0, CNX_E_BADARG, "gemm_dgrad_gelu_bwd_x3: bad shape (K3 = 3K, K %% 8 == 0)");
+  CNX_REQUIRE(N % 32 == 0, CNX_E_SHAPE, "gemm_dgrad_gelu_bwd_x3: N=%lld must be a multiple of 32", (long long)N);
+  CNX_REQUIRE(a_segments == 3 || (a_segments == 2 && (K3 / 3) % 32 == 0), CNX_E_SHAPE,
+              "gemm_dgrad_gelu_bwd_x3: a_segments must be 3, or 2 with K3/3 a multiple of 32 (K3=%lld)", (long long)K3);
+  EpiParams ep = {nullptr, nullptr, nullptr, 1, gprime, dh2, nullptr, N};
+  if (a_segments == 2) ep.a_wrap = (int32_t)(2 * (K3 / 3));
+  return gemm_tn_tc<EPI_DGELU3, bf16>(dz2, Bt3, M, N, K3, ep, (cudaStream_t)stream);
+}
+
 int cnx_gemm_plain(const void* A, const void* B, const float* bias, void* out, int out_dtype, int64_t M,
                    int64_t N, int64_t K, int dtype, int flags, void* stream) {
   CNX_REQUIRE(A && B && out, CNX_E_BADARG, "gemm_plain: null pointer");

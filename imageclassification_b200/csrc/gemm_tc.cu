@@ -389,7 +389,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   auto in_bar = [&](int w, int b) { return bars + 8u * (2 * STAGES + 5 + 2 * w + b); };   // slab-input barriers, per warp
-  constexpr bool HAS_IN = SLAB && (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
+  constexpr bool HAS_IN = SLAB && (KIND == EPI_SCALE_RES || KIND == EPI_DGELU || KIND == EPI_DGELU3);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;       // 0 = the pair's leader (issues the MMAs)
@@ -559,6 +559,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t row_off = (uint32_t)lane * ROWB;
     const uint32_t swz = (sizeof(TOUT) == 4) ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
     constexpr int NV = (int)ROWB / 16;                                 // 16-byte vectors per slab row
+    constexpr uint32_t IN_BYTES = (KIND == EPI_DGELU3) ? 4096u : 32u * ROWB;   // EPI_DGELU3: the input slab is fp32 [32][32]
     int as = 0; uint32_t aph = 0;
     int buf = 0; uint32_t inph[2] = {0u, 0u};
     int64_t t_cur = first_tile; int c_cur = half;
@@ -577,7 +578,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (HAS_IN && lane == 0 && t_cur < num_tiles) {
       int32_t x, y;
       chunk_coords(t_cur, c_cur, x, y);
-      mbar_expect_tx(in_bar(ew, 0), 32 * ROWB);
+      mbar_expect_tx(in_bar(ew, 0), IN_BYTES);
       tma_load_2d(slab0, &tmIn, in_bar(ew, 0), x, y);
     }
     while (t_cur < num_tiles) {
@@ -590,7 +591,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (t_nxt < num_tiles) {
             int32_t x, y;
             chunk_coords(t_nxt, c_nxt, x, y);
-            mbar_expect_tx(in_bar(ew, buf ^ 1), 32 * ROWB);
+            mbar_expect_tx(in_bar(ew, buf ^ 1), IN_BYTES);
             tma_load_2d(slab0 + (uint32_t)(buf ^ 1) * kSlabBytes, &tmIn, in_bar(ew, buf ^ 1), x, y);
           }
         } else if (KIND == EPI_BIAS_GELU3 && ep.out0 != nullptr) {
@@ -669,7 +670,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       uint32_t pg[16], pd[16];
-      const bool want_gp = (KIND == EPI_BIAS_GELU3) || ((KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr));
+      const bool want_gp = (KIND == EPI_BIAS_GELU3) || (KIND == EPI_DGELU3) || ((KIND == EPI_BIAS_GELU) && (ep.out0 != nullptr));
       if (KIND == EPI_BIAS_GELU3) {
         // fp32 h, exact-erf GELU in fp32, g split into two bf16 pieces: g ~ hi + mid to 2^-17 relative.  Training (ep.out0): the
         // fp32 GELU'(h) leaves through the OTHER slab of this warp ([32 rows][128 B], fp32 swizzle) as it is formed
@@ -721,7 +722,26 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           pg[i / 2 + 1] = pack_bf16(gb.x, gb.y);
         }
       }
-      if (HAS_IN) {
+      if constexpr (KIND == EPI_DGELU3) {
+        // fp32 GELU'(h) slab ([32 rows][128 B], fp32 swizzle) -> dh = acc * gp in fp32 -> two bf16 pieces
+        mbar_wait(in_bar(ew, buf), inph[buf]);
+        inph[buf] ^= 1;
+        const uint32_t irow = slab + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t a0, a1, a2, a3;
+          lds128(irow + (((uint32_t)j ^ (uint32_t)(lane & 7)) << 4), a0, a1, a2, a3);
+          const float2 da = __fmul2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(__uint_as_float(a0), __uint_as_float(a1)));
+          const float2 db = __fmul2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(__uint_as_float(a2), __uint_as_float(a3)));
+          const uint32_t ha = pack_bf16(da.x, da.y), hb = pack_bf16(db.x, db.y);
+          pg[2 * j] = ha;
+          pg[2 * j + 1] = hb;
+          const float2 ra = __fadd2_rn(da, make_float2(-bf16_lo(ha), -bf16_hi(ha)));
+          const float2 rb = __fadd2_rn(db, make_float2(-bf16_lo(hb), -bf16_hi(hb)));
+          pd[2 * j] = pack_bf16(ra.x, ra.y);
+          pd[2 * j + 1] = pack_bf16(rb.x, rb.y);
+        }
+      } else if (HAS_IN) {
         mbar_wait(in_bar(ew, buf), inph[buf]);
         inph[buf] ^= 1;
 #pragma unroll
@@ -750,7 +770,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const uint32_t addr = slab + row_off + (((uint32_t)j ^ swz) << 4);
-        if (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3) {   // two bf16 outputs share the slab: g (hi) in the first 2 KB, GELU' (mid) in the second
+        if (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3 || KIND == EPI_DGELU3) {   // two bf16 outputs share the slab: g (hi) in the first 2 KB, GELU' (mid) in the second
           sts128(addr, pg[4 * j], pg[4 * j + 1], pg[4 * j + 2], pg[4 * j + 3]);
           if (want_gp) sts128(addr + 2048u, pd[4 * j], pd[4 * j + 1], pd[4 * j + 2], pd[4 * j + 3]);
         } else if (sizeof(TOUT) == 4)
@@ -766,7 +786,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int32_t x, y;
         chunk_coords(t_cur, c_cur, x, y);
         tma_store_2d(&tmOut, slab, x, y);
-        if (KIND == EPI_BIAS_GELU3) {              // [hi | mid] column blocks of the [M, 2N] split operand
+        if (KIND == EPI_DGELU3) {                  // [hi | mid] column blocks of the [M, 2N] split operand
+          tma_store_2d(&tmOut, slab + 2048u, x + (int32_t)N, y);
+        } else if (KIND == EPI_BIAS_GELU3) {
           tma_store_2d(&tmOut, slab + 2048u, x + (int32_t)N, y);
           if (ep.out0 != nullptr) tma_store_2d(&tmIn, slab0 + (uint32_t)(buf ^ 1) * kSlabBytes, x, y);      // fp32 GELU'(h) [M, N]
         } else if (want_gp) {
@@ -1825,8 +1847,10 @@ static int launch_tn_impl(const void* A, const void* B, int64_t M, int64_t N, in
     constexpr bool kGelu = (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3);
     void* o = kGelu ? ep.out1 : ep.out0;
     const void* in = kGelu ? (ep.out0 ? ep.out0 : ep.out1) : (ep.aux ? ep.aux : ep.out0);
-    if (int rc = make_slab_map(&tmOut, o, M, (KIND == EPI_BIAS_GELU3) ? 2 * N : N, (int)sizeof(TOUT))) return rc;
-    if (KIND == EPI_BIAS_GELU3) {
+    if (int rc = make_slab_map(&tmOut, o, M, (KIND == EPI_BIAS_GELU3 || KIND == EPI_DGELU3) ? 2 * N : N, (int)sizeof(TOUT))) return rc;
+    if (KIND == EPI_DGELU3) {
+      if (int rc = make_slab_map(&tmIn, ep.aux, M, N, 4)) return rc;            // fp32 GELU'(h)
+    } else if (KIND == EPI_BIAS_GELU3) {
       tmIn = tmOut;
       if (ep.out0 != nullptr)
         if (int rc = make_slab_map(&tmIn, ep.out0, M, N, 4)) return rc;         // fp32 GELU'(h), training
@@ -1884,9 +1908,9 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
   constexpr bool kGelu = (KIND == EPI_BIAS_GELU || KIND == EPI_BIAS_GELU3);
   constexpr bool kSlabKind = (BN % 32 == 0) && (!kGelu || sizeof(TOUT) == 2);
   if constexpr (kSlabKind) {
-    const bool need_in = (KIND == EPI_SCALE_RES || KIND == EPI_DGELU);
+    const bool need_in = (KIND == EPI_SCALE_RES || KIND == EPI_DGELU || KIND == EPI_DGELU3);
     const void* o = kGelu ? ep.out1 : ep.out0;
-    if ((slab_enabled() || KIND == EPI_BIAS_GELU3) && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
+    if ((slab_enabled() || KIND == EPI_BIAS_GELU3 || KIND == EPI_DGELU3) && N % 32 == 0 && (!need_in || ep.aux != nullptr) && o != nullptr) {
       // the GELU epilogue is issue-bound: 16 epilogue warps (4 per scheduler) where the tile has >= 4 column chunks
       if constexpr (kGelu && BN >= 128) {
         // 16 warps' slabs (128 KB) leave a 3-stage operand ring.  The split-output fc1 with K' >= 576 (C >= 192) is tensor-
@@ -1900,8 +1924,8 @@ static int launch_tn(const void* A, const void* B, int64_t M, int64_t N, int64_t
       } else return launch_tn_impl<BN, KIND, TOUT, NCTA, true>(A, B, M, N, K, ep, s);
     }
   }
-  if constexpr (KIND == EPI_BIAS_GELU3) {
-    set_error("gemm_bias_gelu_fwd_x3: N=%lld must be a multiple of 32", (long long)N);
+  if constexpr (KIND == EPI_BIAS_GELU3 || KIND == EPI_DGELU3) {
+    set_error("split-output GEMM (x3): N=%lld must be a multiple of 32 and the output / GELU' pointers non-null", (long long)N);
     return CNX_E_SHAPE;
   } else {
     return launch_tn_impl<BN, KIND, TOUT, NCTA, false>(A, B, M, N, K, ep, s);
@@ -2013,6 +2037,7 @@ CNX_INST(EPI_SCALE_RES, float)
 CNX_INST(EPI_SCALE_RES, bf16)
 CNX_INST(EPI_DGELU, bf16)
 CNX_INST(EPI_BIAS_GELU3, bf16)
+CNX_INST(EPI_DGELU3, bf16)
 #undef CNX_INST
 
 static bool wgrad384_enabled() {               // CNX_WGRAD_BN384=0: 256 x 256 pair tiles only (A/B measurements)

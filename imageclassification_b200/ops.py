@@ -306,12 +306,17 @@ def _mlp_backward_x3(lib, params, doutl, a2, gp, g2, w1, w2, b2, gamma, dp, M, C
     L.check(lib.cnx_split3(L.ptr(dz32), M, C, L.ptr(dz2), 2, st), "split3")
     # 2. dh = (dz . (gamma*W2)) * GELU'(h), leaving as a split operand
     w2gt3 = _split_of((w2, gamma), ("w2gt_x3",), lambda: _weight_prep(w2, 2, gamma, f32), C4, C)            # [4C, 3C]
-    t1 = torch.empty((M, C4), dtype=f32, device=dev)
-    L.check(lib.cnx_gemm_plain(L.ptr(dz2), L.ptr(w2gt3), None, L.ptr(t1), L.dt(f32), M, C4, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st),
-            "gemm_plain(x3 dgrad fc2)")
     dh2 = torch.empty((M, 2 * C4), dtype=bf, device=dev)
-    L.check(lib.cnx_mul_split(L.ptr(t1), L.ptr(gp), M, C4, L.ptr(dh2), st), "mul_split")
-    del t1
+    if X3_TRAIN_FUSED and C4 % 32 == 0:
+        # the multiply by GELU'(h) and the hi / mid split happen in the GEMM's epilogue: no fp32 [M, 4C] product round trip
+        L.check(lib.cnx_gemm_dgrad_gelu_bwd_x3(L.ptr(dz2), L.ptr(w2gt3), L.ptr(gp), L.ptr(dh2), M, C4, 3 * C, 2, st),
+                "gemm_dgrad_gelu_bwd_x3")
+    else:
+        t1 = torch.empty((M, C4), dtype=f32, device=dev)
+        L.check(lib.cnx_gemm_plain(L.ptr(dz2), L.ptr(w2gt3), None, L.ptr(t1), L.dt(f32), M, C4, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st),
+                "gemm_plain(x3 dgrad fc2)")
+        L.check(lib.cnx_mul_split(L.ptr(t1), L.ptr(gp), M, C4, L.ptr(dh2), st), "mul_split")
+        del t1
     # 3. fc2 wgrad on the unscaled gradient + layer-scale identities
     ws_bytes = max(lib.cnx_gemm_wgrad_workspace_bytes(M, C, C4, L.CNX_BF16, 0), lib.cnx_gemm_wgrad_workspace_bytes(M, C4, C, L.CNX_BF16, 0))
     ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)

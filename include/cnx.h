@@ -234,6 +234,11 @@ CNX_API int cnx_gemm_bias_gelu_fwd_x3(const void* A3, const void* W3, const floa
  * of an fp32 [M,4C] tensor per Block (convnext.py:48-49 under engine.py:52 without autocast). */
 CNX_API int cnx_gemm_bias_gelu_fwd_x3_train(const void* A3, const void* W3, const float* b1, int64_t M, int64_t N, int64_t K3,
                                     void* g3, float* gprime, int a_segments, void* stream);
+/* fp32 training, data gradient of fc2 with the GELU derivative, leaving as a split operand:
+ *   dh2 [M,2N] bf16 = [hi | mid] of (dz . Bt^T)[m,n] * gprime[m,n]      (dz2 [M,2K] or [M,3K] split, Bt3 [N,3K] = [hi|hi|mid],
+ * gprime fp32 [M,N] as written by cnx_gemm_bias_gelu_fwd_x3_train) — replaces cnx_gemm_plain (fp32 product) + cnx_mul_split. */
+CNX_API int cnx_gemm_dgrad_gelu_bwd_x3(const void* dz2, const void* Bt3, const float* gprime, void* dh2, int64_t M, int64_t N,
+                               int64_t K3, int a_segments, void* stream);
 
 /* fp32 TRAINING on the tensor cores (the reference's default --use_amp false): the same split-operand scheme for the training
  * forward and the four backward GEMMs.  Elementwise pieces between the GEMMs:

@@ -1,4 +1,4 @@
-# round 2, session z17: fp32 training with GELU / split / GELU'(h) fused into the fc1 epilogue: parity + fp32 bench on / off
+# round 2, session z17: fp32 training with GELU, split, GELU'(h) fused into the fc1 epilogue and the GELU' multiply + split into the fc2 data-gradient epilogue: parity + fp32 bench on / off
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests/test_block_gpu.py tests/test_engine_gpu.py tests/test_gemm_gpu.py tests/test_parity_round2_gpu.py tests/test_ddp_nccl_gpu.py -m gpu -x -q > gpurun_out/r02z17_pytest.log 2>&1; echo "pytest rc=$?"; tail -n 4 gpurun_out/r02z17_pytest.log
 for v in 1 0; do
