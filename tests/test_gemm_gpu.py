@@ -223,3 +223,53 @@ def test_dgrad_gelu_recompute_matches_saved_gelu_prime(M, C):
     gpd = 0.5 * (1 + torch.erf(h / math.sqrt(2))) + h * torch.exp(-0.5 * h * h) / math.sqrt(2 * math.pi)
     exact = (dz.double() @ Bt.double().t()) * gpd
     assert max_rel(dh.double(), exact) <= 2e-2
+
+
+@pytest.mark.parametrize("M,C", [(3136, 96), (777, 128), (1000, 384), (130, 768), (50176, 96)])
+def test_x3_training_epilogues_fc1_gelu_prime_and_dgelu_split(M, C):
+    """fp32 training on split operands: cnx_gemm_bias_gelu_fwd_x3_train (g as [hi | mid] AND fp32 GELU'(h) from one epilogue) and
+    cnx_gemm_dgrad_gelu_bwd_x3 ((dz . W2s) * GELU'(h) leaving as [hi | mid]) against float64 on the same fp32 inputs, and against
+    the separate-pass kernels they replace (cnx_gemm_plain + cnx_gelu_split / cnx_mul_split)."""
+    from imageclassification_b200 import _lib as L
+    lib = L.load()
+    A, W1, b1, W2, b2, gamma = _mk(M, C, torch.float32, 7 * M + C)
+    bf, f32 = torch.bfloat16, torch.float32
+    st = L.stream()
+    N = 4 * C
+    a2 = torch.empty(M, 2 * C, dtype=bf, device=DEV)
+    w13 = torch.empty(N, 3 * C, dtype=bf, device=DEV)
+    L.check(lib.cnx_split3(L.ptr(A), M, C, L.ptr(a2), 2, st))
+    L.check(lib.cnx_weight_prep(L.ptr(W1), N, C, None, 3, L.ptr(w13), L.dt(bf), st))
+    g2 = torch.empty(M, 2 * N, dtype=bf, device=DEV)
+    gp = torch.empty(M, N, dtype=f32, device=DEV)
+    L.check(lib.cnx_gemm_bias_gelu_fwd_x3_train(L.ptr(a2), L.ptr(w13), L.ptr(b1), M, N, 3 * C, L.ptr(g2), L.ptr(gp), 2, st))
+    hd = (A.double() @ W1.double().t() + b1.double()).requires_grad_(True)
+    gd = F.gelu(hd)
+    gd.sum().backward()
+    assert max_rel(g2[:, :N].double() + g2[:, N:].double(), gd.detach()) <= 2e-5
+    assert max_rel(gp.double(), hd.grad) <= 4e-5          # the 1e-5 of the x3 pre-activation times max |GELU''| ~ 1.1 (19 M values)
+    # the two-kernel path it replaces: same g pieces up to the erf implementation (A-S 7.1.26 vs erff), same GELU' to 1e-6
+    h = torch.empty(M, N, dtype=f32, device=DEV)
+    g2b = torch.empty_like(g2)
+    L.check(lib.cnx_gemm_plain(L.ptr(a2), L.ptr(w13), L.ptr(b1), L.ptr(h), L.dt(f32), M, N, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st))
+    L.check(lib.cnx_gelu_split(L.ptr(h), M, N, L.ptr(g2b), st))
+    assert max_rel(gp, h) <= 2e-6
+    # (the pieces carry g to 2^-17: two g's that differ in the last fp32 bits can round their mid pieces differently)
+    assert max_rel(g2[:, :N].float() + g2[:, N:].float(), g2b[:, :N].float() + g2b[:, N:].float()) <= 2e-5
+    # backward: dh = (dz . (gamma W2)) * GELU'(h), split
+    g = torch.Generator(device=DEV).manual_seed(M)
+    dz = torch.randn(M, C, device=DEV, generator=g)
+    dz2 = torch.empty(M, 2 * C, dtype=bf, device=DEV)
+    L.check(lib.cnx_split3(L.ptr(dz), M, C, L.ptr(dz2), 2, st))
+    w2s = (W2 * gamma[:, None]).t().contiguous()                     # [4C, C]
+    w2s3 = torch.empty(N, 3 * C, dtype=bf, device=DEV)
+    L.check(lib.cnx_weight_prep(L.ptr(w2s), N, C, None, 3, L.ptr(w2s3), L.dt(bf), st))
+    dh2 = torch.empty(M, 2 * N, dtype=bf, device=DEV)
+    L.check(lib.cnx_gemm_dgrad_gelu_bwd_x3(L.ptr(dz2), L.ptr(w2s3), L.ptr(gp), L.ptr(dh2), M, N, 3 * C, 2, st))
+    ref = (dz.double() @ w2s.double().t()) * gp.double()
+    assert max_rel(dh2[:, :N].double() + dh2[:, N:].double(), ref) <= 2e-5
+    t1 = torch.empty(M, N, dtype=f32, device=DEV)
+    dh2b = torch.empty_like(dh2)
+    L.check(lib.cnx_gemm_plain(L.ptr(dz2), L.ptr(w2s3), None, L.ptr(t1), L.dt(f32), M, N, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st))
+    L.check(lib.cnx_mul_split(L.ptr(t1), L.ptr(gp), M, N, L.ptr(dh2b), st))
+    assert torch.equal(dh2, dh2b)                                    # same MMAs, same fp32 multiply, same split
