@@ -259,7 +259,7 @@ def kernel_work(name, a):
         M, N1, N2 = a[2:5]
         e = es(a[10])
         return M * (N1 + N2) * e + N1 * N2 * 4, 2 * M * N1 * N2, f"wgrad {N1}x{N2}"
-    if name == "cnx_gemm_wgrad_x3":
+    if name in ("cnx_gemm_wgrad_x3", "cnx_gemm_wgrad_x3_one_loop"):
         M, N1, N2 = a[2:5]
         return 3 * M * (N1 + N2) * 2 + N1 * N2 * 4, 2 * M * N1 * N2, f"wgrad_x3 {N1}x{N2}"
     if name in ("cnx_gelu_split", "cnx_mul_split"):

@@ -73,6 +73,7 @@ SIGNATURES = {
     "cnx_gelu_split": (c_int, [_P, _L, _L, _P, _P]),
     "cnx_mul_split": (c_int, [_P, _P, _L, _L, _P, _P]),
     "cnx_gemm_wgrad_x3": (c_int, [_P, _P, _L, _L, _L, _I, _P, _P, _P, _L, _P]),
+    "cnx_gemm_wgrad_x3_one_loop": (c_int, [_P, _P, _L, _L, _L, _I, _P, _P, _P, _L, _P]),
     "cnx_mlp_fused_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _L, _P]),
     "cnx_mlp_fused_fwd_x3": (c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L, _L, _P]),
     "cnx_gemm_dgrad_gelu_bwd": (c_int, [_P, _P, _P, _P, _L, _L, _L, _I, _I, _P]),
@@ -100,7 +101,7 @@ KERNELS_PER_CALL = {
     "cnx_ema_lerp_multi": 1, "cnx_adamw_ema_multi": 1, "cnx_grad_sumsq_multi": 2, "cnx_scale_multi": 1, "cnx_soft_target_ce_fwd": 1, "cnx_soft_target_ce_bwd": 1,
     "cnx_mixup_target": 1, "cnx_mixup_batch": 1, "cnx_dwconv7_ln_fwd": 1, "cnx_ln_fwd": 1, "cnx_ln_bwd": 1, "cnx_reduce_partials": 1, "cnx_reduce_partials_split": 1,
     "cnx_dwconv7_dgrad": 1, "cnx_dwconv7_dgrad_dz": 1, "cnx_dwconv7_wgrad": 1, "cnx_dwconv7_wgrad_finalize": 1, "cnx_dwconv7_weight_prep": 1, "cnx_gemm_bias_gelu_fwd": 1,
-    "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_dgrad_gelu_recompute_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2, "cnx_gemm_wgrad_x3": 6, "cnx_gelu_split": 1, "cnx_mul_split": 1,
+    "cnx_gemm_bias_scale_residual_fwd": 1, "cnx_gemm_dgrad_gelu_bwd": 1, "cnx_gemm_dgrad_gelu_recompute_bwd": 1, "cnx_gemm_plain": 1, "cnx_gemm_wgrad": 2, "cnx_gemm_wgrad_x3": 6, "cnx_gemm_wgrad_x3_one_loop": 2, "cnx_gelu_split": 1, "cnx_mul_split": 1,
     "cnx_grad_prep": 1, "cnx_weight_prep": 1, "cnx_weight_prep_multi": 1, "cnx_mlp_fused_fwd": 1, "cnx_mlp_fused_fwd_x3": 1, "cnx_split3": 1, "cnx_dwconv7_ln_fwd_x3": 1, "cnx_gemm_bias_gelu_fwd_x3": 1, "cnx_gemm_bias_gelu_fwd_x3_train": 1, "cnx_gemm_dgrad_gelu_bwd_x3": 1, "cnx_layerscale_finalize": 1, "cnx_cast_f32_to_bf16": 1,
     "cnx_avgpool_nhwc_fwd": 1, "cnx_avgpool_nhwc_bwd": 1, "cnx_patchify4_nchw": 1, "cnx_patch2": 1, "cnx_ln_fwd_patch2": 1, "cnx_ln_bwd_patch2": 1,
 }

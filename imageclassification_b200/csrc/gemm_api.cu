@@ -12,7 +12,8 @@ template <typename TIN>
 int gemm_wgrad_simt(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                     float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
-                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx = 0, int64_t ldy = 0);
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx = 0, int64_t ldy = 0,
+                  int passes = 1);
 int mlp_fused_fwd_x3_tc(const void* xn2, const void* W1x3, const float* b1, const void* W2x3, const float* b2, const float* gamma,
                         const float* dp, int64_t rows_per_sample, const float* shortcut, float* out, int64_t M, int64_t C,
                         cudaStream_t s);
@@ -197,6 +198,16 @@ int cnx_gemm_wgrad(const void* X, const void* Y, int64_t M, int64_t N1, int64_t 
 /* fp32-accurate weight gradient on the tensor cores: X2 [M, 2*N1] = [hi | mid] and Y2 [M, 2*N2] = [hi | mid] (cnx_split3 with
  * segments = 2, or the split outputs of the x3 kernels); out = Xhi^T.Yhi + Xmid^T.Yhi + Xhi^T.Ymid (three bf16 wgrad GEMMs over
  * column blocks of the split tensors, accumulated in fp32), colsum_x = column sums of Xhi + Xmid. */
+int cnx_gemm_wgrad_x3_one_loop(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
+                               float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream) {
+  CNX_REQUIRE(X2 && Y2 && out && workspace, CNX_E_BADARG, "gemm_wgrad_x3_one_loop: null pointer");
+  CNX_REQUIRE(M > 0 && N1 > 0 && N2 > 0, CNX_E_BADARG, "gemm_wgrad_x3_one_loop: bad shape");
+  CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_x3_one_loop: N1, N2 must be multiples of 8");
+  // ONE launch whose K loop walks the three products: one set of split-K partials, one reduction — and accumulation chains in
+  // TMEM three times as long as cnx_gemm_wgrad_x3's (see include/cnx.h for what that costs in accuracy)
+  return gemm_wgrad_tc(X2, Y2, M, N1, N2, accumulate, out, colsum_x, workspace, workspace_bytes, (cudaStream_t)stream, 2 * N1, 2 * N2, 3);
+}
+
 int cnx_gemm_wgrad_x3(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                       float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream) {
   CNX_REQUIRE(X2 && Y2 && out && workspace, CNX_E_BADARG, "gemm_wgrad_x3: null pointer");

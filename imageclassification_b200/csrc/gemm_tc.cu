@@ -832,7 +832,7 @@ template <int BN> struct WgCfg {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, int64_t Mtot,
-                     int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part) {
+                     int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part, int passes) {
   typedef WgCfg<BN> Cfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -850,7 +850,11 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int64_t j_tiles = (N2 + BN - 1) / BN;
   const int64_t it = blockIdx.x / j_tiles, jt = blockIdx.x - it * j_tiles;
   const int split = blockIdx.y;
-  const int kb_total = (int)((Mtot + BK - 1) / BK);
+  // passes = 3: split operands X2 = [hi | mid] (2 N1 columns), Y2 = [hi | mid] (2 N2 columns): ONE K loop over the three products
+  // hi.hi, mid.hi, hi.mid (pass p reads X at column offset (p == 1) N1 and Y at (p == 2) N2) instead of three launches with
+  // three sets of split-K partials; the column sums of X come from passes 0 and 1 (hi + mid)
+  const int kb_rows = (int)((Mtot + BK - 1) / BK);
+  const int kb_total = passes * kb_rows;
   const int kb0 = split * kb_per_split;
   int kb1 = kb0 + kb_per_split;
   if (kb1 > kb_total) kb1 = kb_total;
@@ -884,13 +888,15 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int32_t mrow = (kb0 + kb) * BK;
+        const int g = kb0 + kb, pass = g / kb_rows;
+        const int32_t mrow = (g - pass * kb_rows) * BK;
+        const int32_t xo = (pass == 1) ? (int32_t)N1 : 0, yo = (pass == 2) ? (int32_t)N2 : 0;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
-        tma_load_2d(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), (int32_t)(it * BM), mrow);
-        tma_load_2d(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), (int32_t)(it * BM + 64), mrow);
-        tma_load_2d(sB + s * Cfg::B_BYTES, &tmY, full_bar(s), (int32_t)(jt * BN), mrow);
-        tma_load_2d(sB + s * Cfg::B_BYTES + 8192, &tmY, full_bar(s), (int32_t)(jt * BN + 64), mrow);
+        tma_load_2d(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), (int32_t)(it * BM) + xo, mrow);
+        tma_load_2d(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), (int32_t)(it * BM + 64) + xo, mrow);
+        tma_load_2d(sB + s * Cfg::B_BYTES, &tmY, full_bar(s), (int32_t)(jt * BN) + yo, mrow);
+        tma_load_2d(sB + s * Cfg::B_BYTES + 8192, &tmY, full_bar(s), (int32_t)(jt * BN + 64) + yo, mrow);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -901,6 +907,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       constexpr uint32_t idesc_ones = make_idesc(BM, 16, 1, 1);
       const uint64_t odesc = make_smem_desc(sOnes, 8192, 1024);
       int s = 0; uint32_t ph = 0;
+      uint32_t cs_acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -911,7 +918,10 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int k = 0; k < BK / 16; ++k) {
           // one UMMA_K = 16 rows = two 8-row groups = 2048 B further into the tile
           umma_f16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
-          if (do_colsum) umma_f16(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
+          if (do_colsum && (kb0 + kb) < 2 * kb_rows) {       // (passes = 1: always; passes = 3: the hi and mid passes of X)
+            umma_f16(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, cs_acc);
+            cs_acc = 1;
+          }
         }
         umma_commit(empty_bar(s));
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -950,7 +960,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     if (do_colsum && half == 0) {
       float v[16];
-      if (nkb > 0) {
+      if (nkb > 0 && kb0 < 2 * kb_rows) {              // this split issued at least one column-sum MMA
         tmem_ld16(t_row + Cfg::CS_COL, v);
         tmem_ld_wait();
       } else {
@@ -1575,7 +1585,7 @@ template <int BN> struct WgPairCfg {
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, int64_t Mtot,
-                       int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part) {
+                       int64_t N1, int64_t N2, int kb_per_split, float* __restrict__ part, float* __restrict__ cs_part, int passes) {
   typedef WgPairCfg<BN> Cfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -1595,7 +1605,8 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
   const int64_t tile = blockIdx.x >> 1;
   const int64_t it = tile / j_tiles, jt = tile - it * j_tiles;
   const int split = blockIdx.y;
-  const int kb_total = (int)((Mtot + BK - 1) / BK);
+  const int kb_rows = (int)((Mtot + BK - 1) / BK);     // passes = 3: one K loop over hi.hi, mid.hi, hi.mid (see gemm_wgrad_tc_kernel)
+  const int kb_total = passes * kb_rows;
   const int kb0 = split * kb_per_split;
   int kb1 = kb0 + kb_per_split;
   if (kb1 > kb_total) kb1 = kb_total;
@@ -1633,14 +1644,16 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       const int32_t b_ch = (int32_t)(jt * BN + rank * (BN == 384 ? 128 : BN / 2));
       const int32_t b_ch2 = (int32_t)(jt * BN + 256 + rank * 64);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int32_t mrow = (kb0 + kb) * BK;
+        const int g = kb0 + kb, pass = g / kb_rows;
+        const int32_t mrow = (g - pass * kb_rows) * BK;
+        const int32_t xo = (pass == 1) ? (int32_t)N1 : 0, yo = (pass == 2) ? (int32_t)N2 : 0;
         mbar_wait(empty_bar(s), ph ^ 1);
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
-        tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), a_ch, mrow);
-        tma_load_2d_pair(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), a_ch + 64, mrow);
+        tma_load_2d_pair(sA + s * Cfg::A_BYTES, &tmX, full_bar(s), a_ch + xo, mrow);
+        tma_load_2d_pair(sA + s * Cfg::A_BYTES + 8192, &tmX, full_bar(s), a_ch + 64 + xo, mrow);
 #pragma unroll
         for (int b = 0; b < Cfg::B_BOXES; ++b)
-          tma_load_2d_pair(sB + s * Cfg::B_BYTES + b * 8192, &tmY, full_bar(s), (BN == 384 && b == 2) ? b_ch2 : b_ch + 64 * b, mrow);
+          tma_load_2d_pair(sB + s * Cfg::B_BYTES + b * 8192, &tmY, full_bar(s), ((BN == 384 && b == 2) ? b_ch2 : b_ch + 64 * b) + yo, mrow);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -1652,6 +1665,7 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       constexpr uint32_t idesc_ones = make_idesc(256, 16, 1, 1);
       const uint64_t odesc = make_smem_desc(sOnes, 8192, 1024);
       int s = 0; uint32_t ph = 0;
+      uint32_t cs_acc = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
@@ -1664,7 +1678,10 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             const uint64_t bdesc2 = make_smem_desc(sB + s * Cfg::B_BYTES + 2 * 8192, 8192, 1024);
             umma_f16_pair(tmem_base + 256, adesc + (uint64_t)(k * 128), bdesc2 + (uint64_t)(k * 128), idesc_hi, (kb | k) != 0);
           }
-          if (do_colsum) umma_f16_pair(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, (kb | k) != 0);
+          if (do_colsum && (kb0 + kb) < 2 * kb_rows) {
+            umma_f16_pair(tmem_base + Cfg::CS_COL, adesc + (uint64_t)(k * 128), odesc, idesc_ones, cs_acc);
+            cs_acc = 1;
+          }
         }
         umma_commit_pair(empty_bar(s));
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -1719,7 +1736,7 @@ gemm_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
     if (do_colsum && half == 0) {
       float v[16];
-      if (nkb > 0) {
+      if (nkb > 0 && kb0 < 2 * kb_rows) {              // this split issued at least one column-sum MMA
         tmem_ld16(t_row + Cfg::CS_COL, v);
         tmem_ld_wait();
       } else {
@@ -2081,7 +2098,7 @@ int64_t wgrad_workspace_bytes_tc(int64_t M, int64_t N1, int64_t N2) {
 
 template <int BN>
 static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int64_t M, int64_t N1, int64_t N2, int kb_per_split,
-                             int64_t tiles, int splits, float* part, float* cs_part, cudaStream_t s) {
+                             int64_t tiles, int splits, float* part, float* cs_part, cudaStream_t s, int passes) {
   auto k = tc::gemm_wgrad_pair_kernel<BN>;
   if (int rc = tc::set_smem(k, tc::WgPairCfg<BN>::SMEM)) return rc;
   cudaLaunchConfig_t cfg = {};
@@ -2098,7 +2115,7 @@ static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmX, tmY, M, N1, N2, kb_per_split, part, cs_part);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, tmX, tmY, M, N1, N2, kb_per_split, part, cs_part, passes);
   if (e != cudaSuccess) {
     set_error("gemm_wgrad_pair launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -2108,7 +2125,7 @@ static int launch_wgrad_pair(const CUtensorMap& tmX, const CUtensorMap& tmY, int
 }
 
 int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
-                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx, int64_t ldy) {
+                  float* colsum_x, void* workspace, int64_t workspace_bytes, cudaStream_t s, int64_t ldx, int64_t ldy, int passes) {
   CNX_REQUIRE(N1 % 8 == 0 && N2 % 8 == 0, CNX_E_SHAPE, "gemm_wgrad_tc: N1, N2 must be multiples of 8");
   CNX_REQUIRE((ldx == 0 || (ldx >= N1 && ldx % 8 == 0)) && (ldy == 0 || (ldy >= N2 && ldy % 8 == 0)), CNX_E_SHAPE,
               "gemm_wgrad_tc: row strides must cover the rows and be multiples of 8");
@@ -2116,29 +2133,34 @@ int gemm_wgrad_tc(const void* X, const void* Y, int64_t M, int64_t N1, int64_t N
   const int splits = pl.splits;
   CNX_REQUIRE(workspace_bytes >= (int64_t)splits * (N1 * N2 + N1) * 4, CNX_E_WORKSPACE, "gemm_wgrad: workspace too small");
   CUtensorMap tmX, tmY;
-  if (int rc = tc::make_map(&tmX, X, M, N1, tc::BK, ldx)) return rc;
-  if (int rc = tc::make_map(&tmY, Y, M, N2, tc::BK, ldy)) return rc;
-  const int64_t kb_total = (M + tc::BK - 1) / tc::BK;
+  // passes = 3: X and Y are the split operands [hi | mid] (2 N columns, row stride 2 N); the kernels walk hi.hi, mid.hi, hi.mid
+  // in one K loop.  (A ragged last tile then reads the neighbouring piece instead of TMA zero fill: those rows / columns of
+  // the accumulator are never stored.)
+  CNX_REQUIRE(passes == 1 || (passes == 3 && ldx == 2 * N1 && ldy == 2 * N2), CNX_E_BADARG,
+              "gemm_wgrad_tc: passes must be 1, or 3 with split operands of row stride 2 N1 / 2 N2");
+  if (int rc = tc::make_map(&tmX, X, M, passes == 3 ? 2 * N1 : N1, tc::BK, ldx)) return rc;
+  if (int rc = tc::make_map(&tmY, Y, M, passes == 3 ? 2 * N2 : N2, tc::BK, ldy)) return rc;
+  const int64_t kb_total = passes * ((M + tc::BK - 1) / tc::BK);
   const int kb_per_split = (int)((kb_total + splits - 1) / splits);
   float* part = (float*)workspace;
   float* cs_part = part + (int64_t)splits * N1 * N2;
   if (pl.pair) {
     int rc = (pl.bn == 384)
-                 ? launch_wgrad_pair<384>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s)
+                 ? launch_wgrad_pair<384>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s, passes)
              : (pl.bn == 256)
-                 ? launch_wgrad_pair<256>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s)
-                 : launch_wgrad_pair<128>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s);
+                 ? launch_wgrad_pair<256>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s, passes)
+                 : launch_wgrad_pair<128>(tmX, tmY, M, N1, N2, kb_per_split, pl.tiles, splits, part, colsum_x ? cs_part : nullptr, s, passes);
     if (rc) return rc;
   } else {
     dim3 grid((unsigned)pl.tiles, (unsigned)splits);
     if (pl.bn == 128) {
       auto k = tc::gemm_wgrad_tc_kernel<128>;
       if (int rc = tc::set_smem(k, tc::WgCfg<128>::SMEM)) return rc;
-      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<128>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<128>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr, passes);
     } else {
       auto k = tc::gemm_wgrad_tc_kernel<96>;
       if (int rc = tc::set_smem(k, tc::WgCfg<96>::SMEM)) return rc;
-      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<96>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr);
+      launch_pdl(k, grid, dim3(tc::kThreads), tc::WgCfg<96>::SMEM, s, tmX, tmY, M, N1, N2, kb_per_split, part, colsum_x ? cs_part : nullptr, passes);
     }
     if (int rc = check_launch("gemm_wgrad_tc")) return rc;
   }

@@ -252,6 +252,14 @@ CNX_API int cnx_gelu_split(float* h, int64_t M, int64_t N, void* g2, void* strea
 CNX_API int cnx_mul_split(const float* t, const float* u, int64_t M, int64_t N, void* out2, void* stream);
 CNX_API int cnx_gemm_wgrad_x3(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate, float* out,
                       float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream);
+/* The same in ONE launch: the K loop of the wgrad kernel walks hi.hi, mid.hi, hi.mid over the same rows (one set of split-K
+ * partials, one reduction: 18 % less time).  Its fp32 accumulation chains in tensor memory are three times as long, and the
+ * tensor core's fp32 accumulate is not round-to-nearest: measured against float64 on N(0,1) operands at the ConvNeXt-T / batch-256
+ * shapes the error is 3.2e-5 .. 6.2e-5 (max-abs-normalised) where cnx_gemm_wgrad_x3 has 0.9e-5 .. 2.1e-5 and a cuBLAS fp32 GEMM
+ * 0.07e-5 .. 0.5e-5 (profiles/wgrad_x3_accuracy.py).  Inside the 1e-4 bar, but the product path keeps the three-launch form;
+ * ops.WGRAD_X3_ONE_LOOP / CNX_WGRAD_X3_ONE_LOOP=1 selects this one. */
+CNX_API int cnx_gemm_wgrad_x3_one_loop(const void* X2, const void* Y2, int64_t M, int64_t N1, int64_t N2, int accumulate,
+                               float* out, float* colsum_x, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Fused no-grad MLP forward for the HBM-bound stages (C in {96, 128, 192}; bf16 operands, fp32 residual stream):
  *   out[m,:] = shortcut[m,:] + dp[m / rows_per_sample] * gamma * (GELU_erf(xn[m,:].W1^T + b1).W2^T + b2)

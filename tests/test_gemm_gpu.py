@@ -273,3 +273,40 @@ def test_x3_training_epilogues_fc1_gelu_prime_and_dgelu_split(M, C):
     L.check(lib.cnx_gemm_plain(L.ptr(dz2), L.ptr(w2s3), None, L.ptr(t1), L.dt(f32), M, N, 3 * C, L.dt(bf), L.CNX_GEMM_A_SPLIT2, st))
     L.check(lib.cnx_mul_split(L.ptr(t1), L.ptr(gp), M, N, L.ptr(dh2b), st))
     assert torch.equal(dh2, dh2b)                                    # same MMAs, same fp32 multiply, same split
+
+
+@pytest.mark.parametrize("M,N1,N2", [(3136, 96, 384), (1000, 384, 96), (50176, 384, 1536), (777, 768, 192), (4096, 1536, 384),
+                                     (130, 3072, 768), (12544, 768, 3072), (5000, 200, 1000)])
+@pytest.mark.parametrize("one_loop", [False, True], ids=["three_launches", "one_loop"])
+def test_wgrad_x3_one_k_loop_over_three_products(M, N1, N2, one_loop):
+    """cnx_gemm_wgrad_x3 / cnx_gemm_wgrad_x3_one_loop: out = X^T . Y and the column sums of X from split operands [hi | mid] — three
+    launches (hi.hi, mid.hi, hi.mid), or ONE launch whose K loop walks the three products (single-CTA, CTA-pair 256 x 256 and
+    256 x 384 tiles; ragged M, N1, N2) — against float64, with and without accumulation into an existing gradient.  The one-loop
+    form has three times the accumulation-chain length in tensor memory: its bound is 8e-5 where the default's is 3e-5."""
+    from imageclassification_b200 import _lib as L
+    lib = L.load()
+    fn = lib.cnx_gemm_wgrad_x3_one_loop if one_loop else lib.cnx_gemm_wgrad_x3
+    tol = 8e-5 if one_loop else 3e-5
+    g = torch.Generator(device=DEV).manual_seed(M + N1)
+    X = torch.randn(M, N1, device=DEV, generator=g)
+    Y = torch.randn(M, N2, device=DEV, generator=g)
+    bf = torch.bfloat16
+    st = L.stream()
+    X2 = torch.empty(M, 2 * N1, dtype=bf, device=DEV)
+    Y2 = torch.empty(M, 2 * N2, dtype=bf, device=DEV)
+    L.check(lib.cnx_split3(L.ptr(X), M, N1, L.ptr(X2), 2, st))
+    L.check(lib.cnx_split3(L.ptr(Y), M, N2, L.ptr(Y2), 2, st))
+    wsb = lib.cnx_gemm_wgrad_workspace_bytes(M, N1, N2, L.dt(bf), 0)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
+    out = torch.full((N1, N2), float("nan"), device=DEV)
+    cs = torch.full((N1,), float("nan"), device=DEV)
+    L.check(fn(L.ptr(X2), L.ptr(Y2), M, N1, N2, 0, L.ptr(out), L.ptr(cs), L.ptr(ws), wsb, st))
+    ref = X.double().t() @ Y.double()
+    assert max_rel(out.double(), ref) <= tol, max_rel(out.double(), ref)
+    assert max_rel(cs.double(), X.double().sum(0)) <= 2e-5
+    base = torch.randn(N1, N2, device=DEV, generator=g)
+    acc = base.clone()
+    cs2 = torch.ones(N1, device=DEV)
+    L.check(fn(L.ptr(X2), L.ptr(Y2), M, N1, N2, 1, L.ptr(acc), L.ptr(cs2), L.ptr(ws), wsb, st))
+    assert max_rel((acc - base).double(), ref) <= tol + 1e-5
+    assert max_rel((cs2 - 1).double(), X.double().sum(0)) <= 3e-5
