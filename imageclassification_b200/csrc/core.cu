@@ -472,16 +472,20 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t j = (int64_t)blockIdx.x * 32 + tx;
-  float s0 = 0.f, s1 = 0.f;
+  // eight independent loads in flight per thread (the buffer is a few hundred rows of a few hundred columns, read from L2 by a
+  // handful of CTAs: with two in flight a launch took 12 us of pure latency); fixed association, so still deterministic
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (j < L) {
     int p = ty;
-    for (; p + 8 < P; p += 16) {
-      s0 += partial[(int64_t)p * L + j];
-      s1 += partial[(int64_t)(p + 8) * L + j];
+    for (; p + 56 < P; p += 64) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += partial[(int64_t)(p + 8 * u) * L + j];
     }
-    if (p < P) s0 += partial[(int64_t)p * L + j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (p + 8 * u < P) s[u] += partial[(int64_t)(p + 8 * u) * L + j];
   }
-  red[ty][tx] = s0 + s1;
+  red[ty][tx] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   if (ty == 0 && j < L) {
     float s = 0.f;
